@@ -1,0 +1,221 @@
+/*
+ * sfod_b200.h -- C ABI of libsfod_b200.so: the B200 (sm_100a) implementation of the
+ * simple-SFOD teacher-student pseudo-labelling hot path.
+ *
+ * The reference (EPFL-IMOS/simple-SFOD) is pure Python and has NO FFI of its own: its
+ * arithmetic is reached through detectron2 0.6 -> torchvision / ATen operators.  Every
+ * entry point below therefore cites the reference call site (file:line, relative to the
+ * reference root) whose native work it replaces, and the operator signature it mirrors.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; no torch / C++ types; `int` status return
+ *     (0 = SFOD_OK, otherwise an sfod_status value; >= 1000 encodes 1000 + cudaError_t);
+ *   - no exceptions, no logging, no global mutable state, re-entrant;
+ *   - every buffer is owned by the caller (inputs, outputs, workspace); workspace sizes
+ *     come from the matching *_workspace_bytes() query; all device pointers must be
+ *     valid on the current CUDA device; fp32 buffers must be 16-byte aligned unless noted;
+ *   - kernels are enqueued on `stream` and the call returns without synchronising;
+ *     variable-length results are returned as a device-side count plus a max-sized buffer;
+ *   - indices are int64 on the API (torch convention) unless noted.
+ */
+#ifndef SFOD_B200_H
+#define SFOD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *sfod_stream_t; /* identical to cudaStream_t */
+
+enum sfod_status {
+  SFOD_OK = 0,
+  SFOD_ERR_INVALID_ARG = 1,
+  SFOD_ERR_WORKSPACE_TOO_SMALL = 2,
+  SFOD_ERR_UNSUPPORTED = 3,
+  SFOD_ERR_ALIGNMENT = 4,
+  SFOD_ERR_CUDA_BASE = 1000
+};
+
+enum sfod_layout { SFOD_NCHW = 0, SFOD_NHWC = 1 };
+enum sfod_dtype { SFOD_F32 = 0, SFOD_I64 = 1 };
+
+int sfod_abi_version(void);
+const char *sfod_status_string(int status);
+
+/* ------------------------------------------------------------------------------------
+ * Mean-teacher EMA.  Replaces the per-tensor loop of
+ *   daod/engine/trainers/source_free_adaptive_teacher.py:593-603 (_update_teacher_model)
+ *   (same body: adaptive_teacher.py:339-358).
+ * teacher[i] = fp32(student[i] * fp32(1-k)) + fp32(teacher[i] * fp32(k)), two separately
+ * rounded products and one rounded sum (no FMA), written in place into the teacher tensor
+ * (what load_state_dict's copy_ does).  int64 tensors (BatchNorm num_batches_tracked) are
+ * promoted to fp32, blended, and truncated back, exactly like the reference.
+ * One launch covers every tensor of the state dict through a chunk table ("plan").
+ * The plan is built on the host from the tensor table and uploaded by the caller. */
+typedef struct sfod_ema_tensor {
+  const void *student; /* device pointer */
+  void *teacher;       /* device pointer, updated in place */
+  int64_t numel;
+  int32_t dtype; /* enum sfod_dtype */
+  int32_t reserved;
+} sfod_ema_tensor;
+
+int64_t sfod_ema_plan_chunks(const sfod_ema_tensor *tensors, int n_tensors);
+size_t sfod_ema_plan_bytes(int64_t n_chunks);
+int sfod_ema_plan_build(const sfod_ema_tensor *tensors, int n_tensors, void *host_plan, size_t host_plan_bytes);
+int sfod_ema_multi_tensor(const void *device_plan, int64_t n_chunks, double keep_rate, sfod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * ROIAlign / ROIPool, forward and backward.  Replace torchvision.ops.roi_align / roi_pool
+ * as reached from d2 ROIPooler, built at
+ *   daod/modeling/roi_heads/source_free_adaptive_teacher_roi_heads.py:42-47, called :117
+ * (pooler_type "ROIAlignV2" -> aligned=1, "ROIAlign" -> aligned=0, "ROIPool" -> roi_pool).
+ * input (N,C,H,W) fp32 in `layout`; rois (R,5) = [batch_index, x1, y1, x2, y2];
+ * output (R,C,PH,PW) contiguous (torchvision layout).  `exact` != 0 selects the kernel that
+ * reproduces torchvision's per-sample summation order bit for bit (NCHW gather); exact == 0
+ * selects the separable channels-last kernel (<= 1e-5 relative). */
+size_t sfod_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int layout, int exact);
+int sfod_roi_align_fwd(const float *input, int layout, const float *rois, int N, int C, int H, int W, int R, int PH,
+                       int PW, float spatial_scale, int sampling_ratio, int aligned, int exact, float *output,
+                       void *workspace, size_t workspace_bytes, sfod_stream_t stream);
+/* grad_in (N,C,H,W) in `layout` is fully overwritten (zero-filled then accumulated). */
+size_t sfod_roi_align_bwd_workspace_bytes(int N, int C, int H, int W, int layout);
+int sfod_roi_align_bwd(const float *grad_out, const float *rois, int N, int C, int H, int W, int R, int PH, int PW,
+                       float spatial_scale, int sampling_ratio, int aligned, float *grad_in, int layout,
+                       void *workspace, size_t workspace_bytes, sfod_stream_t stream);
+int sfod_roi_pool_fwd(const float *input, const float *rois, int N, int C, int H, int W, int R, int PH, int PW,
+                      float spatial_scale, float *output, int32_t *argmax, sfod_stream_t stream);
+int sfod_roi_pool_bwd(const float *grad_out, const float *rois, const int32_t *argmax, int N, int C, int H, int W,
+                      int R, int PH, int PW, float *grad_in, sfod_stream_t stream);
+/* layout helpers used by the wrappers (tiled shared-memory transposes) */
+int sfod_nchw_to_nhwc(const float *src, float *dst, int N, int C, int HW, sfod_stream_t stream);
+int sfod_nhwc_to_nchw(const float *src, float *dst, int N, int C, int HW, sfod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * NMS with torchvision semantics.  Replaces torchvision.ops.nms / batched_nms as reached
+ * from d2 find_top_rpn_proposals (called by daod/modeling/proposal_generator/rpn.py:54-56)
+ * and from daod/modeling/roi_heads/fast_rcnn.py:133.
+ * boxes (n,4) xyxy fp32, scores (n) fp32, idxs (n) int64 or NULL (plain nms).
+ * keep_out (n) int64 receives the kept indices in score-descending order (ties: lower
+ * index first = torchvision CPU's stable sort); *num_keep_dev (device int64) the count.
+ * IoU arithmetic: inter / (area_i + area_j - inter) in separately rounded fp32, suppress
+ * iff (double)iou > iou_threshold.  With idxs != NULL and n <= coord_trick_max_n the boxes
+ * are first offset by idx * (max_coordinate + 1) in fp32, reproducing torchvision's
+ * _batched_nms_coordinate_trick rounding (CPU switches strategy at numel > 4000, i.e.
+ * coord_trick_max_n = 1000); above it suppression is per class on the raw boxes
+ * (_batched_nms_vanilla). */
+size_t sfod_nms_workspace_bytes(int64_t n);
+int sfod_nms(const float *boxes, const float *scores, const int64_t *idxs, int64_t n, double iou_threshold,
+             int64_t coord_trick_max_n, int64_t *keep_out, int64_t *num_keep_dev, void *workspace,
+             size_t workspace_bytes, sfod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * RPN proposal selection for one feature level (every shipped config is single-level).
+ * Replaces d2 RPN.predict_proposals = _decode_proposals + find_top_rpn_proposals as called
+ * at daod/modeling/proposal_generator/rpn.py:54-56, for all N images in one call:
+ *   per image: stable descending sort of the HWA logits, keep top pre_nms_topk;
+ *   decode anchor (+) delta (Box2BoxTransform weights, dw/dh clamp), fp32 ops in d2's order;
+ *   drop non-finite (counted in invalid_count_dev; d2 raises in training), clip to (h,w),
+ *   drop boxes with w <= min_box_size or h <= min_box_size; greedy NMS (iou_threshold);
+ *   first post_nms_topk survivors.
+ * logits (N,HWA) and deltas (N,HWA,4) are the flattened head outputs of rpn.py:28-41.
+ * anchors: (HWA,4) device tensor, or NULL to recompute d2's DefaultAnchorGenerator grid in
+ * closed form from cell_anchors (A,4) host floats, feature size (Hf,Wf), stride and offset.
+ * image_hw_dev: (N,2) int32 device [h, w].
+ * Outputs: out_boxes (N,post_nms_topk,4), out_logits (N,post_nms_topk), out_src_index
+ * (N,post_nms_topk) int64 flat anchor index of each proposal, out_count_dev (N) int32. */
+typedef struct sfod_rpn_params {
+  int N, HWA, A, Hf, Wf, stride;
+  float anchor_offset;
+  float weights[4];
+  float scale_clamp;
+  int pre_nms_topk, post_nms_topk;
+  float min_box_size;
+  double nms_thresh;
+  float cell_anchors[64 * 4]; /* up to 64 cell anchors, used when anchors == NULL */
+} sfod_rpn_params;
+
+size_t sfod_rpn_select_workspace_bytes(const sfod_rpn_params *p);
+int sfod_rpn_select(const sfod_rpn_params *p, const float *logits, const float *deltas, const float *anchors,
+                    const int32_t *image_hw_dev, float *out_boxes, float *out_logits, int64_t *out_src_index,
+                    int32_t *out_count_dev, int32_t *invalid_count_dev, void *workspace, size_t workspace_bytes,
+                    sfod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fast R-CNN post-processing + pseudo-label filter for all N images in one call.
+ * Replaces FastRCNNOutputLayers.inference (called at
+ * daod/modeling/roi_heads/source_free_adaptive_teacher_roi_heads.py:161) =
+ * predict_boxes + predict_probs + fast_rcnn_inference_single_image
+ * (on-disk statement: daod/modeling/roi_heads/fast_rcnn.py:108-142), followed by
+ * threshold_bbox(proposal_type="roih") of
+ * daod/engine/trainers/source_free_adaptive_teacher.py:167-181.
+ * cls_logits (R,K+1), deltas (R,4K) (or (R,4) when class_agnostic), proposals (R,4);
+ * rows of image i are [row_offsets_dev[i], row_offsets_dev[i+1]) (int32, N+1 entries).
+ * mode 0: inference (score > score_thresh, per-class NMS, top-k);
+ * Outputs per image, padded to topk: det_boxes (N,topk,4), det_scores (N,topk),
+ * det_classes (N,topk) int64, det_rows (N,topk) int64 (row within the image),
+ * det_count_dev (N) int32, pseudo_count_dev (N) int32 = #detections with score >
+ * pseudo_thresh (detections are score-descending, so the pseudo-label set is that prefix).
+ * probs_out (R,K+1) optional (may be NULL) receives the softmax probabilities;
+ * boxes_out (R,4K) optional receives the decoded (unclipped) boxes (predict_boxes). */
+typedef struct sfod_frcnn_params {
+  int N, R, K;
+  int class_agnostic;
+  int max_rows_per_image;
+  float weights[4];
+  float scale_clamp;
+  float score_thresh;
+  double nms_thresh;
+  int topk;
+  float pseudo_thresh;
+  int64_t coord_trick_max_n; /* 1000 reproduces torchvision-CPU's strategy switch */
+} sfod_frcnn_params;
+
+size_t sfod_frcnn_postprocess_workspace_bytes(const sfod_frcnn_params *p);
+int sfod_frcnn_postprocess(const sfod_frcnn_params *p, const float *cls_logits, const float *deltas,
+                           const float *proposals, const int32_t *row_offsets_dev, const int32_t *image_hw_dev,
+                           float *det_boxes, float *det_scores, int64_t *det_classes, int64_t *det_rows,
+                           int32_t *det_count_dev, int32_t *pseudo_count_dev, float *probs_out, float *boxes_out,
+                           void *workspace, size_t workspace_bytes, sfod_stream_t stream);
+
+/* Box2BoxTransform.apply_deltas (d2 box_regression) and softmax as separate
+ * operators: deltas (R,4k), boxes (R,4) -> out (R,4k).  Used by predict_boxes /
+ * convert_bbox_scores (daod/modeling/roi_heads/source_free_fast_rcnn.py:15-17). */
+int sfod_apply_deltas(const float *deltas, const float *boxes, int64_t R, int k, const float *weights4_host,
+                      float scale_clamp, float *out, sfod_stream_t stream);
+int sfod_softmax_lastdim(const float *x, int64_t R, int K1, float *out, sfod_stream_t stream);
+
+/* Generic confidence filter: threshold_bbox (source_free_adaptive_teacher.py:150-183).
+ * For S segments laid out with fixed stride: values (S,stride), counts_dev (S) int32 valid
+ * entries; writes the indices (ascending) of entries with value > thres to out_index
+ * (S,stride) int64 and their number to out_count_dev (S) int32. */
+int sfod_threshold_select(const float *values, const int32_t *counts_dev, int S, int stride, float thres,
+                          int64_t *out_index, int32_t *out_count_dev, sfod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * BatchNorm train-mode forward / AdaBN statistic recomputation.  Replaces the
+ * nn.BatchNorm2d train-mode forwards driven by test_refinement
+ * (daod/engine/trainers/base.py:274-299, after reset_bn_stats :318-323) and by the teacher
+ * forward under no_grad (source_free_adaptive_teacher.py:385-390).
+ * Phase 1 (sfod_bn_partial_stats): per-channel (sum x, sum x^2) over (N,H,W) accumulated
+ *   in fp64 into stats_dev (C,2) doubles (zeroed by the call) -- the tensor a multi-GPU
+ *   caller all-reduces (together with the element count) before phase 2.
+ * Phase 2 (sfod_bn_finalize_apply): mean, biased var (fp64), running stats
+ *   r = (1-m) r + m stat with the unbiased variance n/(n-1), num_batches_tracked += 1,
+ *   y = (x-mean)*invstd*weight+bias (optionally fused ReLU); y may alias x. */
+size_t sfod_bn_stats_bytes(int C);
+int sfod_bn_partial_stats(const float *x, int layout, int N, int C, int64_t HW, double *stats_dev,
+                          sfod_stream_t stream);
+int sfod_bn_finalize_apply(const float *x, float *y, int layout, int N, int C, int64_t HW, const double *stats_dev,
+                           double total_count, const float *weight, const float *bias, float *running_mean,
+                           float *running_var, int64_t *num_batches_tracked, double momentum, double eps,
+                           int fuse_relu, float *save_mean, float *save_invstd, sfod_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFOD_B200_H */

@@ -1,0 +1,295 @@
+// bn.cu -- BatchNorm train-mode forward split for AdaBN statistic recomputation.
+// Replaces the nn.BatchNorm2d train-mode forwards that reference daod/engine/trainers/base.py:274-299
+// (test_refinement, after reset_bn_stats :318-323) and the no_grad teacher forward
+// (source_free_adaptive_teacher.py:385-390) run only for their running-statistic side effect.
+//
+// HBM-bound: the statistics pass reads x once (4 B/element, SURVEY.md 8d: 777 MB per VGG image), the
+// apply pass reads x and writes y (8 B/element).  Accuracy contract (1e-5 relative vs ATen's fp64
+// accumulation): every thread accumulates at most 64 pivot-shifted elements in fp32, everything above
+// that (warp, block, grid, and the E[x^2]-E[x]^2 combination) is fp64.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kChunk = 16384;  // elements of one (n, c) plane per CTA: 64 per thread
+
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+// Adds the CTA's (count m, shifted sums about pivot K) to the unshifted fp64 channel totals.
+__device__ __forceinline__ void flush_channel(double *stats, int c, double sd, double sd2, double m, double K) {
+  // sum x = sd + m K ; sum x^2 = sd2 + 2 K sd + m K^2
+  atomicAdd(stats + 2 * c, sd + m * K);
+  atomicAdd(stats + 2 * c + 1, sd2 + 2.0 * K * sd + m * K * K);
+}
+
+__global__ void __launch_bounds__(kThreads) bn_stats_nchw_kernel(const float *__restrict__ x, int C, long long HW,
+                                                                 double *__restrict__ stats) {
+  __shared__ double red[2][kThreads / 32];
+  const int plane = blockIdx.y;          // n * C + c
+  const int c = plane % C;
+  const long long start = (long long)blockIdx.x * kChunk;
+  const long long len = min((long long)kChunk, HW - start);
+  if (len <= 0) return;
+  const float *p = x + (size_t)plane * HW + start;
+  const float K = x[(size_t)c * HW];     // pivot: first element of the channel in image 0
+  float s = 0.f, s2 = 0.f;
+  // peel to 16-byte alignment, then 128-bit loads
+  const int mis = (int)((reinterpret_cast<uintptr_t>(p) >> 2) & 3);
+  const int head = mis ? min((long long)(4 - mis), len) : 0;
+  if (threadIdx.x < head) { const float d = p[threadIdx.x] - K; s += d; s2 = fmaf(d, d, s2); }
+  const float4 *p4 = reinterpret_cast<const float4 *>(p + head);
+  const int n4 = (int)((len - head) >> 2);
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n4; i += kThreads) {
+    const float4 v = __ldg(p4 + i);
+    const float d0 = v.x - K, d1 = v.y - K, d2 = v.z - K, d3 = v.w - K;
+    s += (d0 + d1) + (d2 + d3);
+    s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+  }
+  const int tail0 = head + (n4 << 2);
+  if (tail0 + (int)threadIdx.x < len) { const float d = p[tail0 + threadIdx.x] - K; s += d; s2 = fmaf(d, d, s2); }
+  double ds = warp_sum((double)s), ds2 = warp_sum((double)s2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = ds; red[1][warp] = ds2; }
+  __syncthreads();
+  if (warp == 0) {
+    ds = lane < kThreads / 32 ? red[0][lane] : 0.0;
+    ds2 = lane < kThreads / 32 ? red[1][lane] : 0.0;
+    ds = warp_sum(ds); ds2 = warp_sum(ds2);
+    if (lane == 0) flush_channel(stats, c, ds, ds2, (double)len, (double)K);
+  }
+}
+
+// NHWC: x viewed as (M = N*HW rows, C columns).  A CTA covers `cols` float4 column groups x `rowlanes`
+// row lanes; each thread walks up to 64 rows with 128-bit loads (4 channels per load).
+__global__ void __launch_bounds__(kThreads) bn_stats_nhwc_kernel(const float *__restrict__ x, long long M, int C, int cols,
+                                                                 int rowlanes, double *__restrict__ stats) {
+  extern __shared__ double sred[];  // rowlanes * cols * 8 doubles
+  const int G = C >> 2;
+  const int col = threadIdx.x % cols, rl = threadIdx.x / cols;
+  const int g = blockIdx.y * cols + col;
+  const long long row0 = (long long)blockIdx.x * rowlanes * 64;
+  const bool on = rl < rowlanes && g < G;
+  float4 K = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 s = K, s2 = K;
+  int cnt = 0;
+  if (on) {
+    K = __ldg(reinterpret_cast<const float4 *>(x) + g);  // pivot: row 0
+    const float4 *p = reinterpret_cast<const float4 *>(x) + g;
+#pragma unroll 4
+    for (int i = 0; i < 64; ++i) {
+      const long long r = row0 + (long long)i * rowlanes + rl;
+      if (r < M) {
+        const float4 v = __ldg(p + (size_t)r * G);
+        const float d0 = v.x - K.x, d1 = v.y - K.y, d2 = v.z - K.z, d3 = v.w - K.w;
+        s.x += d0; s.y += d1; s.z += d2; s.w += d3;
+        s2.x = fmaf(d0, d0, s2.x); s2.y = fmaf(d1, d1, s2.y); s2.z = fmaf(d2, d2, s2.z); s2.w = fmaf(d3, d3, s2.w);
+        ++cnt;
+      }
+    }
+  }
+  double *mine = sred + ((size_t)rl * cols + col) * 9;
+  if (rl < rowlanes) {
+    mine[0] = s.x; mine[1] = s.y; mine[2] = s.z; mine[3] = s.w;
+    mine[4] = s2.x; mine[5] = s2.y; mine[6] = s2.z; mine[7] = s2.w; mine[8] = (double)cnt;
+  }
+  __syncthreads();
+  if (rl == 0 && g < G) {
+    double a[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a[k] = 0.0;
+    for (int q = 0; q < rowlanes; ++q) {
+      const double *o = sred + ((size_t)q * cols + col) * 9;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a[k] += o[k];
+    }
+    const double Kd[4] = {(double)K.x, (double)K.y, (double)K.z, (double)K.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) flush_channel(stats, 4 * g + k, a[k], a[4 + k], a[8], Kd[k]);
+  }
+}
+
+// scalar fallback for NHWC with C % 4 != 0 (not used by any shipped config)
+__global__ void __launch_bounds__(kThreads) bn_stats_nhwc_scalar_kernel(const float *__restrict__ x, long long M, int C,
+                                                                        double *__restrict__ stats) {
+  const int c = blockIdx.x;
+  double s = 0.0, s2 = 0.0;
+  for (long long r = threadIdx.x; r < M; r += kThreads) { const double v = x[(size_t)r * C + c]; s += v; s2 += v * v; }
+  __shared__ double red[2][kThreads / 32];
+  s = warp_sum(s); s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) { s += red[0][w]; s2 += red[1][w]; }
+    stats[2 * c] += s; stats[2 * c + 1] += s2;
+  }
+}
+
+// One thread per channel: ATen batch_norm_cpu_update_stats arithmetic in fp64.
+__global__ void bn_finalize_kernel(const double *__restrict__ stats, int C, double n, const float *__restrict__ weight,
+                                   const float *__restrict__ bias, float *__restrict__ running_mean,
+                                   float *__restrict__ running_var, long long *__restrict__ nbt, double momentum, double eps,
+                                   float *__restrict__ save_mean, float *__restrict__ save_invstd, float *__restrict__ scale,
+                                   float *__restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  const double mean = stats[2 * c] / n;
+  double var = stats[2 * c + 1] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double invstd = 1.0 / sqrt(var + eps);
+  const float mean_f = (float)mean;
+  if (save_mean) save_mean[c] = mean_f;
+  if (save_invstd) save_invstd[c] = (float)invstd;
+  if (running_mean) running_mean[c] = (float)(momentum * (double)mean_f + (1.0 - momentum) * (double)running_mean[c]);
+  if (running_var) {
+    const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+    running_var[c] = (float)(momentum * unbiased + (1.0 - momentum) * (double)running_var[c]);
+  }
+  const double w = weight ? (double)weight[c] : 1.0, b = bias ? (double)bias[c] : 0.0;
+  scale[c] = (float)(w * invstd);
+  shift[c] = (float)(b - mean * w * invstd);
+}
+
+template <bool kRelu>
+__device__ __forceinline__ float bn1(float v, float sc, float sh) {
+  const float y = fmaf(v, sc, sh);
+  return kRelu ? fmaxf(y, 0.f) : y;
+}
+
+template <bool kRelu>
+__global__ void __launch_bounds__(kThreads) bn_apply_nchw_kernel(const float *__restrict__ x, float *__restrict__ y, int C,
+                                                                 long long HW, const float *__restrict__ scale,
+                                                                 const float *__restrict__ shift) {
+  const int plane = blockIdx.y;
+  const int c = plane % C;
+  const long long start = (long long)blockIdx.x * kChunk;
+  const long long len = min((long long)kChunk, HW - start);
+  if (len <= 0) return;
+  const float sc = scale[c], sh = shift[c];
+  const float *p = x + (size_t)plane * HW + start;
+  float *q = y + (size_t)plane * HW + start;
+  const int mis = (int)((reinterpret_cast<uintptr_t>(p) >> 2) & 3);
+  const int head = mis ? min((long long)(4 - mis), len) : 0;
+  if (threadIdx.x < head) q[threadIdx.x] = bn1<kRelu>(p[threadIdx.x], sc, sh);
+  const float4 *p4 = reinterpret_cast<const float4 *>(p + head);
+  float4 *q4 = reinterpret_cast<float4 *>(q + head);
+  const int n4 = (int)((len - head) >> 2);
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n4; i += kThreads) {
+    const float4 v = p4[i];
+    q4[i] = make_float4(bn1<kRelu>(v.x, sc, sh), bn1<kRelu>(v.y, sc, sh), bn1<kRelu>(v.z, sc, sh), bn1<kRelu>(v.w, sc, sh));
+  }
+  const int tail0 = head + (n4 << 2);
+  if (tail0 + (int)threadIdx.x < len) q[tail0 + threadIdx.x] = bn1<kRelu>(p[tail0 + threadIdx.x], sc, sh);
+}
+
+template <bool kRelu>
+__global__ void __launch_bounds__(kThreads) bn_apply_nhwc_kernel(const float *__restrict__ x, float *__restrict__ y, long long total4,
+                                                                 int G, const float *__restrict__ scale,
+                                                                 const float *__restrict__ shift) {
+  const float4 *x4 = reinterpret_cast<const float4 *>(x);
+  float4 *y4 = reinterpret_cast<float4 *>(y);
+  const float4 *sc4 = reinterpret_cast<const float4 *>(scale), *sh4 = reinterpret_cast<const float4 *>(shift);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total4; i += (long long)gridDim.x * kThreads) {
+    const int g = (int)(i % G);
+    const float4 v = x4[i], sc = __ldg(sc4 + g), sh = __ldg(sh4 + g);
+    y4[i] = make_float4(bn1<kRelu>(v.x, sc.x, sh.x), bn1<kRelu>(v.y, sc.y, sh.y), bn1<kRelu>(v.z, sc.z, sh.z),
+                        bn1<kRelu>(v.w, sc.w, sh.w));
+  }
+}
+
+template <bool kRelu>
+__global__ void __launch_bounds__(kThreads) bn_apply_nhwc_scalar_kernel(const float *__restrict__ x, float *__restrict__ y,
+                                                                        long long total, int C, const float *__restrict__ scale,
+                                                                        const float *__restrict__ shift) {
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int c = (int)(i % C);
+    y[i] = bn1<kRelu>(x[i], scale[c], shift[c]);
+  }
+}
+
+}  // namespace
+
+SFOD_API size_t sfod_bn_stats_bytes(int C) { return C > 0 ? sfod_align_up((size_t)C * 4 * sizeof(double), 256) : 256; }
+// stats_dev layout: [0, 2C) doubles = (sum x, sum x^2) per channel (the all-reduce payload);
+// [2C, 4C) reused by phase 2 as float scale/shift scratch.
+
+SFOD_API int sfod_bn_partial_stats(const float *x, int layout, int N, int C, int64_t HW, double *stats_dev, sfod_stream_t stream) {
+  if (!x || !stats_dev || N <= 0 || C <= 0 || HW <= 0) return SFOD_ERR_INVALID_ARG;
+  if (layout != SFOD_NCHW && layout != SFOD_NHWC) return SFOD_ERR_INVALID_ARG;
+  cudaStream_t st = sfod_cu(stream);
+  SFOD_CUDA_TRY(cudaMemsetAsync(stats_dev, 0, (size_t)C * 2 * sizeof(double), st));
+  if (layout == SFOD_NCHW) {
+    const long long planes = (long long)N * C;
+    const long long step = 65535 / C * (long long)C;  // grid.y limit; multiples of C keep channel = plane % C
+    if (step == 0) return SFOD_ERR_UNSUPPORTED;
+    for (long long p0 = 0; p0 < planes; p0 += step) {
+      const long long np = planes - p0 < step ? planes - p0 : step;
+      dim3 grid((unsigned)((HW + kChunk - 1) / kChunk), (unsigned)np);
+      bn_stats_nchw_kernel<<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, C, HW, stats_dev);
+      SFOD_LAUNCH_CHECK();
+    }
+    return SFOD_OK;
+  }
+  const long long M = (long long)N * HW;
+  if ((C & 3) || !sfod_aligned16(x)) {
+    bn_stats_nhwc_scalar_kernel<<<C, kThreads, 0, st>>>(x, M, C, stats_dev);
+    SFOD_LAUNCH_CHECK();
+    return SFOD_OK;
+  }
+  const int G = C >> 2;
+  const int cols = G < 64 ? G : 64;
+  const int rowlanes = kThreads / cols;
+  dim3 grid((unsigned)((M + (long long)rowlanes * 64 - 1) / ((long long)rowlanes * 64)), (unsigned)((G + cols - 1) / cols));
+  const size_t smem = (size_t)rowlanes * cols * 9 * sizeof(double);
+  bn_stats_nhwc_kernel<<<grid, kThreads, smem, st>>>(x, M, C, cols, rowlanes, stats_dev);
+  SFOD_LAUNCH_CHECK();
+  return SFOD_OK;
+}
+
+SFOD_API int sfod_bn_finalize_apply(const float *x, float *y, int layout, int N, int C, int64_t HW, const double *stats_dev,
+                                    double total_count, const float *weight, const float *bias, float *running_mean,
+                                    float *running_var, int64_t *num_batches_tracked, double momentum, double eps, int fuse_relu,
+                                    float *save_mean, float *save_invstd, sfod_stream_t stream) {
+  if (!stats_dev || N <= 0 || C <= 0 || HW <= 0 || total_count <= 0) return SFOD_ERR_INVALID_ARG;
+  if (layout != SFOD_NCHW && layout != SFOD_NHWC) return SFOD_ERR_INVALID_ARG;
+  cudaStream_t st = sfod_cu(stream);
+  float *scale = reinterpret_cast<float *>(const_cast<double *>(stats_dev) + 2 * (size_t)C);
+  float *shift = scale + sfod_align_up((size_t)C, 4);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_dev, C, total_count, weight, bias, running_mean, running_var,
+                                                      reinterpret_cast<long long *>(num_batches_tracked), momentum, eps,
+                                                      save_mean, save_invstd, scale, shift);
+  SFOD_LAUNCH_CHECK();
+  if (!x || !y) return SFOD_OK;  // statistics-only mode (AdaBN does not need the normalised output of the last layer)
+  if (layout == SFOD_NCHW) {
+    const long long planes = (long long)N * C;
+    const long long step = 65535 / C * (long long)C;
+    if (step == 0) return SFOD_ERR_UNSUPPORTED;
+    for (long long p0 = 0; p0 < planes; p0 += step) {
+      const long long np = planes - p0 < step ? planes - p0 : step;
+      dim3 grid((unsigned)((HW + kChunk - 1) / kChunk), (unsigned)np);
+      if (fuse_relu) bn_apply_nchw_kernel<true><<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, y + (size_t)p0 * HW, C, HW, scale, shift);
+      else bn_apply_nchw_kernel<false><<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, y + (size_t)p0 * HW, C, HW, scale, shift);
+      SFOD_LAUNCH_CHECK();
+    }
+    return SFOD_OK;
+  }
+  const long long total = (long long)N * HW * C;
+  if ((C & 3) || !sfod_aligned16(x) || !sfod_aligned16(y)) {
+    const unsigned grid = (unsigned)min((long long)SFOD_NUM_SMS * 8, (total + kThreads - 1) / kThreads);
+    if (fuse_relu) bn_apply_nhwc_scalar_kernel<true><<<grid, kThreads, 0, st>>>(x, y, total, C, scale, shift);
+    else bn_apply_nhwc_scalar_kernel<false><<<grid, kThreads, 0, st>>>(x, y, total, C, scale, shift);
+  } else {
+    const long long total4 = total >> 2;
+    const unsigned grid = (unsigned)min((long long)SFOD_NUM_SMS * 16, (total4 + kThreads - 1) / kThreads);
+    if (fuse_relu) bn_apply_nhwc_kernel<true><<<grid, kThreads, 0, st>>>(x, y, total4, C >> 2, scale, shift);
+    else bn_apply_nhwc_kernel<false><<<grid, kThreads, 0, st>>>(x, y, total4, C >> 2, scale, shift);
+  }
+  SFOD_LAUNCH_CHECK();
+  return SFOD_OK;
+}

@@ -1,0 +1,477 @@
+"""Torch-facing operators of the B200 hot path: thin wrappers that hand raw device pointers of torch
+tensors (device memory + streams are the only thing torch provides here) to libsfod_b200.so.
+
+Signatures follow the operators the reference reaches through detectron2/torchvision:
+``nms`` / ``batched_nms`` / ``roi_align`` / ``roi_pool`` have torchvision's signatures
+(torchvision/ops/boxes.py:20,51 and roi_align.py:204); the fused entry points (``rpn_select``,
+``frcnn_postprocess``) replace whole per-image Python loops of detectron2.
+Every function requires CUDA tensors and raises if the native library is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import EmaTensor, FrcnnParams, RpnParams, check
+
+NCHW, NHWC = 0, 1
+SCALE_CLAMP = math.log(1000.0 / 16)
+COORD_TRICK_MAX_N = 1000  # torchvision CPU switches batched_nms strategy at boxes.numel() > 4000
+
+_ws_cache: Dict[Tuple[str, int], Tensor] = {}
+_small_cache: Dict[Tuple, Tensor] = {}
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _require_cuda(*ts: Tensor) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("sfod_b200 operators run on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("all tensors must be on the same CUDA device")
+    assert dev is not None
+    return dev
+
+
+def _workspace(dev: torch.device, tag: str, nbytes: int) -> Tensor:
+    """Grow-only per-(device, tag) workspace; stream-ordered reuse is safe because every user of a tag
+    enqueues on the current stream."""
+    key = (tag, dev.index if dev.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _small_i32(dev: torch.device, values: Sequence[int]) -> Tensor:
+    key = (dev.index, tuple(int(v) for v in values))
+    t = _small_cache.get(key)
+    if t is None:
+        if len(_small_cache) > 4096:
+            _small_cache.clear()
+        t = torch.tensor(list(key[1]), dtype=torch.int32, device=dev)
+        _small_cache[key] = t
+    return t
+
+
+def _f32c(t: Tensor) -> Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- NMS
+def _nms_impl(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_threshold: float) -> Tensor:
+    dev = _require_cuda(boxes, scores, idxs)
+    if boxes.dim() != 2 or boxes.shape[1] != 4:
+        raise ValueError(f"boxes should be a 2d tensor of shape [N, 4], got {tuple(boxes.shape)}")
+    if scores.dim() != 1 or scores.shape[0] != boxes.shape[0]:
+        raise ValueError("boxes and scores should have same number of elements in dimension 0, got "
+                         f"{boxes.shape[0]} and {scores.shape[0]}")
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=dev)
+    b, s = _f32c(boxes), _f32c(scores)
+    ix = None
+    if idxs is not None:
+        if idxs.shape[0] != n:
+            raise ValueError("idxs must have one entry per box")
+        ix = idxs.detach().to(torch.int64).contiguous()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, "nms", L.sfod_nms_workspace_bytes(n))
+        keep = torch.empty((n,), dtype=torch.int64, device=dev)
+        cnt = torch.empty((1,), dtype=torch.int64, device=dev)
+        check(L.sfod_nms(b.data_ptr(), s.data_ptr(), ix.data_ptr() if ix is not None else None, n, float(iou_threshold),
+                         COORD_TRICK_MAX_N, keep.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)), "sfod_nms")
+        k = int(cnt.item())  # variable-length result: one D2H read, as in torchvision's own CUDA nms
+    return keep[:k]
+
+
+def nms(boxes: Tensor, scores: Tensor, iou_threshold: float) -> Tensor:
+    """torchvision.ops.nms(boxes, scores, iou_threshold) -> int64 indices, score-descending."""
+    return _nms_impl(boxes, scores, None, iou_threshold)
+
+
+def batched_nms(boxes: Tensor, scores: Tensor, idxs: Tensor, iou_threshold: float) -> Tensor:
+    """torchvision.ops.batched_nms / detectron2.layers.batched_nms (boxes are cast to fp32 as d2 does)."""
+    return _nms_impl(boxes, scores, idxs, iou_threshold)
+
+
+# ----------------------------------------------------------------------------------------------- ROI pooling
+def _layout_of(x: Tensor) -> Tuple[Tensor, int]:
+    """Returns (tensor whose storage is dense in the reported layout, layout)."""
+    if x.dim() != 4:
+        raise ValueError("input must be a 4-d (N, C, H, W) tensor")
+    if x.is_contiguous():
+        return x, NCHW
+    if x.is_contiguous(memory_format=torch.channels_last):
+        return x, NHWC
+    return x.contiguous(), NCHW
+
+
+def convert_boxes_to_roi_format(boxes: List[Tensor]) -> Tensor:
+    """torchvision.ops._utils.convert_boxes_to_roi_format / d2 convert_boxes_to_pooler_format."""
+    if len(boxes) == 0:
+        raise ValueError("empty box list")
+    parts = [torch.cat([torch.full((len(b), 1), i, dtype=b.dtype, device=b.device), b], dim=1) for i, b in enumerate(boxes)]
+    return torch.cat(parts, dim=0)
+
+
+def _check_rois(boxes: Union[Tensor, List[Tensor]]) -> Tensor:
+    if isinstance(boxes, (list, tuple)):
+        for b in boxes:
+            if b.dim() != 2 or b.shape[1] != 4:
+                raise ValueError("Expected Tensor[L, 4] in the box list")
+        return convert_boxes_to_roi_format(list(boxes))
+    if boxes.dim() != 2 or boxes.shape[1] != 5:
+        raise ValueError("Expected Tensor[K, 5] rois: (batch_index, x1, y1, x2, y2)")
+    return boxes
+
+
+def _pair(v) -> Tuple[int, int]:
+    return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
+class _RoIAlignFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, rois: Tensor, ph: int, pw: int, scale: float, sr: int, aligned: bool, exact: bool):
+        dev = _require_cuda(x, rois)
+        xin, layout = _layout_of(x.detach().to(torch.float32))
+        r = _f32c(rois)
+        N, Cc, H, W = xin.shape
+        R = r.shape[0]
+        out = torch.empty((R, Cc, ph, pw), dtype=torch.float32, device=dev)
+        L = _lib.lib()
+        if R > 0:
+            with torch.cuda.device(dev):
+                ws = _workspace(dev, "roi", L.sfod_roi_align_fwd_workspace_bytes(N, Cc, H, W, layout, int(exact)))
+                check(L.sfod_roi_align_fwd(xin.data_ptr(), layout, r.data_ptr(), N, Cc, H, W, R, ph, pw, float(scale), int(sr),
+                                           int(aligned), int(exact), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
+                      "sfod_roi_align_fwd")
+        ctx.save_for_backward(r)
+        ctx.meta = (N, Cc, H, W, ph, pw, float(scale), int(sr), int(aligned), layout, x.dtype)
+        return out.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        (r,) = ctx.saved_tensors
+        N, Cc, H, W, ph, pw, scale, sr, aligned, layout, dtype = ctx.meta
+        dev = grad_out.device
+        g = _f32c(grad_out)
+        fmt = torch.channels_last if layout == NHWC else torch.contiguous_format
+        gin = torch.empty((N, Cc, H, W), dtype=torch.float32, device=dev, memory_format=fmt)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            ws = _workspace(dev, "roi", L.sfod_roi_align_bwd_workspace_bytes(N, Cc, H, W, layout))
+            check(L.sfod_roi_align_bwd(g.data_ptr(), r.data_ptr(), N, Cc, H, W, r.shape[0], ph, pw, scale, sr, aligned,
+                                       gin.data_ptr(), layout, ws.data_ptr(), ws.numel(), _stream(dev)), "sfod_roi_align_bwd")
+        return gin.to(dtype), None, None, None, None, None, None, None
+
+
+def roi_align(input: Tensor, boxes: Union[Tensor, List[Tensor]], output_size, spatial_scale: float = 1.0,
+              sampling_ratio: int = -1, aligned: bool = False, exact: bool = False) -> Tensor:
+    """torchvision.ops.roi_align signature (roi_align.py:204-211).  ``exact=True`` reproduces torchvision's
+    summation order bit for bit; the default separable kernel agrees to <= 1e-5 relative."""
+    rois = _check_rois(boxes)
+    ph, pw = _pair(output_size)
+    return _RoIAlignFn.apply(input, rois, ph, pw, spatial_scale, sampling_ratio, aligned, exact)
+
+
+class _RoIPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, rois: Tensor, ph: int, pw: int, scale: float):
+        dev = _require_cuda(x, rois)
+        xin = _f32c(x)
+        r = _f32c(rois)
+        N, Cc, H, W = xin.shape
+        R = r.shape[0]
+        out = torch.empty((R, Cc, ph, pw), dtype=torch.float32, device=dev)
+        argmax = torch.empty((R, Cc, ph, pw), dtype=torch.int32, device=dev)
+        if R > 0:
+            with torch.cuda.device(dev):
+                check(_lib.lib().sfod_roi_pool_fwd(xin.data_ptr(), r.data_ptr(), N, Cc, H, W, R, ph, pw, float(scale),
+                                                   out.data_ptr(), argmax.data_ptr(), _stream(dev)), "sfod_roi_pool_fwd")
+        ctx.save_for_backward(r, argmax)
+        ctx.meta = (N, Cc, H, W, ph, pw, x.dtype)
+        return out.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        r, argmax = ctx.saved_tensors
+        N, Cc, H, W, ph, pw, dtype = ctx.meta
+        dev = grad_out.device
+        g = _f32c(grad_out)
+        gin = torch.empty((N, Cc, H, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().sfod_roi_pool_bwd(g.data_ptr(), r.data_ptr(), argmax.data_ptr(), N, Cc, H, W, r.shape[0], ph, pw,
+                                               gin.data_ptr(), _stream(dev)), "sfod_roi_pool_bwd")
+        return gin.to(dtype), None, None, None, None
+
+
+def roi_pool(input: Tensor, boxes: Union[Tensor, List[Tensor]], output_size, spatial_scale: float = 1.0) -> Tensor:
+    """torchvision.ops.roi_pool signature."""
+    rois = _check_rois(boxes)
+    ph, pw = _pair(output_size)
+    return _RoIPoolFn.apply(input, rois, ph, pw, spatial_scale)
+
+
+def nchw_to_nhwc(x: Tensor) -> Tensor:
+    """Returns a channels_last tensor with x's values (our transpose kernel, not a torch copy)."""
+    dev = _require_cuda(x)
+    xin = _f32c(x)
+    N, Cc, H, W = xin.shape
+    out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+    with torch.cuda.device(dev):
+        check(_lib.lib().sfod_nchw_to_nhwc(xin.data_ptr(), out.data_ptr(), N, Cc, H * W, _stream(dev)), "sfod_nchw_to_nhwc")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- box coder / softmax
+def apply_deltas(deltas: Tensor, boxes: Tensor, weights: Sequence[float], scale_clamp: float = SCALE_CLAMP) -> Tensor:
+    """detectron2 Box2BoxTransform.apply_deltas: deltas (R, 4k), boxes (R, 4) -> (R, 4k)."""
+    dev = _require_cuda(deltas, boxes)
+    d, b = _f32c(deltas), _f32c(boxes)
+    if d.dim() != 2 or d.shape[1] % 4 != 0 or b.shape != (d.shape[0], 4):
+        raise ValueError(f"apply_deltas: deltas {tuple(d.shape)} / boxes {tuple(b.shape)} mismatch")
+    out = torch.empty_like(d)
+    w = (C.c_float * 4)(*[float(v) for v in weights])
+    with torch.cuda.device(dev):
+        check(_lib.lib().sfod_apply_deltas(d.data_ptr(), b.data_ptr(), d.shape[0], d.shape[1] // 4, w, float(scale_clamp),
+                                           out.data_ptr(), _stream(dev)), "sfod_apply_deltas")
+    return out
+
+
+def softmax_lastdim(x: Tensor) -> Tensor:
+    dev = _require_cuda(x)
+    xin = _f32c(x)
+    x2 = xin.reshape(-1, xin.shape[-1])
+    out = torch.empty_like(x2)
+    with torch.cuda.device(dev):
+        check(_lib.lib().sfod_softmax_lastdim(x2.data_ptr(), x2.shape[0], x2.shape[1], out.data_ptr(), _stream(dev)),
+              "sfod_softmax_lastdim")
+    return out.reshape(xin.shape)
+
+
+def threshold_select(values: Tensor, counts: Tensor, thres: float) -> Tuple[Tensor, Tensor]:
+    """Per-row stable selection of ``values > thres`` among the first counts[s] entries.
+    values (S, stride) fp32, counts (S) int32 -> (index (S, stride) int64, count (S) int32)."""
+    dev = _require_cuda(values, counts)
+    v = _f32c(values)
+    c = counts.to(torch.int32).contiguous()
+    S, stride = v.shape
+    idx = torch.empty((S, stride), dtype=torch.int64, device=dev)
+    cnt = torch.empty((S,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().sfod_threshold_select(v.data_ptr(), c.data_ptr(), S, stride, float(thres), idx.data_ptr(),
+                                               cnt.data_ptr(), _stream(dev)), "sfod_threshold_select")
+    return idx, cnt
+
+
+# ----------------------------------------------------------------------------------------------- RPN selection
+def rpn_select(logits: Tensor, deltas: Tensor, image_sizes: Sequence[Tuple[int, int]], *, anchors: Optional[Tensor] = None,
+               cell_anchors: Optional[Tensor] = None, feat_hw: Optional[Tuple[int, int]] = None, stride: int = 0,
+               anchor_offset: float = 0.0, weights: Sequence[float] = (1.0, 1.0, 1.0, 1.0), scale_clamp: float = SCALE_CLAMP,
+               pre_nms_topk: int = 12000, post_nms_topk: int = 2000, nms_thresh: float = 0.7, min_box_size: float = 0.0):
+    """Single-level RPN.predict_proposals for all images: logits (N, HWA), deltas (N, HWA, 4).
+    Either ``anchors`` (HWA, 4) or (``cell_anchors`` (A, 4), ``feat_hw``, ``stride``) must be given.
+    Returns (boxes (N, P, 4), logits (N, P), src_index (N, P) int64, count (N) int32, invalid (N) int32)."""
+    dev = _require_cuda(logits, deltas, anchors)
+    lg, dl = _f32c(logits), _f32c(deltas)
+    N, HWA = lg.shape
+    if dl.shape != (N, HWA, 4):
+        raise ValueError(f"deltas must be (N, HWA, 4) = {(N, HWA, 4)}, got {tuple(dl.shape)}")
+    if len(image_sizes) != N:
+        raise ValueError("one image size per image is required")
+    p = RpnParams()
+    p.N, p.HWA = N, HWA
+    p.stride, p.anchor_offset = int(stride), float(anchor_offset)
+    for i in range(4):
+        p.weights[i] = float(weights[i])
+    p.scale_clamp = float(scale_clamp)
+    p.pre_nms_topk, p.post_nms_topk = int(pre_nms_topk), int(post_nms_topk)
+    p.min_box_size, p.nms_thresh = float(min_box_size), float(nms_thresh)
+    anc = None
+    if anchors is not None:
+        anc = _f32c(anchors)
+        if anc.shape != (HWA, 4):
+            raise ValueError("anchors must be (HWA, 4)")
+        p.A, p.Hf, p.Wf = 0, 0, 0
+    else:
+        if cell_anchors is None or feat_hw is None or stride <= 0:
+            raise ValueError("need anchors or (cell_anchors, feat_hw, stride)")
+        ca = cell_anchors.detach().to("cpu", torch.float32).reshape(-1).tolist()
+        A = len(ca) // 4
+        if A > 64:
+            raise ValueError("at most 64 cell anchors are supported in closed form; pass `anchors`")
+        p.A, p.Hf, p.Wf = A, int(feat_hw[0]), int(feat_hw[1])
+        for i, v in enumerate(ca):
+            p.cell_anchors[i] = v
+    P = int(post_nms_topk)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        hw = _small_i32(dev, [v for s in image_sizes for v in (int(s[0]), int(s[1]))])
+        out_boxes = torch.empty((N, P, 4), dtype=torch.float32, device=dev)
+        out_logits = torch.empty((N, P), dtype=torch.float32, device=dev)
+        out_src = torch.empty((N, P), dtype=torch.int64, device=dev)
+        out_cnt = torch.empty((N,), dtype=torch.int32, device=dev)
+        invalid = torch.empty((N,), dtype=torch.int32, device=dev)
+        ws = _workspace(dev, "rpn", L.sfod_rpn_select_workspace_bytes(C.byref(p)))
+        check(L.sfod_rpn_select(C.byref(p), lg.data_ptr(), dl.data_ptr(), anc.data_ptr() if anc is not None else None,
+                                hw.data_ptr(), out_boxes.data_ptr(), out_logits.data_ptr(), out_src.data_ptr(),
+                                out_cnt.data_ptr(), invalid.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)), "sfod_rpn_select")
+    return out_boxes, out_logits, out_src, out_cnt, invalid
+
+
+# ----------------------------------------------------------------------------------------------- Fast R-CNN post-process
+def frcnn_postprocess(cls_logits: Tensor, deltas: Tensor, proposals: Tensor, rows_per_image: Sequence[int],
+                      image_sizes: Sequence[Tuple[int, int]], *, weights: Sequence[float] = (10.0, 10.0, 5.0, 5.0),
+                      scale_clamp: float = SCALE_CLAMP, score_thresh: float = 0.05, nms_thresh: float = 0.5, topk: int = 100,
+                      pseudo_thresh: float = 0.8, want_probs: bool = False, want_boxes: bool = False):
+    """FastRCNNOutputLayers.inference + threshold_bbox("roih") for all images in one call.
+    cls_logits (R, K+1), deltas (R, 4K) or (R, 4), proposals (R, 4) concatenated over images."""
+    dev = _require_cuda(cls_logits, deltas, proposals)
+    cl, dl, pr = _f32c(cls_logits), _f32c(deltas), _f32c(proposals)
+    R, K1 = cl.shape
+    K = K1 - 1
+    if K < 1:
+        raise ValueError("cls_logits must have K+1 >= 2 columns")
+    if dl.shape[0] != R or dl.shape[1] not in (4, 4 * K) or pr.shape != (R, 4):
+        raise ValueError("deltas / proposals shapes do not match cls_logits")
+    if sum(rows_per_image) != R or len(rows_per_image) != len(image_sizes):
+        raise ValueError("rows_per_image must sum to R and match image_sizes")
+    if topk < 0:
+        raise ValueError("topk_per_image < 0 (return all) is not supported by the fused path")
+    N = len(rows_per_image)
+    p = FrcnnParams()
+    p.N, p.R, p.K = N, R, K
+    p.class_agnostic = int(dl.shape[1] == 4 and K != 1)
+    p.max_rows_per_image = max(1, max(rows_per_image)) if N else 1
+    for i in range(4):
+        p.weights[i] = float(weights[i])
+    p.scale_clamp, p.score_thresh, p.nms_thresh = float(scale_clamp), float(score_thresh), float(nms_thresh)
+    p.topk, p.pseudo_thresh, p.coord_trick_max_n = int(topk), float(pseudo_thresh), COORD_TRICK_MAX_N
+    T = int(topk)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        offs = [0]
+        for r in rows_per_image:
+            offs.append(offs[-1] + int(r))
+        row_off = _small_i32(dev, offs)
+        hw = _small_i32(dev, [v for s in image_sizes for v in (int(s[0]), int(s[1]))])
+        det_boxes = torch.empty((N, T, 4), dtype=torch.float32, device=dev)
+        det_scores = torch.empty((N, T), dtype=torch.float32, device=dev)
+        det_classes = torch.empty((N, T), dtype=torch.int64, device=dev)
+        det_rows = torch.empty((N, T), dtype=torch.int64, device=dev)
+        det_count = torch.empty((N,), dtype=torch.int32, device=dev)
+        pseudo_count = torch.empty((N,), dtype=torch.int32, device=dev)
+        probs = torch.empty((R, K1), dtype=torch.float32, device=dev) if want_probs else None
+        boxes = torch.empty((R, dl.shape[1]), dtype=torch.float32, device=dev) if want_boxes else None
+        ws = _workspace(dev, "frcnn", L.sfod_frcnn_postprocess_workspace_bytes(C.byref(p)))
+        check(L.sfod_frcnn_postprocess(C.byref(p), cl.data_ptr(), dl.data_ptr(), pr.data_ptr(), row_off.data_ptr(), hw.data_ptr(),
+                                       det_boxes.data_ptr(), det_scores.data_ptr(), det_classes.data_ptr(), det_rows.data_ptr(),
+                                       det_count.data_ptr(), pseudo_count.data_ptr(),
+                                       probs.data_ptr() if probs is not None else None,
+                                       boxes.data_ptr() if boxes is not None else None, ws.data_ptr(), ws.numel(), _stream(dev)),
+              "sfod_frcnn_postprocess")
+    return dict(boxes=det_boxes, scores=det_scores, classes=det_classes, rows=det_rows, count=det_count,
+                pseudo_count=pseudo_count, probs=probs, decoded=boxes)
+
+
+# ----------------------------------------------------------------------------------------------- EMA
+class EmaPlan:
+    """One-launch mean-teacher EMA over a fixed set of (student, teacher) tensor pairs.
+
+    The chunk table is built once (tensor storages of a model are stable across steps) and kept on the
+    device; ``step(keep_rate)`` is a single kernel launch at 12 B/element.
+    """
+
+    def __init__(self, pairs: Sequence[Tuple[Tensor, Tensor]]):
+        if len(pairs) == 0:
+            raise ValueError("EmaPlan needs at least one tensor pair")
+        dev = _require_cuda(*[t for pr in pairs for t in pr])
+        arr = (EmaTensor * len(pairs))()
+        self._keepalive = []
+        self.numel = 0
+        for i, (s, t) in enumerate(pairs):
+            if s.shape != t.shape:
+                raise ValueError(f"EMA pair {i}: shape mismatch {tuple(s.shape)} vs {tuple(t.shape)}")
+            if s.dtype != t.dtype:
+                raise ValueError(f"EMA pair {i}: dtype mismatch {s.dtype} vs {t.dtype}")
+            if s.dtype == torch.float32:
+                code = 0
+            elif s.dtype == torch.int64:
+                code = 1
+            else:
+                raise TypeError(f"EMA supports float32 and int64 state tensors, got {s.dtype}")
+            if not s.is_contiguous() or not t.is_contiguous():
+                raise ValueError("EMA tensors must be contiguous (state_dict tensors are)")
+            arr[i].student, arr[i].teacher = s.data_ptr(), t.data_ptr()
+            arr[i].numel, arr[i].dtype = s.numel(), code
+            self._keepalive.append((s, t))
+            self.numel += s.numel()
+        L = _lib.lib()
+        self.n_chunks = int(L.sfod_ema_plan_chunks(arr, len(pairs)))
+        nbytes = int(L.sfod_ema_plan_bytes(self.n_chunks))
+        host = torch.empty(max(nbytes, 8), dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else None
+        check(L.sfod_ema_plan_build(arr, len(pairs), host.data_ptr(), nbytes), "sfod_ema_plan_build")
+        self.device = dev
+        self.plan = host.to(dev, non_blocking=False)
+
+    def step(self, keep_rate: float) -> None:
+        with torch.cuda.device(self.device):
+            check(_lib.lib().sfod_ema_multi_tensor(self.plan.data_ptr(), self.n_chunks, float(keep_rate), _stream(self.device)),
+                  "sfod_ema_multi_tensor")
+
+
+# ----------------------------------------------------------------------------------------------- BatchNorm (AdaBN)
+def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], running_mean: Optional[Tensor],
+                     running_var: Optional[Tensor], num_batches_tracked: Optional[Tensor], momentum: float = 0.1,
+                     eps: float = 1e-5, fuse_relu: bool = False, inplace: bool = False, group=None,
+                     compute_output: bool = True) -> Optional[Tensor]:
+    """Train-mode BatchNorm2d forward without autograd (the AdaBN / no_grad-teacher case): batch statistics,
+    running-stat update, normalise(+ReLU).  With ``group`` (a torch.distributed process group) the per-channel
+    (sum, sum^2, count) triple is all-reduced so that all ranks normalise with the statistics of the
+    concatenated batch."""
+    dev = _require_cuda(x)
+    xin, layout = _layout_of(x.detach())
+    if xin.dtype != torch.float32:
+        raise TypeError("bn_train_forward computes in float32")
+    N, Cc, H, W = xin.shape
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        stats = torch.empty((L.sfod_bn_stats_bytes(Cc) // 8,), dtype=torch.float64, device=dev)
+        check(L.sfod_bn_partial_stats(xin.data_ptr(), layout, N, Cc, H * W, stats.data_ptr(), _stream(dev)), "sfod_bn_partial_stats")
+        total = float(N * H * W)
+        if group is not None:
+            import torch.distributed as dist
+            payload = stats[: 2 * Cc + 1]
+            payload[2 * Cc] = total
+            dist.all_reduce(payload, group=group if group is not True else None)
+            total = float(payload[2 * Cc].item())
+        y = None
+        if compute_output:
+            y = xin if inplace else torch.empty_like(xin)
+        check(L.sfod_bn_finalize_apply(xin.data_ptr() if compute_output else None, y.data_ptr() if y is not None else None, layout,
+                                       N, Cc, H * W, stats.data_ptr(), total,
+                                       weight.data_ptr() if weight is not None else None,
+                                       bias.data_ptr() if bias is not None else None,
+                                       running_mean.data_ptr() if running_mean is not None else None,
+                                       running_var.data_ptr() if running_var is not None else None,
+                                       num_batches_tracked.data_ptr() if num_batches_tracked is not None else None,
+                                       float(momentum), float(eps), int(fuse_relu), None, None, _stream(dev)),
+              "sfod_bn_finalize_apply")
+    return y

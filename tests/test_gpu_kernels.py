@@ -1,0 +1,373 @@
+"""GPU parity tests: every CUDA entry point (through the C ABI via sfod_b200.ops) against the CPU oracle
+on the same seeded inputs.  Integer results (keep indices, top-k indices, classes, rows, counts) must be
+bit-exact; floating-point results match within the tolerance stated in each test (BASELINE.json: 1e-5
+relative fp32; where the CUDA arithmetic is *defined* identically to the oracle's we assert equality)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torchvision
+
+from oracle import c_oracle as co
+from oracle import d2_cpu as o
+import sfod_b200  # noqa: F401
+from sfod_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    import sfod_b200
+    return sfod_b200.ops
+
+
+def _close(a, b, rtol=1e-5, atol_scale=1e-5):
+    a = a.detach().cpu().double(); b = b.detach().cpu().double()
+    scale = max(float(b.abs().max()), 1e-30) if b.numel() else 1.0
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs()
+    tol = atol_scale * scale + rtol * b.abs()
+    assert bool((err <= tol).all()), f"max err {float(err.max()):.3e} (scale {scale:.3e})"
+
+
+# ------------------------------------------------------------------------------------------------ EMA
+@pytest.mark.parametrize("keep_rate", [0.9996, 0.999696, 0.0])
+def test_ema_multi_tensor_bit_exact(ops, cuda_device, keep_rate):
+    g = torch.Generator().manual_seed(7)
+    shapes = [(64,), (64, 3, 3, 3), (1,), (7,), (1000003,), (512, 512, 3, 3), (33, 5), (4099,)]
+    student = {f"p{i}": torch.randn(s, generator=g) for i, s in enumerate(shapes)}
+    teacher = {f"p{i}": torch.randn(s, generator=g) for i, s in enumerate(shapes)}
+    student["nbt"] = torch.tensor(1000, dtype=torch.int64); teacher["nbt"] = torch.tensor(1000, dtype=torch.int64)
+    student["nbt2"] = torch.tensor([5, 0, 123456789], dtype=torch.int64); teacher["nbt2"] = torch.tensor([7, 3, 123456000], dtype=torch.int64)
+    student["p0"][3] = float("nan"); teacher["p1"].view(-1)[5] = -0.0; student["p1"].view(-1)[5] = 0.0
+    ref_t = {k: v.clone() for k, v in teacher.items()}
+    o.load_state_dict_like(ref_t, o.update_teacher_model(student, ref_t, keep_rate))
+    sd = {k: v.to(cuda_device) for k, v in student.items()}
+    td = {k: v.to(cuda_device) for k, v in teacher.items()}
+    plan = ops.EmaPlan([(sd[k], td[k]) for k in td])
+    plan.step(keep_rate)
+    torch.cuda.synchronize()
+    for k in td:
+        got, ref = td[k].cpu(), ref_t[k]
+        if got.dtype == torch.float32:
+            assert np.array_equal(got.numpy().view(np.uint32), ref.numpy().view(np.uint32)), k
+        else:
+            assert torch.equal(got, ref), k
+    # second step keeps matching (state carried on the device)
+    o.load_state_dict_like(ref_t, o.update_teacher_model(student, ref_t, keep_rate))
+    plan.step(keep_rate)
+    assert np.array_equal(td["p4"].cpu().numpy().view(np.uint32), ref_t["p4"].numpy().view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------ NMS
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 500, 2000, 4000, 9990])
+@pytest.mark.parametrize("kind", ["low", "high"])
+def test_nms_bit_exact(ops, cuda_device, n, kind):
+    if kind == "low":
+        b, s = synth.boxes_low_suppression(synth.V, n, 1234)
+    else:
+        b, s = synth.boxes_high_suppression(n, 1234)
+    n = b.shape[0]
+    for thr in (0.7, 0.5):
+        ref = torchvision.ops.nms(b, s, thr)
+        got = ops.nms(b.to(cuda_device), s.to(cuda_device), thr).cpu()
+        assert torch.equal(got, ref), f"n={n} thr={thr}: {got.numel()} vs {ref.numel()} kept"
+
+
+def test_nms_large_multi_tile_sort(ops, cuda_device):
+    b, s = synth.boxes_high_suppression(20000, 99, clusters=600)
+    ref = torchvision.ops.nms(b, s, 0.7)
+    got = ops.nms(b.to(cuda_device), s.to(cuda_device), 0.7).cpu()
+    assert torch.equal(got, ref)
+
+
+def test_nms_semantics_kats(ops, cuda_device):
+    """ties keep the lowest index; degenerate boxes (IoU NaN) are never suppressed; strict >."""
+    d = cuda_device
+    b = torch.tensor([[0, 0, 10, 10], [0, 0, 10, 10], [20, 20, 30, 30], [20, 20, 30, 30]], dtype=torch.float32)
+    s = torch.ones(4)
+    assert ops.nms(b.to(d), s.to(d), 0.5).cpu().tolist() == [0, 2]
+    b = torch.tensor([[5, 5, 5, 5], [5, 5, 5, 5], [0, 0, 10, 10]], dtype=torch.float32)
+    assert ops.nms(b.to(d), torch.tensor([0.9, 0.8, 0.7]).to(d), 0.5).cpu().tolist() == [0, 1, 2]
+    b = torch.tensor([[0, 0, 10, 10], [0, 0, 10, 5]], dtype=torch.float32)  # IoU exactly 0.5
+    assert ops.nms(b.to(d), torch.tensor([0.9, 0.8]).to(d), 0.5).cpu().tolist() == [0, 1]
+    assert ops.nms(torch.zeros(0, 4, device=d), torch.zeros(0, device=d), 0.5).numel() == 0
+    with pytest.raises(ValueError):
+        ops.nms(torch.zeros(3, 5, device=d), torch.zeros(3, device=d), 0.5)
+    with pytest.raises(RuntimeError):
+        ops.nms(torch.zeros(3, 4), torch.zeros(3), 0.5)  # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("n", [900, 1000, 1001, 6000])
+def test_batched_nms_matches_torchvision_cpu_strategy(ops, cuda_device, n):
+    """n <= 1000 -> coordinate trick arithmetic, above -> per-class."""
+    b, s = synth.boxes_high_suppression(n, 5, clusters=60)
+    g = torch.Generator().manual_seed(3)
+    idx = torch.randint(0, 8, (n,), generator=g)
+    ref = o.batched_nms(b, s, idx, 0.5)
+    got = ops.batched_nms(b.to(cuda_device), s.to(cuda_device), idx.to(cuda_device), 0.5).cpu()
+    assert torch.equal(got, ref)
+
+
+# ------------------------------------------------------------------------------------------------ ROIAlign / ROIPool
+@pytest.mark.parametrize("cfg", [synth.V, synth.R101], ids=["V", "R"])
+@pytest.mark.parametrize("aligned", [True, False])
+def test_roi_align_forward(ops, cuda_device, cfg, aligned):
+    N, R = 2, 300
+    x = synth.features(cfg, N, 11)
+    rois = synth.random_rois(N, R, 12)
+    # a few adversarial rois: outside the image, zero / negative size, whole image, tiny
+    extra = torch.tensor([[0, -500, -500, -100, -100], [1, 100, 100, 100, 100], [0, 300, 300, 200, 250],
+                          [1, 0, 0, 1200, 600], [0, 10.3, 20.7, 12.1, 22.9], [1, 1100, 500, 1400, 800]], dtype=torch.float32)
+    rois = torch.cat([rois, extra])
+    scale = 1.0 / cfg["stride"]
+    for sr in (0, 2):
+        ref = torchvision.ops.roi_align(x, rois, (7, 7), scale, sr, aligned)
+        xe = x.to(cuda_device); re_ = rois.to(cuda_device)
+        exact = ops.roi_align(xe, re_, (7, 7), scale, sr, aligned, exact=True).cpu()
+        assert np.array_equal(exact.numpy().view(np.uint32), ref.numpy().view(np.uint32)), "exact kernel must be bit-exact"
+        fast = ops.roi_align(xe, re_, (7, 7), scale, sr, aligned).cpu()
+        _close(fast, ref)
+        fast_cl = ops.roi_align(xe.contiguous(memory_format=torch.channels_last), re_, (7, 7), scale, sr, aligned).cpu()
+        assert torch.equal(fast_cl, fast), "NHWC input must give the same result as the internally transposed NCHW input"
+
+
+def test_roi_align_kat_and_api(ops, cuda_device):
+    """SURVEY.md B-3 known answers + torchvision API forms (list of boxes, other output sizes)."""
+    d = cuda_device
+    x = torch.arange(25, dtype=torch.float32).reshape(1, 1, 5, 5).to(d)
+    rois = torch.tensor([[0, 1, 1, 3, 3]], dtype=torch.float32).to(d)
+    a = ops.roi_align(x, rois, (4, 4), 1.0, 0, False).cpu().reshape(4, 4)
+    assert a.tolist() == [[7.5, 8, 8.5, 9], [10, 10.5, 11, 11.5], [12.5, 13, 13.5, 14], [15, 15.5, 16, 16.5]]
+    a = ops.roi_align(x, rois, (4, 4), 1.0, 0, True).cpu().reshape(4, 4)
+    assert a.tolist() == [[4.5, 5, 5.5, 6], [7, 7.5, 8, 8.5], [9.5, 10, 10.5, 11], [12, 12.5, 13, 13.5]]
+    p = ops.roi_pool(x, rois, (2, 2), 1.0).cpu().reshape(2, 2)
+    assert p.tolist() == [[12, 13], [17, 18]]
+    xs = torch.randn(2, 8, 20, 30)
+    bl = [torch.tensor([[1.0, 2.0, 15.0, 12.0]]), torch.tensor([[0.0, 0.0, 29.0, 19.0], [3.0, 3.0, 9.0, 9.0]])]
+    ref = torchvision.ops.roi_align(xs, bl, 7, 1.0, 0, True)
+    got = ops.roi_align(xs.to(d), [b.to(d) for b in bl], 7, 1.0, 0, True).cpu()
+    _close(got, ref)
+    assert ops.roi_align(xs.to(d), torch.zeros(0, 5, device=d), 7).shape == (0, 8, 7, 7)
+    with pytest.raises(ValueError):
+        ops.roi_align(xs.to(d), torch.zeros(3, 4, device=d), 7)
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_roi_align_backward(ops, cuda_device, layout):
+    cfg = synth.V
+    N, R = 2, 512
+    x = synth.features(cfg, N, 21)
+    rois = synth.random_rois(N, R, 22)
+    g = torch.randn(R, cfg["C"], 7, 7, generator=torch.Generator().manual_seed(23))
+    xr = x.clone().requires_grad_(True)
+    torchvision.ops.roi_align(xr, rois, (7, 7), 1 / 32, 0, True).backward(g)
+    xd = x.to(cuda_device)
+    if layout == "nhwc":
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    xd.requires_grad_(True)
+    y = ops.roi_align(xd, rois.to(cuda_device), (7, 7), 1 / 32, 0, True)
+    y.backward(g.to(cuda_device))
+    _close(xd.grad, xr.grad, rtol=1e-5, atol_scale=1e-5)
+    # generic (non 7x7) path
+    xr2 = x[:, :16].clone().requires_grad_(True)
+    g2 = torch.randn(R, 16, 5, 3, generator=torch.Generator().manual_seed(24))
+    torchvision.ops.roi_align(xr2, rois, (5, 3), 1 / 32, 2, False).backward(g2)
+    xd2 = x[:, :16].to(cuda_device).requires_grad_(True)
+    ops.roi_align(xd2, rois.to(cuda_device), (5, 3), 1 / 32, 2, False).backward(g2.to(cuda_device))
+    _close(xd2.grad, xr2.grad)
+
+
+def test_roi_pool_forward_backward(ops, cuda_device):
+    cfg = synth.V
+    N, R = 2, 256
+    x = synth.features(cfg, N, 31)[:, :64].contiguous()
+    rois = synth.random_rois(N, R, 32)
+    xr = x.clone().requires_grad_(True)
+    ref = torchvision.ops.roi_pool(xr, rois, (7, 7), 1 / 32)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    xd = x.to(cuda_device).requires_grad_(True)
+    got = ops.roi_pool(xd, rois.to(cuda_device), (7, 7), 1 / 32)
+    assert torch.equal(got.detach().cpu(), ref.detach()), "max pooling must be bit-exact"
+    got.backward(g.to(cuda_device))
+    _close(xd.grad, xr.grad)
+
+
+# ------------------------------------------------------------------------------------------------ box decode / softmax
+def test_apply_deltas_and_softmax_defined_arithmetic(ops, cuda_device):
+    g = torch.Generator().manual_seed(41)
+    R = 5000
+    ctr = torch.rand(R, 2, generator=g) * 1000; wh = torch.rand(R, 2, generator=g) * 300 + 1
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    d = torch.randn(R, 32, generator=g) * 2
+    d[0, 3] = 100.0  # clamp path
+    got = ops.apply_deltas(d.to(cuda_device), boxes.to(cuda_device), (10, 10, 5, 5)).cpu()
+    spec = o.apply_deltas(d, boxes, (10, 10, 5, 5), exp=o.exp_correctly_rounded)
+    assert torch.equal(got, spec), "decode must equal the defined (correctly-rounded-exp) arithmetic bit for bit"
+    _close(got, o.apply_deltas(d, boxes, (10, 10, 5, 5)), rtol=1e-5, atol_scale=0)  # vs ATen exp: <= 1 ulp on the exp term
+    kat = ops.apply_deltas(torch.tensor([[0.1, -0.2, 0.3, 10.0]]).to(cuda_device), torch.tensor([[10.0, 20, 50, 100]]).to(cuda_device),
+                           (1, 1, 1, 1)).cpu()[0].tolist()
+    assert kat == [7.0028228759765625, -2456.000244140625, 60.99717712402344, 2544.000244140625]
+    x = torch.randn(4000, 9, generator=g) * 4
+    sm = ops.softmax_lastdim(x.to(cuda_device)).cpu()
+    assert torch.equal(sm, o.softmax_defined(x))
+    _close(sm, torch.softmax(x, -1), rtol=1e-5, atol_scale=0)
+
+
+# ------------------------------------------------------------------------------------------------ RPN selection
+def _rpn_case(ops, dev, cfg, N, seed, pre, post, image_sizes, use_anchor_tensor=False, delta_std=0.5):
+    logits, deltas, cell, anchors = synth.rpn_head_outputs(cfg, N, seed, delta_std)
+    ref = o.rpn_predict_proposals([anchors], [logits], [deltas], image_sizes, 0.7, pre, post, 0.0, False,
+                                  exp=o.exp_correctly_rounded)
+    kw = dict(anchors=anchors.to(dev)) if use_anchor_tensor else dict(cell_anchors=cell, feat_hw=(cfg["H"], cfg["W"]), stride=cfg["stride"])
+    boxes, lg, src, cnt, invalid = ops.rpn_select(logits.to(dev), deltas.to(dev), image_sizes, pre_nms_topk=pre,
+                                                  post_nms_topk=post, nms_thresh=0.7, **kw)
+    cnt = cnt.cpu().tolist()
+    assert invalid.cpu().tolist() == [0] * N
+    for i in range(N):
+        k = cnt[i]
+        assert k == len(ref[i]["src_index"]), (i, k, len(ref[i]["src_index"]))
+        assert torch.equal(src[i, :k].cpu(), ref[i]["src_index"]), f"image {i}: proposal index mismatch"
+        assert torch.equal(boxes[i, :k].cpu(), ref[i]["proposal_boxes"])
+        assert torch.equal(lg[i, :k].cpu(), ref[i]["objectness_logits"])
+    return ref, (boxes, lg, src, cnt)
+
+
+def test_rpn_select_vgg_teacher_train_mode(ops, cuda_device):
+    _rpn_case(ops, cuda_device, synth.V, 2, 1234, 12000, 2000, [(600, 1200), (600, 1200)])
+
+
+def test_rpn_select_vgg_eval_and_ragged_image_sizes(ops, cuda_device):
+    _rpn_case(ops, cuda_device, synth.V, 3, 1235, 6000, 1000, [(600, 1200), (576, 1100), (300, 400)])
+
+
+def test_rpn_select_explicit_anchor_tensor(ops, cuda_device):
+    _rpn_case(ops, cuda_device, synth.V, 1, 1236, 12000, 2000, [(600, 1200)], use_anchor_tensor=True)
+
+
+def test_rpn_select_r101_topk_12000_of_34200(ops, cuda_device):
+    _rpn_case(ops, cuda_device, synth.R101, 1, 1237, 12000, 2000, [(600, 1200)])
+
+
+def test_rpn_select_high_suppression_and_reference_exp(ops, cuda_device):
+    """Tiny deltas -> anchors at the same cell overlap heavily -> few survivors (count < post_nms_topk).
+    Also compares with the reference-faithful oracle (ATen exp): boxes within 1e-5, keep sets reported."""
+    cfg = synth.V
+    ref_cr, (boxes, lg, src, cnt) = _rpn_case(ops, cuda_device, cfg, 1, 1238, 12000, 2000, [(600, 1200)], delta_std=0.05)
+    logits, deltas, cell, anchors = synth.rpn_head_outputs(cfg, 1, 1238, 0.05)
+    ref_aten = o.rpn_predict_proposals([anchors], [logits], [deltas], [(600, 1200)], 0.7, 12000, 2000, 0.0, False)
+    a, b = set(ref_aten[0]["src_index"].tolist()), set(src[0, :cnt[0]].cpu().tolist())
+    # the 1-ulp exp difference may flip an IoU decision in rare cases; sets must agree to >= 99.9 %
+    assert len(a ^ b) <= max(2, len(a) // 1000), f"{len(a ^ b)} proposals differ between ATen-exp and defined-exp"
+
+
+def test_rpn_select_invalid_counts_nonfinite(ops, cuda_device):
+    logits, deltas, cell, anchors = synth.rpn_head_outputs(synth.V, 1, 77)
+    deltas[0, 5, 0] = float("inf"); logits[0, 9] = float("nan")
+    _, _, _, cnt, invalid = ops.rpn_select(logits.to(cuda_device), deltas.to(cuda_device), [(600, 1200)], cell_anchors=cell,
+                                           feat_hw=(18, 37), stride=32)
+    assert invalid.cpu().tolist() == [2]
+    ref = o.rpn_predict_proposals([anchors], [logits], [deltas], [(600, 1200)], training=False, exp=o.exp_correctly_rounded)
+    assert cnt.cpu().tolist()[0] == len(ref[0]["src_index"])
+
+
+# ------------------------------------------------------------------------------------------------ Fast R-CNN post-process
+def _frcnn_case(ops, dev, rows, K, seed, logit_std, image_sizes, delta_std=1.0, pseudo=0.8):
+    R = sum(rows)
+    cls, dl = synth.box_head_outputs(R, K, seed, logit_std, delta_std)
+    props = synth.random_rois(1, R, seed + 1)[:, 1:].contiguous()
+    plist = list(props.split(rows))
+    ref = o.box_predictor_inference(cls, dl, plist, image_sizes, 0.05, 0.5, 100, exp=o.exp_correctly_rounded,
+                                    softmax=o.softmax_defined)
+    out = ops.frcnn_postprocess(cls.to(dev), dl.to(dev), props.to(dev), rows, image_sizes, pseudo_thresh=pseudo,
+                                want_probs=True, want_boxes=True)
+    cnt = out["count"].cpu().tolist(); pc = out["pseudo_count"].cpu().tolist()
+    for i, r in enumerate(ref):
+        k = cnt[i]
+        assert k == len(r["scores"]), (i, k, len(r["scores"]))
+        assert torch.equal(out["classes"][i, :k].cpu(), r["pred_classes"])
+        assert torch.equal(out["rows"][i, :k].cpu(), r["kept_rows"])
+        assert torch.equal(out["scores"][i, :k].cpu(), r["scores"])
+        assert torch.equal(out["boxes"][i, :k].cpu(), r["pred_boxes"])
+        pl = o.threshold_bbox(r, pseudo, "roih")
+        assert pc[i] == len(pl["scores"]), "pseudo-label set size"
+        assert torch.equal(out["boxes"][i, :pc[i]].cpu(), pl["gt_boxes"]) and torch.equal(out["classes"][i, :pc[i]].cpu(), pl["gt_classes"])
+    assert torch.equal(out["probs"].cpu(), o.softmax_defined(cls))
+    assert torch.equal(out["decoded"].cpu(), o.apply_deltas(dl, props, (10, 10, 5, 5), exp=o.exp_correctly_rounded))
+    return ref, out, (cls, dl, plist)
+
+
+def test_frcnn_postprocess_confident_logits(ops, cuda_device):
+    """logits N(0,4): ~25 % of the 16 000 (row, class) pairs pass 0.05, some scores exceed 0.8."""
+    ref, out, _ = _frcnn_case(ops, cuda_device, [2000, 2000], 8, 51, 4.0, [(600, 1200), (600, 1200)])
+    assert sum(out["pseudo_count"].cpu().tolist()) > 0
+
+
+def test_frcnn_postprocess_random_init_like(ops, cuda_device):
+    """near-uniform softmax (random-init heads): all 16 000 candidates pass 0.05, empty pseudo-label set."""
+    ref, out, _ = _frcnn_case(ops, cuda_device, [2000], 8, 52, 0.05, [(600, 1200)], delta_std=0.1)
+    assert out["pseudo_count"].cpu().tolist() == [0]
+
+
+def test_frcnn_postprocess_small_uses_coordinate_trick_and_ragged(ops, cuda_device):
+    """<= 1000 candidates per image -> torchvision-CPU's coordinate-trick arithmetic; ragged rows incl. an empty image."""
+    _frcnn_case(ops, cuda_device, [150, 0, 37, 1000], 8, 53, 4.0, [(600, 1200), (600, 1200), (300, 500), (600, 1200)])
+
+
+def test_frcnn_postprocess_single_class_variant(ops, cuda_device):
+    _frcnn_case(ops, cuda_device, [1000, 800], 1, 54, 3.0, [(600, 1200), (600, 1200)])
+
+
+def test_frcnn_postprocess_vs_reference_faithful_oracle(ops, cuda_device):
+    """Against the oracle that uses ATen's own exp/softmax (<= 1 ulp different): boxes/scores within 1e-5,
+    detection (row, class) sets identical up to threshold-straddling rarities."""
+    ref_spec, out, (cls, dl, plist) = _frcnn_case(ops, cuda_device, [2000], 8, 55, 4.0, [(600, 1200)])
+    ref = o.box_predictor_inference(cls, dl, plist, [(600, 1200)], 0.05, 0.5, 100)[0]
+    k = out["count"].cpu().tolist()[0]
+    a = set(zip(ref["kept_rows"].tolist(), ref["pred_classes"].tolist()))
+    b = set(zip(out["rows"][0, :k].cpu().tolist(), out["classes"][0, :k].cpu().tolist()))
+    assert len(a ^ b) <= 2
+    if a == b and torch.equal(ref["kept_rows"], out["rows"][0, :k].cpu()):
+        _close(out["boxes"][0, :k], ref["pred_boxes"], rtol=1e-5, atol_scale=1e-6)
+        _close(out["scores"][0, :k], ref["scores"], rtol=1e-5, atol_scale=0)
+
+
+def test_threshold_select(ops, cuda_device):
+    g = torch.Generator().manual_seed(61)
+    v = torch.rand(5, 700, generator=g)
+    counts = torch.tensor([700, 0, 1, 333, 512], dtype=torch.int32)
+    idx, cnt = ops.threshold_select(v.to(cuda_device), counts.to(cuda_device), 0.8)
+    for s in range(5):
+        ref = (v[s, :counts[s]] > 0.8).nonzero().flatten()
+        assert cnt[s].item() == ref.numel() and torch.equal(idx[s, :ref.numel()].cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ BatchNorm / AdaBN
+@pytest.mark.parametrize("shape", [(2, 64, 75, 150), (2, 512, 37, 75), (1, 128, 64, 96), (3, 24, 17, 19)])
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_bn_train_forward(ops, cuda_device, shape, layout):
+    g = torch.Generator().manual_seed(71)
+    x = torch.randn(shape, generator=g) * 3 + torch.linspace(-50, 50, shape[1]).view(1, -1, 1, 1)
+    bn = torch.nn.BatchNorm2d(shape[1])
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.uniform_(-1, 1, generator=g)
+        bn.running_mean.normal_(generator=g); bn.running_var.uniform_(0.5, 2.0, generator=g)
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    bn.train()
+    with torch.no_grad():
+        yref = bn(x)
+    d = cuda_device
+    xd = x.to(d)
+    if layout == "nhwc":
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    rm, rv = rm0.to(d), rv0.to(d); nbt = torch.zeros((), dtype=torch.int64, device=d)
+    y = ops.bn_train_forward(xd, bn.weight.detach().to(d), bn.bias.detach().to(d), rm, rv, nbt, 0.1, 1e-5)
+    _close(rm, bn.running_mean, rtol=1e-5, atol_scale=1e-6)
+    _close(rv, bn.running_var, rtol=1e-5, atol_scale=0)
+    _close(y, yref, rtol=1e-5, atol_scale=1e-5)
+    assert nbt.item() == 1
+    yr = ops.bn_train_forward(xd, bn.weight.detach().to(d), bn.bias.detach().to(d), None, None, None, 0.1, 1e-5, fuse_relu=True)
+    _close(yr, torch.relu(yref), rtol=1e-5, atol_scale=1e-5)
