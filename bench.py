@@ -1,0 +1,366 @@
+"""bench.py -- pseudo-labelled images/s of the teacher pseudo-labelling hot path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2], teacher half): Faster R-CNN VGG16-BN teacher of
+faster_rcnn_VGG_cityscapes_foggy_adaptive_teacher_source_free, batch 8 images/GPU of synthetic 600x1200 Cityscapes-shaped
+uint8 images, 8 classes, random-init weights (seed 42), teacher in train() mode under no_grad exactly as the reference runs
+it.  One step = preprocess -> backbone (cuDNN convs; BatchNorm statistics + normalise+ReLU on the sm_100a kernels)
+-> PseudoLabRPN (fused decode/top-k/NMS kernel chain) -> ROIAlignV2 kernel -> box head (cuBLAS) -> fused Fast R-CNN
+post-process + pseudo-label filter -> List[Instances] pseudo-labels, followed by one mean-teacher EMA launch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                         # the reference's CPU path (oracle) on the host cores
+
+Under torchrun (N > 1) every rank owns a teacher replica and its own 8 images (no data-path collective: weak scaling);
+timing is barrier + synchronize on both sides, CUDA events, max over ranks; rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pseudo_labelled_images_per_s"
+UNIT = "images/s"
+IMAGE_HW = (600, 1200)
+NUM_CLASSES = 8
+WORKLOAD = ("configs[2] teacher half: faster_rcnn_VGG_cityscapes_foggy_adaptive_teacher_source_free, VGG16-BN teacher "
+            "pseudo-labelling (train-mode BN, RPN 9990->2000, ROIAlignV2, per-class NMS, >0.8 filter) + EMA, "
+            "synthetic 600x1200 uint8, 8 classes, random init")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step (configs[2]: 8)")
+    ap.add_argument("--tf32", type=int, default=0, help="1 = let cuDNN/cuBLAS use TF32 for the (library) convs/FCs")
+    ap.add_argument("--channels-last", type=int, default=0, help="1 = run the backbone in NHWC")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`); "
+                         "numbers printed under a profiler are not bench values")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock budget of the reference arm")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_images(batch: int, seed: int):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (batch, 3) + IMAGE_HW, dtype=torch.uint8, generator=g)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML every 100 ms while the timed region runs."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.mask, self.max_mhz, self.stop_flag, self.ok = index, [], 0, None, threading.Event(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag.set()
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.samples)
+        reasons = [n for b, n in self.REASONS.items() if self.mask & b and n != "gpu_idle"]
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_reference_run(steps: int, warmup: int, budget_s: float, seed: int = 1234, images_per_step: int = 1, with_ema: bool = True):
+    """Times the oracle (CPU restatement of the reference's path) on all host cores: each step pseudo-labels
+    ``images_per_step`` synthetic image(s) and performs one EMA update.  Returns (images/s, dict)."""
+    import torch
+    from oracle import teacher_cpu
+    import sfod_b200  # noqa: F401  (only for the model definition that supplies the random-init state_dict)
+    from sfod_b200 import config, modeling
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(42)
+    cfg = config.vgg_source_free_cfg()
+    cfg.MODEL.DEVICE = "cpu"
+    teacher_sd = {k: v.clone() for k, v in modeling.SourceFreeAdaptiveTeacherGeneralizedRCNN(cfg).state_dict().items()}
+    student_sd = {k: (v + 0.01 * torch.randn_like(v) if v.is_floating_point() else v.clone()) for k, v in teacher_sd.items()}
+    imgs = synth_images(images_per_step, seed)
+
+    def step():
+        out = teacher_cpu.teacher_pseudo_label(teacher_sd, imgs, training=True, num_classes=NUM_CLASSES, bbox_threshold=0.8)
+        if with_ema:
+            teacher_cpu.ema_update(student_sd, teacher_sd, 0.9996)
+        return out
+
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    w_done = 1
+    # bounded sample: shrink the number of executed steps if K+W steps would blow the wall-clock budget
+    w_run = max(0, min(warmup, int((budget_s * 0.25) // max(first, 1e-3))) - 1)
+    for _ in range(w_run):
+        step()
+        w_done += 1
+    left = budget_s - (time.perf_counter() - t0)
+    k_run = max(1, min(steps, int(left // max(first, 1e-3))))
+    t1 = time.perf_counter()
+    for _ in range(k_run):
+        step()
+    dt = time.perf_counter() - t1
+    value = images_per_step * k_run / dt
+    info = {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{k_run} timed step(s) of {images_per_step} image(s) 600x1200 (+{w_done} warm-up), full teacher pseudo-labelling "
+                      f"+ EMA on torch-CPU/torchvision-CPU, {1e3 * dt / k_run:.0f} ms/step"}
+    return value, info, k_run, w_done, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    value, info, k_run, w_done, dt = cpu_reference_run(args.steps, args.warmup, args.cpu_budget_s)
+    line = {"impl": "reference", "metric": METRIC, "value": info["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": k_run,
+            "warmup": w_done, "ms_per_step": round(1e3 * dt / k_run, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_step": 1, "image_hw": list(IMAGE_HW), "num_classes": NUM_CLASSES,
+                       "note": "CPU arm runs on rank 0 only; bounded sample of 1 image per step"},
+            "cpu_baseline": info,
+            "e2e": {"value": info["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py measures the CUDA path: no CUDA device is visible (there is no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import sfod_b200  # noqa: F401
+    from sfod_b200 import config, engine, modeling, ops
+
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.benchmark = True
+
+    torch.manual_seed(42)  # SEED: 42 of the reference config; identical weights on every rank
+    cfg = config.vgg_source_free_cfg()
+    cfg.MODEL.DEVICE = "cpu"
+    teacher = modeling.SourceFreeAdaptiveTeacherGeneralizedRCNN(cfg)
+    student = modeling.SourceFreeAdaptiveTeacherGeneralizedRCNN(cfg)
+    student.load_state_dict(teacher.state_dict())
+    with torch.no_grad():
+        for p in student.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    teacher.to(dev).train()   # the reference never .eval()s the teacher
+    student.to(dev).train()
+    if args.channels_last:
+        teacher.backbone.to(memory_format=torch.channels_last)
+    ema = engine.TeacherEMA(student, teacher, world_size=1)
+    thr = cfg.SEMISUPNET.BBOX_THRESHOLD
+    B = args.batch
+
+    n_rot = 4
+    host_batches = [synth_images(B, 1234 + rank * 1000 + i).pin_memory() for i in range(n_rot)]
+    dev_batches = [h.to(dev) for h in host_batches]
+
+    def pseudo_label(images_dev):
+        with torch.no_grad():
+            _, proposals_rpn, proposals_roih = teacher(images_dev.to(memory_format=torch.channels_last) if args.channels_last else images_dev,
+                                                       branch="unsup_data_weak")
+        pl, _ = engine.process_pseudo_label(proposals_roih, thr, "roih", "thresholding")
+        return proposals_rpn, proposals_roih, pl
+
+    def step_resident(i):
+        out = pseudo_label(dev_batches[i % n_rot])
+        ema.step(cfg.SEMISUPNET.EMA_KEEP_RATE)
+        return out
+
+    # pinned result buffers of the end-to-end arm (what a trainer reads back: the pseudo-labels of every image)
+    T = cfg.TEST.DETECTIONS_PER_IMAGE
+    res_host = {"boxes": torch.empty((B, T, 4), dtype=torch.float32).pin_memory(), "scores": torch.empty((B, T), dtype=torch.float32).pin_memory(),
+                "classes": torch.empty((B, T), dtype=torch.int64).pin_memory()}
+    d2h_bytes = sum(t.numel() * t.element_size() for t in res_host.values()) + 2 * B * 4 + 2 * B * 4  # + the two count reads
+    h2d_bytes = host_batches[0].numel()
+
+    def step_e2e(i):
+        imgs = host_batches[i % n_rot].to(dev, non_blocking=True)
+        _, dets, pl = pseudo_label(imgs)
+        batch = dets[0]._sfod_batch
+        res_host["boxes"].copy_(batch.boxes, non_blocking=True)
+        res_host["scores"].copy_(batch.scores, non_blocking=True)
+        res_host["classes"].copy_(batch.classes, non_blocking=True)
+        ema.step(cfg.SEMISUPNET.EMA_KEEP_RATE)
+        torch.cuda.current_stream().synchronize()
+        return _, dets, pl
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, with_timers=False):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.launch_count()
+        if with_timers:
+            ops.timers.start()
+        e0.record()
+        for i in range(steps):
+            out = fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        ktimes = ops.timers.stop() if with_timers else {}
+        launches = ops.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, ktimes, out
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if args.profiler_range:
+        torch.cuda.profiler.start()
+    ms, launches, ktimes, out = timed(step_resident, args.steps, with_timers=True)
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
+    clocks = sampler.result()
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+
+    value = world * B * args.steps / (ms / 1e3)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+
+    # ---- per-kernel algorithmic bytes of one step (DESIGN.md "Algorithmic bytes"), fp32
+    peak, peak_src = peaks()
+    # activation elements entering the 13 BN layers of VGG16 at 600x1200 (per image): SURVEY.md App. C = 194 342 400
+    hw = [(600, 1200)] * 2 + [(300, 600)] * 2 + [(150, 300)] * 3 + [(75, 150)] * 3 + [(37, 75)] * 3
+    ch = [64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512]
+    bn_elems = sum(c * h * w for c, (h, w) in zip(ch, hw)) * B
+    R = sum(len(p) for p in out[0])          # proposals actually pooled / post-processed in the last step
+    Cf, Hf, Wf = 512, IMAGE_HW[0] // 32, IMAGE_HW[1] // 32
+    hwa = Hf * Wf * 15
+    alg = {
+        "bn_finalize_apply": 8.0 * bn_elems,                                  # read x + write y
+        "bn_partial_stats": 4.0 * bn_elems,                                   # read x
+        "ema_multi_tensor": 12.0 * ema.numel,                                 # read student, read teacher, write teacher
+        "roi_align_fwd": 4.0 * (B * Cf * Hf * Wf + 5 * R + 49 * R * Cf),      # feature map + rois in, (R, C, 7, 7) out
+        "rpn_select": B * 20.0 * hwa + 20.0 * R,                              # logits + deltas in, boxes + logit out
+        "frcnn_postprocess": 4.0 * R * (4 + 4 * NUM_CLASSES + NUM_CLASSES + 1) + B * T * 28.0,
+    }
+    kernels = {}
+    for tag, (calls, tot_ms) in sorted(ktimes.items()):
+        per_step_ms = tot_ms / args.steps
+        rec = {"calls_per_step": calls / args.steps, "ms_per_step": round(per_step_ms, 4)}
+        if tag in alg and per_step_ms > 0:
+            gbs = alg[tag] / (per_step_ms * 1e-3) / 1e9
+            rec.update({"alg_MB_per_step": round(alg[tag] / 1e6, 2), "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)})
+        kernels[tag] = rec
+    hot_ms = sum(v["ms_per_step"] for v in kernels.values())
+
+    dominant = max((t for t in kernels if "GBps" in kernels[t]), key=lambda t: kernels[t]["ms_per_step"], default=None)
+    roofline = None
+    if dominant is not None:
+        k = kernels[dominant]
+        per_launch_ms = k["ms_per_step"] / k["calls_per_step"]
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": k["GBps"], "peak": peak, "unit": "GB/s", "frac": k["frac_of_peak"],
+                    "traffic": None, "peak_source": peak_src, "avg_call_ms": round(per_launch_ms, 4),
+                    "alg_bytes_per_step": alg[dominant], "note": "CUDA events around the C-ABI call, inside the timed region"}
+
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_gpu": B, "global_batch": B * world, "image_hw": list(IMAGE_HW),
+                       "num_classes": NUM_CLASSES, "parallelism": f"dp{world} (images sharded per GPU, replicated teacher, no data-path collective)",
+                       "library_math": "cuDNN/cuBLAS " + ("TF32 allowed" if args.tf32 else "strict fp32 (TF32 off)"),
+                       "backbone_layout": "NHWC" if args.channels_last else "NCHW",
+                       "l2": f"inputs larger than L2: {n_rot} rotating input batches, per-step activation footprint "
+                             f"{4.0 * bn_elems / 1e9:.1f} GB per BN pass >> 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "kernels": kernels,
+            "hot_path": {"ms_per_step": round(hot_ms, 3), "share_of_step": round(hot_ms / (ms / args.steps), 4),
+                         "note": "sum of the event-timed C-ABI calls; the rest of the step is cuDNN conv / cuBLAS FC / torch glue"},
+            "proposals_last_step": [len(p) for p in out[0]],
+            "detections_last_step": [len(p) for p in out[1]],
+            "pseudo_labels_last_step": [len(p) for p in out[2]]}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            _, info, _, _, _ = cpu_reference_run(1, 1, 40.0)
+            line["cpu_baseline"] = info
+        except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -45,6 +45,9 @@ enum sfod_dtype { SFOD_F32 = 0, SFOD_I64 = 1 };
 
 int sfod_abi_version(void);
 const char *sfod_status_string(int status);
+/* Number of kernel launches the library has issued in this process so far (diagnostic, monotonically
+ * increasing; bench.py reports the difference across its timed region as "gpu_launches"). */
+uint64_t sfod_debug_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
  * Mean-teacher EMA.  Replaces the per-tensor loop of

@@ -40,6 +40,7 @@ class FrcnnParams(C.Structure):
 SIGNATURES = {
     "sfod_abi_version": (C.c_int, []),
     "sfod_status_string": (C.c_char_p, [C.c_int]),
+    "sfod_debug_launch_count": (C.c_uint64, []),
     "sfod_ema_plan_chunks": (C.c_int64, [C.POINTER(EmaTensor), C.c_int]),
     "sfod_ema_plan_bytes": (C.c_size_t, [C.c_int64]),
     "sfod_ema_plan_build": (C.c_int, [C.POINTER(EmaTensor), C.c_int, c_ptr, C.c_size_t]),

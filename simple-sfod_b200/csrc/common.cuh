@@ -14,8 +14,13 @@
     if (_e != cudaSuccess) return SFOD_ERR_CUDA_BASE + (int)_e;    \
   } while (0)
 
+// Diagnostic launch counter (the only process-wide state of the library; monotonically increasing, never read by
+// any kernel path): every kernel launch of the library passes through SFOD_LAUNCH_CHECK exactly once.
+void sfod_count_launch();
+
 #define SFOD_LAUNCH_CHECK()                                        \
   do {                                                             \
+    sfod_count_launch();                                           \
     cudaError_t _e = cudaGetLastError();                           \
     if (_e != cudaSuccess) return SFOD_ERR_CUDA_BASE + (int)_e;    \
   } while (0)

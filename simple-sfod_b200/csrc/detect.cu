@@ -322,6 +322,10 @@ SFOD_API int sfod_threshold_select(const float *values, const int32_t *counts_de
   return SFOD_OK;
 }
 
+static unsigned long long g_sfod_launches = 0;
+void sfod_count_launch() { __atomic_fetch_add(&g_sfod_launches, 1ull, __ATOMIC_RELAXED); }
+SFOD_API uint64_t sfod_debug_launch_count(void) { return __atomic_load_n(&g_sfod_launches, __ATOMIC_RELAXED); }
+
 SFOD_API int sfod_abi_version(void) { return 1; }
 
 SFOD_API const char *sfod_status_string(int status) {

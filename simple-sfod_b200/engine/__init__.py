@@ -1,0 +1,5 @@
+"""Host-side mirror of the trainer-level hot-path functions of the reference (reference daod/engine/trainers/*)."""
+from .pseudo_label import process_pseudo_label, threshold_bbox  # noqa: F401
+from .ema import TeacherEMA, update_teacher_model  # noqa: F401
+from .adabn import adabn_refinement, recursive_traversal, reset_bn_stats, test_refinement  # noqa: F401
+from .sharding import images_per_rank, shard_range  # noqa: F401

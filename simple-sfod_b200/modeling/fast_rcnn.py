@@ -1,0 +1,178 @@
+"""Fast R-CNN output layers with the inference half on the fused sm_100a post-processing call.
+
+``FastRCNNOutputLayers`` mirrors detectron2's class; ``inference`` -- reached from reference
+daod/modeling/roi_heads/source_free_adaptive_teacher_roi_heads.py:161 -- is ONE call into libsfod_b200 for all images:
+softmax + class-specific decode + clip + ``score > thresh`` + per-class NMS + top-k (the per-image body is on disk at
+reference daod/modeling/roi_heads/fast_rcnn.py:108-142), and the same call already counts the detections above the
+pseudo-label threshold (``threshold_bbox``, reference daod/engine/trainers/source_free_adaptive_teacher.py:167-181).
+``SourceFreeFastRCNNOutputLayers.convert_bbox_scores`` is the reference's no-NMS sibling
+(reference daod/modeling/roi_heads/source_free_fast_rcnn.py:15-147).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from ..structures import Boxes, Instances, ShapeSpec
+from .box_regression import Box2BoxTransform
+
+
+class DetectionBatch:
+    """Device-side result of the fused post-processing of one batch (padded to ``topk`` per image)."""
+
+    def __init__(self, out: Dict[str, Tensor], image_sizes, pseudo_thresh: float):
+        self.boxes, self.scores, self.classes, self.rows = out["boxes"], out["scores"], out["classes"], out["rows"]
+        self.count, self.pseudo_count = out["count"], out["pseudo_count"]
+        self.image_sizes = list(image_sizes)
+        self.pseudo_thresh = pseudo_thresh
+        self._host: Optional[List[List[int]]] = None
+
+    def host_counts(self) -> List[List[int]]:
+        """[[detections per image], [pseudo-labels per image]] -- the one device->host read of the batch."""
+        if self._host is None:
+            self._host = torch.stack([self.count, self.pseudo_count]).cpu().tolist()
+        return self._host
+
+    def instances(self) -> Tuple[List[Instances], List[Tensor]]:
+        det, _ = self.host_counts()
+        res, kept = [], []
+        for i, size in enumerate(self.image_sizes):
+            k = det[i]
+            r = Instances(size)
+            r.pred_boxes = Boxes(self.boxes[i, :k])
+            r.scores = self.scores[i, :k]
+            r.pred_classes = self.classes[i, :k]
+            res.append(r)
+            kept.append(self.rows[i, :k])
+        return res, kept
+
+    def pseudo_labels(self) -> List[Instances]:
+        """threshold_bbox(proposal_type='roih') of every image: detections are score-descending, so the set with
+        ``score > thres`` is the prefix of length pseudo_count."""
+        _, ps = self.host_counts()
+        res = []
+        for i, size in enumerate(self.image_sizes):
+            k = ps[i]
+            r = Instances(size)
+            r.gt_boxes = Boxes(self.boxes[i, :k])
+            r.gt_classes = self.classes[i, :k]
+            r.scores = self.scores[i, :k]
+            res.append(r)
+        return res
+
+
+class FastRCNNOutputLayers(nn.Module):
+    """detectron2.modeling.roi_heads.fast_rcnn.FastRCNNOutputLayers: two linear layers (K+1 scores, 4K deltas)."""
+
+    def __init__(self, cfg_or_shape, input_shape: Optional[ShapeSpec] = None, *, box2box_transform: Box2BoxTransform = None,
+                 num_classes: int = None, test_score_thresh: float = 0.0, test_nms_thresh: float = 0.5,
+                 test_topk_per_image: int = 100, cls_agnostic_bbox_reg: bool = False, pseudo_label_thresh: float = 0.8):
+        super().__init__()
+        if hasattr(cfg_or_shape, "MODEL"):
+            cfg = cfg_or_shape
+            box2box_transform = Box2BoxTransform(weights=cfg.MODEL.ROI_BOX_HEAD.BBOX_REG_WEIGHTS)
+            num_classes = cfg.MODEL.ROI_HEADS.NUM_CLASSES
+            cls_agnostic_bbox_reg = cfg.MODEL.ROI_BOX_HEAD.CLS_AGNOSTIC_BBOX_REG
+            test_score_thresh = cfg.MODEL.ROI_HEADS.SCORE_THRESH_TEST
+            test_nms_thresh = cfg.MODEL.ROI_HEADS.NMS_THRESH_TEST
+            test_topk_per_image = cfg.TEST.DETECTIONS_PER_IMAGE
+            pseudo_label_thresh = cfg.SEMISUPNET.BBOX_THRESHOLD
+        else:
+            input_shape = cfg_or_shape
+        if isinstance(input_shape, int):
+            input_shape = ShapeSpec(channels=input_shape)
+        self.num_classes = num_classes
+        input_size = input_shape.channels * (input_shape.width or 1) * (input_shape.height or 1)
+        self.cls_score = nn.Linear(input_size, num_classes + 1)
+        num_bbox_reg_classes = 1 if cls_agnostic_bbox_reg else num_classes
+        box_dim = len(box2box_transform.weights)
+        self.bbox_pred = nn.Linear(input_size, num_bbox_reg_classes * box_dim)
+        nn.init.normal_(self.cls_score.weight, std=0.01)
+        nn.init.normal_(self.bbox_pred.weight, std=0.001)
+        for l in (self.cls_score, self.bbox_pred):
+            nn.init.constant_(l.bias, 0)
+        self.box2box_transform = box2box_transform
+        self.test_score_thresh = test_score_thresh
+        self.test_nms_thresh = test_nms_thresh
+        self.test_topk_per_image = test_topk_per_image
+        self.pseudo_label_thresh = pseudo_label_thresh
+
+    def forward(self, x: Tensor) -> Tuple[Tensor, Tensor]:
+        if x.dim() > 2:
+            x = torch.flatten(x, start_dim=1)
+        return self.cls_score(x), self.bbox_pred(x)
+
+    def losses(self, predictions, proposals):
+        raise NotImplementedError("Fast R-CNN losses belong to the student's training step (SURVEY.md 8f rank 1)")
+
+    def predict_boxes(self, predictions: Tuple[Tensor, Tensor], proposals: List[Instances]) -> Tuple[Tensor, ...]:
+        if not len(proposals):
+            return ()
+        _, proposal_deltas = predictions
+        num_prop_per_image = [len(p) for p in proposals]
+        proposal_boxes = torch.cat([p.proposal_boxes.tensor for p in proposals], dim=0)
+        return self.box2box_transform.apply_deltas(proposal_deltas, proposal_boxes).split(num_prop_per_image)
+
+    def predict_probs(self, predictions: Tuple[Tensor, Tensor], proposals: List[Instances]) -> Tuple[Tensor, ...]:
+        scores, _ = predictions
+        num_inst_per_image = [len(p) for p in proposals]
+        return ops.softmax_lastdim(scores).split(num_inst_per_image, dim=0)
+
+    @torch.no_grad()
+    def inference_batch(self, predictions: Tuple[Tensor, Tensor], proposals: List[Instances],
+                        pseudo_thresh: Optional[float] = None) -> DetectionBatch:
+        """The fused call; nothing is read back to the host until the caller asks for Instances."""
+        scores, proposal_deltas = predictions
+        rows = [len(p) for p in proposals]
+        image_sizes = [p.image_size for p in proposals]
+        proposal_boxes = torch.cat([p.proposal_boxes.tensor for p in proposals], dim=0)
+        thr = self.pseudo_label_thresh if pseudo_thresh is None else pseudo_thresh
+        out = ops.frcnn_postprocess(scores, proposal_deltas, proposal_boxes, rows, image_sizes,
+                                    weights=self.box2box_transform.weights, scale_clamp=self.box2box_transform.scale_clamp,
+                                    score_thresh=self.test_score_thresh, nms_thresh=self.test_nms_thresh,
+                                    topk=self.test_topk_per_image, pseudo_thresh=thr)
+        return DetectionBatch(out, image_sizes, thr)
+
+    def inference(self, predictions: Tuple[Tensor, Tensor], proposals: List[Instances]):
+        """d2 FastRCNNOutputLayers.inference -> (List[Instances{pred_boxes, scores, pred_classes}], List[kept row indices])."""
+        batch = self.inference_batch(predictions, proposals)
+        instances, kept = batch.instances()
+        for i, inst in enumerate(instances):  # keeps the fused pseudo-label counts reachable from the d2-shaped result
+            inst._sfod_batch, inst._sfod_index = batch, i
+        return instances, kept
+
+
+class SourceFreeFastRCNNOutputLayers(FastRCNNOutputLayers):
+    """reference daod/modeling/roi_heads/source_free_fast_rcnn.py:14-147."""
+
+    @torch.no_grad()
+    def convert_bbox_scores(self, predictions, proposals):
+        """Decode + softmax + clip, ``scores > 0`` and NO NMS: dense per-class instances for ``bpc_loss``
+        (reference source_free_fast_rcnn.py:82-147).  Decode and softmax run on the sm_100a kernels; the boolean-mask
+        gathers of this student-side helper are plain torch indexing."""
+        boxes = self.predict_boxes(predictions, proposals)
+        scores = self.predict_probs(predictions, proposals)
+        image_shapes = [x.image_size for x in proposals]
+        results, kept = [], []
+        for b, s, shape in zip(boxes, scores, image_shapes):
+            valid_mask = torch.isfinite(b).all(dim=1) & torch.isfinite(s).all(dim=1)
+            if not valid_mask.all():
+                b, s = b[valid_mask], s[valid_mask]
+            s = s[:, :-1]
+            k = b.shape[1] // 4
+            bx = Boxes(b.reshape(-1, 4))
+            bx.clip(shape)
+            b3 = bx.tensor.view(-1, k, 4)
+            filter_mask = s > 0
+            filter_inds = filter_mask.nonzero()
+            bsel = b3[filter_inds[:, 0], 0] if k == 1 else b3[filter_mask]
+            result = Instances(shape)
+            result.pred_boxes = Boxes(bsel)
+            result.scores = s[filter_mask]
+            result.pred_classes = filter_inds[:, 1]
+            results.append(result)
+            kept.append(filter_inds[:, 0])
+        return results, kept

@@ -1,0 +1,105 @@
+"""Teacher-side meta-architecture: the ``unsup_data_weak`` branch of the reference's
+``SourceFreeAdaptiveTeacherGeneralizedRCNN`` (reference daod/modeling/meta_arch/source_free_adaptive_teacher_rcnn.py:310-339)
+plus detectron2's ``GeneralizedRCNN.inference``.  This is the caller of the hot path: preprocess ->
+backbone (cuDNN convs + native BN) -> PseudoLabRPN -> ROI heads -> detections; the pseudo-label filter is fused in.
+The student-side branches (``supervised``, ``supervised_target``, ``domain_classifier``) are training-step
+orchestration (out of scope) and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+from torch import Tensor, nn
+
+from ..registry import META_ARCH_REGISTRY, build_backbone, build_proposal_generator, build_roi_heads
+from ..structures import ImageList, Instances
+
+
+class _ImageDomainClassifier(nn.Module):
+    """Parameter layout of the reference's image-level discriminator (reference daod/modeling/dann/dann.py:10-29).  It is not
+    evaluated on the teacher's pseudo-labelling branch; it exists so that the teacher/student state_dicts -- and therefore
+    the EMA update (47 636 547 elements) -- have the reference's keys and sizes."""
+
+    def __init__(self, in_channels: int, ndf1: int = 256, ndf2: int = 128):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, ndf1, 3, padding=1)
+        self.conv2 = nn.Conv2d(ndf1, ndf2, 3, padding=1)
+        self.conv3 = nn.Conv2d(ndf2, ndf2, 3, padding=1)
+        self.classifier = nn.Conv2d(ndf2, 1, 3, padding=1)
+
+    def forward(self, x: Tensor) -> Tensor:
+        act = nn.functional.leaky_relu
+        return self.classifier(act(self.conv3(act(self.conv2(act(self.conv1(x), 0.2)), 0.2)), 0.2))
+
+
+class _InstanceDomainClassifier(nn.Module):
+    """Parameter layout of the reference's instance-level discriminator (reference daod/modeling/dann/dann.py:97-155)."""
+
+    def __init__(self, in_channels: int, levels: List[str]):
+        super().__init__()
+        for level in levels:
+            for i, (a, b) in enumerate(((in_channels, 1024), (1024, 1024), (1024, 1)), start=1):
+                fc = nn.Linear(a, b)
+                nn.init.normal_(fc.weight, std=0.01)
+                nn.init.constant_(fc.bias, 0)
+                self.add_module("da_ins_fc{}_level_{}".format(i, level), fc)
+
+
+@META_ARCH_REGISTRY.register()
+class SourceFreeAdaptiveTeacherGeneralizedRCNN(nn.Module):
+    def __init__(self, cfg=None, *, backbone: nn.Module = None, proposal_generator: nn.Module = None, roi_heads: nn.Module = None,
+                 pixel_mean=(103.530, 116.280, 123.675), pixel_std=(1.0, 1.0, 1.0), dis_type: Optional[str] = None,
+                 ins_dc: bool = False):
+        super().__init__()
+        if cfg is not None:
+            dis_type, ins_dc = cfg.SEMISUPNET.DIS_TYPE, cfg.SEMISUPNET.INS_DC
+            backbone = build_backbone(cfg)
+            proposal_generator = build_proposal_generator(cfg, backbone.output_shape())
+            roi_heads = build_roi_heads(cfg, backbone.output_shape())
+            pixel_mean, pixel_std = cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD
+        self.backbone, self.proposal_generator, self.roi_heads = backbone, proposal_generator, roi_heads
+        self.register_buffer("pixel_mean", torch.tensor(pixel_mean).view(-1, 1, 1), False)
+        self.register_buffer("pixel_std", torch.tensor(pixel_std).view(-1, 1, 1), False)
+        assert self.pixel_mean.shape == self.pixel_std.shape
+        self.dis_type, self.ins_dc = dis_type, ins_dc
+        if dis_type is not None and dis_type in getattr(backbone, "_out_feature_channels", {}):
+            self.DC_img = _ImageDomainClassifier(backbone._out_feature_channels[dis_type])  # reference ...rcnn.py:68
+            if ins_dc:
+                self.DC_ins = _InstanceDomainClassifier(roi_heads.box_predictor.cls_score.in_features, [dis_type])  # :71
+
+    @property
+    def device(self) -> torch.device:
+        return self.pixel_mean.device
+
+    def preprocess_image(self, batched_inputs: List[Dict[str, Tensor]]) -> ImageList:
+        """d2 GeneralizedRCNN.preprocess_image (reference ...rcnn.py:92-104): normalise, pad, batch."""
+        images = [x["image"].to(self.device, non_blocking=True) for x in batched_inputs]
+        images = [(x - self.pixel_mean) / self.pixel_std for x in images]
+        return ImageList.from_tensors(images, self.backbone.size_divisibility)
+
+    def preprocess_batch(self, images: Tensor) -> ImageList:
+        """Same arithmetic for an already batched (N, 3, H, W) tensor of equally sized images (one launch)."""
+        x = (images.to(self.device, non_blocking=True) - self.pixel_mean) / self.pixel_std
+        return ImageList(x, [tuple(images.shape[-2:])] * images.shape[0])
+
+    def forward(self, batched_inputs, branch: str = "supervised", given_proposals=None, val_mode: bool = False):
+        if not self.training and not val_mode:
+            return self.inference(batched_inputs)
+        if branch != "unsup_data_weak":
+            raise NotImplementedError(f"branch {branch!r} is the student's training step (out of scope, SURVEY.md section 2 row 6); "
+                                      "the B200 path implements the teacher's 'unsup_data_weak' branch")
+        images = self.preprocess_batch(batched_inputs) if isinstance(batched_inputs, Tensor) else self.preprocess_image(batched_inputs)
+        features = self.backbone(images.tensor)
+        proposals_rpn, _ = self.proposal_generator(images, features, None, compute_loss=False)
+        proposals_roih, _ = self.roi_heads(images, features, proposals_rpn, targets=None, compute_loss=False, branch=branch)
+        return {}, proposals_rpn, proposals_roih
+
+    @torch.no_grad()
+    def inference(self, batched_inputs, detected_instances=None, do_postprocess: bool = False):
+        assert not self.training
+        images = self.preprocess_batch(batched_inputs) if isinstance(batched_inputs, Tensor) else self.preprocess_image(batched_inputs)
+        features = self.backbone(images.tensor)
+        proposals, _ = self.proposal_generator(images, features, None)
+        results, _ = self.roi_heads(images, features, proposals, None, compute_loss=False)
+        return [{"instances": r} for r in results]

@@ -1,0 +1,201 @@
+"""RPN plugins of the reference (``PseudoLabRPN`` / ``DARPN``, reference daod/modeling/proposal_generator/rpn.py:10-113)
+on top of a detectron2-shaped ``RPN`` base whose ``predict_proposals`` is ONE fused call into libsfod_b200
+(decode + per-image top-k + clip + non-empty filter + NMS + post top-k for all images).
+
+The loss half of the reference's forward (``label_and_sample_anchors`` + ``losses``, rpn.py:43-50) belongs to the
+student's training step, which SURVEY.md 8(f) ranks as the first "next" row; it is not part of the pseudo-labelling
+path and raises ``NotImplementedError`` here.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from ..registry import PROPOSAL_GENERATOR_REGISTRY, RPN_HEAD_REGISTRY
+from ..structures import Boxes, ImageList, Instances, ShapeSpec
+from .anchor_generator import DefaultAnchorGenerator
+from .box_regression import Box2BoxTransform
+
+
+@RPN_HEAD_REGISTRY.register()
+class StandardRPNHead(nn.Module):
+    """detectron2 StandardRPNHead: 3x3 conv + ReLU, then 1x1 objectness (A) and 1x1 anchor deltas (4A).
+    The convolutions stay on cuDNN (BASELINE.json north_star)."""
+
+    def __init__(self, cfg_or_channels=None, input_shape: List[ShapeSpec] = None, *, in_channels: int = None,
+                 num_anchors: int = None, box_dim: int = 4):
+        super().__init__()
+        if in_channels is None and hasattr(cfg_or_channels, "MODEL"):
+            cfg = cfg_or_channels
+            chans = [s.channels for s in input_shape]
+            assert len(set(chans)) == 1, "Each level must have the same channel!"
+            in_channels = chans[0]
+            ag = DefaultAnchorGenerator(cfg, input_shape)
+            assert len(set(ag.num_anchors)) == 1, "Each level must have the same number of anchors per spatial position"
+            num_anchors, box_dim = ag.num_anchors[0], ag.box_dim
+        elif in_channels is None:
+            in_channels = cfg_or_channels
+        self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
+        self.objectness_logits = nn.Conv2d(in_channels, num_anchors, kernel_size=1, stride=1)
+        self.anchor_deltas = nn.Conv2d(in_channels, num_anchors * box_dim, kernel_size=1, stride=1)
+        for layer in (self.conv, self.objectness_logits, self.anchor_deltas):
+            nn.init.normal_(layer.weight, std=0.01)
+            nn.init.constant_(layer.bias, 0)
+
+    def forward(self, features: List[Tensor]):
+        pred_objectness_logits, pred_anchor_deltas = [], []
+        for x in features:
+            t = torch.relu(self.conv(x))
+            pred_objectness_logits.append(self.objectness_logits(t))
+            pred_anchor_deltas.append(self.anchor_deltas(t))
+        return pred_objectness_logits, pred_anchor_deltas
+
+
+class RPN(nn.Module):
+    """detectron2.modeling.proposal_generator.RPN (inference half)."""
+
+    def __init__(self, cfg=None, input_shape: Dict[str, ShapeSpec] = None, *, in_features: List[str] = None, head: nn.Module = None,
+                 anchor_generator: nn.Module = None, box2box_transform: Box2BoxTransform = None,
+                 pre_nms_topk: Tuple[int, int] = (12000, 6000), post_nms_topk: Tuple[int, int] = (2000, 1000),
+                 nms_thresh: float = 0.7, min_box_size: float = 0.0, loss_weight=1.0):
+        super().__init__()
+        if cfg is not None:
+            in_features = cfg.MODEL.RPN.IN_FEATURES
+            shapes = [input_shape[f] for f in in_features]
+            anchor_generator = DefaultAnchorGenerator(cfg, shapes)
+            head = RPN_HEAD_REGISTRY.get(cfg.MODEL.RPN.HEAD_NAME)(cfg, shapes)
+            box2box_transform = Box2BoxTransform(weights=cfg.MODEL.RPN.BBOX_REG_WEIGHTS)
+            pre_nms_topk = (cfg.MODEL.RPN.PRE_NMS_TOPK_TRAIN, cfg.MODEL.RPN.PRE_NMS_TOPK_TEST)
+            post_nms_topk = (cfg.MODEL.RPN.POST_NMS_TOPK_TRAIN, cfg.MODEL.RPN.POST_NMS_TOPK_TEST)
+            nms_thresh = cfg.MODEL.RPN.NMS_THRESH
+            min_box_size = cfg.MODEL.PROPOSAL_GENERATOR.MIN_SIZE
+            loss_weight = {"loss_rpn_cls": cfg.MODEL.RPN.LOSS_WEIGHT,
+                           "loss_rpn_loc": cfg.MODEL.RPN.BBOX_REG_LOSS_WEIGHT * cfg.MODEL.RPN.LOSS_WEIGHT}
+        self.in_features = in_features
+        self.rpn_head = head
+        self.anchor_generator = anchor_generator
+        self.box2box_transform = box2box_transform
+        self.pre_nms_topk = {True: pre_nms_topk[0], False: pre_nms_topk[1]}
+        self.post_nms_topk = {True: post_nms_topk[0], False: post_nms_topk[1]}
+        self.nms_thresh = nms_thresh
+        self.min_box_size = float(min_box_size)
+        if isinstance(loss_weight, float):
+            loss_weight = {"loss_rpn_cls": loss_weight, "loss_rpn_loc": loss_weight}
+        self.loss_weight = loss_weight
+
+    # ------------------------------------------------------------------ training half: SURVEY.md 8(f) rank 1
+    def label_and_sample_anchors(self, anchors, gt_instances):
+        raise NotImplementedError("RPN anchor labelling/sampling belongs to the student's training step "
+                                  "(SURVEY.md 8f rank 1); the B200 path implements proposal prediction")
+
+    def losses(self, *args, **kwargs):
+        raise NotImplementedError("RPN losses belong to the student's training step (SURVEY.md 8f rank 1)")
+
+    # ------------------------------------------------------------------ inference half: the hot path
+    def _flatten_head_outputs(self, pred_objectness_logits: List[Tensor], pred_anchor_deltas: List[Tensor]):
+        """reference rpn.py:28-41: (N, A, Hi, Wi) -> (N, Hi*Wi*A); (N, A*B, Hi, Wi) -> (N, Hi*Wi*A, B)."""
+        B = self.anchor_generator.box_dim
+        logits = [s.permute(0, 2, 3, 1).flatten(1) for s in pred_objectness_logits]
+        deltas = [x.view(x.shape[0], -1, B, x.shape[-2], x.shape[-1]).permute(0, 3, 4, 1, 2).flatten(1, -2) for x in pred_anchor_deltas]
+        return logits, deltas
+
+    def select_proposals(self, pred_objectness_logits: List[Tensor], pred_anchor_deltas: List[Tensor], image_sizes,
+                         feat_hw: Optional[List[Tuple[int, int]]] = None, anchors: Optional[List[Boxes]] = None):
+        """Device-side result of ``predict_proposals`` without the host read of the counts:
+        (boxes (N, P, 4), logits (N, P), src_index (N, P), count (N) int32, invalid (N) int32)."""
+        if len(pred_objectness_logits) != 1:
+            raise NotImplementedError("multi-level RPN selection: every shipped config is single-level "
+                                      "(RPN.IN_FEATURES ['vgg4'] / ['res4'], SURVEY.md 8a-a3)")
+        ag = self.anchor_generator
+        kw = {}
+        if feat_hw is not None and isinstance(ag, DefaultAnchorGenerator) and ag.num_anchors[0] <= 64:
+            # our own forward: the grid is known, the kernel regenerates the anchors in closed form (0 B of traffic)
+            kw = dict(cell_anchors=ag.host_cell_anchors[0], feat_hw=feat_hw[0], stride=ag.strides[0], anchor_offset=ag.offset)
+        else:
+            kw = dict(anchors=anchors[0].tensor)
+        return ops.rpn_select(pred_objectness_logits[0], pred_anchor_deltas[0], image_sizes,
+                              weights=self.box2box_transform.weights, scale_clamp=self.box2box_transform.scale_clamp,
+                              pre_nms_topk=self.pre_nms_topk[self.training], post_nms_topk=self.post_nms_topk[self.training],
+                              nms_thresh=self.nms_thresh, min_box_size=self.min_box_size, **kw)
+
+    def _closed_form_anchors(self) -> bool:
+        ag = self.anchor_generator
+        return isinstance(ag, DefaultAnchorGenerator) and ag.num_features == 1 and ag.num_anchors[0] <= 64
+
+    @torch.no_grad()
+    def predict_proposals(self, anchors: List[Boxes], pred_objectness_logits: List[Tensor], pred_anchor_deltas: List[Tensor],
+                          image_sizes: List[Tuple[int, int]], feat_hw: Optional[List[Tuple[int, int]]] = None) -> List[Instances]:
+        """d2 RPN.predict_proposals: List[Instances{proposal_boxes, objectness_logits}], score-descending."""
+        boxes, logits, _, count, invalid = self.select_proposals(pred_objectness_logits, pred_anchor_deltas, image_sizes, feat_hw, anchors)
+        host = torch.stack([count, invalid]).cpu().tolist()  # the one device->host read of the batch
+        if self.training and any(v > 0 for v in host[1]):
+            raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+        results = []
+        for i, image_size in enumerate(image_sizes):
+            k = host[0][i]
+            res = Instances(image_size)
+            res.proposal_boxes = Boxes(boxes[i, :k])
+            res.objectness_logits = logits[i, :k]
+            results.append(res)
+        return results
+
+    def forward(self, images: ImageList, features: Dict[str, Tensor], gt_instances: Optional[List[Instances]] = None):
+        feats = [features[f] for f in self.in_features]
+        anchors = self.anchor_generator(feats)
+        pred_objectness_logits, pred_anchor_deltas = self.rpn_head(feats)
+        feat_hw = [tuple(f.shape[-2:]) for f in feats]
+        pred_objectness_logits, pred_anchor_deltas = self._flatten_head_outputs(pred_objectness_logits, pred_anchor_deltas)
+        if self.training:
+            gt_labels, gt_boxes = self.label_and_sample_anchors(anchors, gt_instances)
+            losses = self.losses(anchors, pred_objectness_logits, gt_labels, pred_anchor_deltas, gt_boxes)
+        else:
+            losses = {}
+        proposals = self.predict_proposals(anchors, pred_objectness_logits, pred_anchor_deltas, images.image_sizes, feat_hw)
+        return proposals, losses
+
+
+@PROPOSAL_GENERATOR_REGISTRY.register()
+class PseudoLabRPN(RPN):
+    """reference daod/modeling/proposal_generator/rpn.py:10-58: an RPN that can skip its loss so that a
+    label-free teacher can emit proposals.  Same forward signature and return value."""
+
+    def forward(self, images: ImageList, features: Dict[str, Tensor], gt_instances: Optional[List[Instances]] = None,
+                compute_loss: bool = True, compute_val_loss: bool = False):
+        feats = [features[f] for f in self.in_features]
+        need_loss = (self.training and compute_loss) or compute_val_loss
+        # the selection kernel regenerates the anchor grid in closed form; the anchor tensor is only built when a loss needs it
+        anchors = self.anchor_generator(feats) if (need_loss or not self._closed_form_anchors()) else None
+        pred_objectness_logits, pred_anchor_deltas = self.rpn_head(feats)
+        feat_hw = [tuple(f.shape[-2:]) for f in feats]
+        pred_objectness_logits, pred_anchor_deltas = self._flatten_head_outputs(pred_objectness_logits, pred_anchor_deltas)
+        if need_loss:
+            gt_labels, gt_boxes = self.label_and_sample_anchors(anchors, gt_instances)
+            losses = self.losses(anchors, pred_objectness_logits, gt_labels, pred_anchor_deltas, gt_boxes)
+            losses = {k: v * self.loss_weight.get(k, 1.0) for k, v in losses.items()}
+        else:  # inference
+            losses = {}
+        proposals = self.predict_proposals(anchors, pred_objectness_logits, pred_anchor_deltas, images.image_sizes, feat_hw)
+        return proposals, losses
+
+
+@PROPOSAL_GENERATOR_REGISTRY.register()
+class DARPN(RPN):
+    """reference daod/modeling/proposal_generator/rpn.py:61-113: an RPN that accepts unlabeled inputs -- losses only
+    when training AND ``gt_instances`` is given, proposals always."""
+
+    def forward(self, images: ImageList, features: Dict[str, Tensor], gt_instances: Optional[List[Instances]] = None):
+        feats = [features[f] for f in self.in_features]
+        anchors = self.anchor_generator(feats)
+        pred_objectness_logits, pred_anchor_deltas = self.rpn_head(feats)
+        feat_hw = [tuple(f.shape[-2:]) for f in feats]
+        pred_objectness_logits, pred_anchor_deltas = self._flatten_head_outputs(pred_objectness_logits, pred_anchor_deltas)
+        if self.training and gt_instances is not None:
+            gt_labels, gt_boxes = self.label_and_sample_anchors(anchors, gt_instances)
+            losses = self.losses(anchors, pred_objectness_logits, gt_labels, pred_anchor_deltas, gt_boxes)
+        else:
+            losses = {}
+        proposals = self.predict_proposals(anchors, pred_objectness_logits, pred_anchor_deltas, images.image_sizes, feat_hw)
+        return proposals, losses

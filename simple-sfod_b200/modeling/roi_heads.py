@@ -1,0 +1,186 @@
+"""ROI-heads plugins of the reference on the sm_100a kernels.
+
+``SourceFreeAdaptiveTeacherStandardROIHeads`` (reference daod/modeling/roi_heads/source_free_adaptive_teacher_roi_heads.py:25-215),
+its eval sibling (``..._eval.py:25-128``) and ``AdaptiveTeacherStandardROIHeads`` (reference adaptive_teacher_roi_heads.py:22-187)
+share one body: ROIPooler -> box head -> predictor, then either ``box_predictor.inference`` (the pseudo-labelling
+path implemented here: pooling, decode, per-class NMS, top-k all run in libsfod_b200) or the training losses.  Proposal
+labelling/sampling and the losses are the student's training step and raise NotImplementedError.
+The box-head FCs stay on cuBLAS (dense GEMMs are library work per BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from ..registry import ROI_BOX_HEAD_REGISTRY, ROI_HEADS_REGISTRY
+from ..structures import Boxes, ImageList, Instances, ShapeSpec
+from .fast_rcnn import FastRCNNOutputLayers, SourceFreeFastRCNNOutputLayers
+from .poolers import ROIPooler
+
+
+@ROI_BOX_HEAD_REGISTRY.register()
+class FastRCNNConvFCHead(nn.Sequential):
+    """detectron2 FastRCNNConvFCHead (conv layers optional, then FCs with ReLU); c2_xavier / c2_msra init."""
+
+    def __init__(self, cfg_or_shape, input_shape: Optional[ShapeSpec] = None, *, conv_dims: List[int] = None,
+                 fc_dims: List[int] = None, conv_norm: str = ""):
+        super().__init__()
+        if hasattr(cfg_or_shape, "MODEL"):
+            cfg = cfg_or_shape
+            conv_dims = [cfg.MODEL.ROI_BOX_HEAD.CONV_DIM] * cfg.MODEL.ROI_BOX_HEAD.NUM_CONV
+            fc_dims = [cfg.MODEL.ROI_BOX_HEAD.FC_DIM] * cfg.MODEL.ROI_BOX_HEAD.NUM_FC
+            conv_norm = cfg.MODEL.ROI_BOX_HEAD.NORM
+        else:
+            input_shape = cfg_or_shape
+        conv_dims, fc_dims = list(conv_dims or []), list(fc_dims or [])
+        assert len(conv_dims) + len(fc_dims) > 0
+        assert conv_norm == "", "normalised conv heads are not used by any shipped config"
+        self._output_size = (input_shape.channels, input_shape.height, input_shape.width)
+        self.conv_norm_relus, self.fcs = [], []
+        for k, conv_dim in enumerate(conv_dims):
+            conv = nn.Conv2d(self._output_size[0], conv_dim, kernel_size=3, padding=1)
+            nn.init.kaiming_normal_(conv.weight, mode="fan_out", nonlinearity="relu")
+            nn.init.constant_(conv.bias, 0)
+            self.add_module("conv{}".format(k + 1), conv)
+            self.add_module("conv_relu{}".format(k + 1), nn.ReLU())
+            self.conv_norm_relus.append(conv)
+            self._output_size = (conv_dim, self._output_size[1], self._output_size[2])
+        for k, fc_dim in enumerate(fc_dims):
+            if k == 0:
+                self.add_module("flatten", nn.Flatten())
+            fc = nn.Linear(int(np.prod(self._output_size)), fc_dim)
+            nn.init.kaiming_uniform_(fc.weight, a=1)  # c2_xavier_fill
+            nn.init.constant_(fc.bias, 0)
+            self.add_module("fc{}".format(k + 1), fc)
+            self.add_module("fc_relu{}".format(k + 1), nn.ReLU())
+            self.fcs.append(fc)
+            self._output_size = fc_dim
+
+    @property
+    def output_shape(self) -> ShapeSpec:
+        o = self._output_size
+        return ShapeSpec(channels=o) if isinstance(o, int) else ShapeSpec(channels=o[0], height=o[1], width=o[2])
+
+
+def build_box_head(cfg, input_shape: ShapeSpec):
+    """detectron2.modeling.roi_heads.box_head.build_box_head."""
+    return ROI_BOX_HEAD_REGISTRY.get(cfg.MODEL.ROI_BOX_HEAD.NAME)(cfg, input_shape)
+
+
+class _StandardROIHeadsBase(nn.Module):
+    """The slice of detectron2 StandardROIHeads the reference's subclasses rely on (box branch only: MASK_ON False)."""
+
+    predictor_cls = FastRCNNOutputLayers
+
+    def __init__(self, cfg=None, input_shape: Dict[str, ShapeSpec] = None, *, box_in_features: List[str] = None,
+                 box_pooler: ROIPooler = None, box_head: nn.Module = None, box_predictor: nn.Module = None,
+                 num_classes: int = None, batch_size_per_image: int = 512, positive_fraction: float = 0.25,
+                 proposal_append_gt: bool = True, train_on_pred_boxes: bool = False):
+        super().__init__()
+        if cfg is not None:
+            parts = self._init_box_head(cfg, input_shape)
+            box_in_features, box_pooler = parts["box_in_features"], parts["box_pooler"]
+            box_head, box_predictor = parts["box_head"], parts["box_predictor"]
+            num_classes = cfg.MODEL.ROI_HEADS.NUM_CLASSES
+            batch_size_per_image = cfg.MODEL.ROI_HEADS.BATCH_SIZE_PER_IMAGE
+            positive_fraction = cfg.MODEL.ROI_HEADS.POSITIVE_FRACTION
+            proposal_append_gt = cfg.MODEL.ROI_HEADS.PROPOSAL_APPEND_GT
+            train_on_pred_boxes = cfg.MODEL.ROI_BOX_HEAD.TRAIN_ON_PRED_BOXES
+        self.in_features = self.box_in_features = box_in_features
+        self.box_pooler, self.box_head, self.box_predictor = box_pooler, box_head, box_predictor
+        self.num_classes = num_classes
+        self.batch_size_per_image, self.positive_fraction = batch_size_per_image, positive_fraction
+        self.proposal_append_gt, self.train_on_pred_boxes = proposal_append_gt, train_on_pred_boxes
+
+    @classmethod
+    def _init_box_head(cls, cfg, input_shape):
+        """reference source_free_adaptive_teacher_roi_heads.py:28-66 (ROIPooler built at :42-47)."""
+        in_features = cfg.MODEL.ROI_HEADS.IN_FEATURES
+        pooler_resolution = cfg.MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION
+        pooler_scales = tuple(1.0 / input_shape[k].stride for k in in_features)
+        sampling_ratio = cfg.MODEL.ROI_BOX_HEAD.POOLER_SAMPLING_RATIO
+        pooler_type = cfg.MODEL.ROI_BOX_HEAD.POOLER_TYPE
+        in_channels = [input_shape[f].channels for f in in_features]
+        assert len(set(in_channels)) == 1, in_channels
+        in_channels = in_channels[0]
+        box_pooler = ROIPooler(output_size=pooler_resolution, scales=pooler_scales, sampling_ratio=sampling_ratio,
+                               pooler_type=pooler_type)
+        box_head = build_box_head(cfg, ShapeSpec(channels=in_channels, height=pooler_resolution, width=pooler_resolution))
+        if cfg.MODEL.ROI_HEADS.LOSS == "CrossEntropy":
+            box_predictor = cls.predictor_cls(cfg, box_head.output_shape)
+        else:
+            raise ValueError("Unknown ROI head loss.")
+        return {"box_in_features": in_features, "box_pooler": box_pooler, "box_head": box_head, "box_predictor": box_predictor}
+
+    def label_and_sample_proposals(self, proposals, targets, branch: str = ""):
+        raise NotImplementedError("proposal labelling/sampling belongs to the student's training step (SURVEY.md 8f rank 1)")
+
+    def _wants_loss(self, compute_loss: bool, compute_val_loss: bool) -> bool:
+        return (self.training and compute_loss) or compute_val_loss
+
+    def forward(self, images: ImageList, features: Dict[str, Tensor], proposals: List[Instances],
+                targets: Optional[List[Instances]] = None, compute_loss=True, branch="", compute_val_loss=False):
+        """reference source_free_adaptive_teacher_roi_heads.py:68-106."""
+        del images
+        if self.training and compute_loss:
+            assert targets
+            proposals = self.label_and_sample_proposals(proposals, targets, branch=branch)
+        elif compute_val_loss:
+            assert targets
+            tmp = self.proposal_append_gt
+            self.proposal_append_gt = False
+            proposals = self.label_and_sample_proposals(proposals, targets, branch=branch)
+            self.proposal_append_gt = tmp
+        del targets
+        if self._wants_loss(compute_loss, compute_val_loss):
+            return (proposals,) + tuple(self._forward_box(features, proposals, compute_loss, compute_val_loss, branch))
+        pred_instances, predictions = self._forward_box(features, proposals, compute_loss, compute_val_loss, branch)
+        return pred_instances, predictions
+
+    def _box_predictions(self, features: Dict[str, Tensor], proposals: List[Instances]):
+        feats = [features[f] for f in self.box_in_features]
+        box_features = self.box_pooler(feats, [x.proposal_boxes for x in proposals])  # reference ...roi_heads.py:117
+        box_features = self.box_head(box_features)
+        return box_features, self.box_predictor(box_features)
+
+    def _forward_box(self, features: Dict[str, Tensor], proposals: List[Instances], compute_loss: bool = True,
+                     compute_val_loss: bool = False, branch: str = ""):
+        box_features, predictions = self._box_predictions(features, proposals)
+        if self._wants_loss(compute_loss, compute_val_loss):
+            losses = self.box_predictor.losses(predictions, proposals)  # raises: SURVEY.md 8f rank 1
+            return losses, predictions, box_features
+        pred_instances, _ = self.box_predictor.inference(predictions, proposals)  # reference ...roi_heads.py:161
+        return pred_instances, predictions
+
+
+@ROI_HEADS_REGISTRY.register()
+class SourceFreeAdaptiveTeacherStandardROIHeads(_StandardROIHeadsBase):
+    predictor_cls = SourceFreeFastRCNNOutputLayers
+
+
+@ROI_HEADS_REGISTRY.register()
+class SourceFreeAdaptiveTeacherEvalStandardROIHeads(_StandardROIHeadsBase):
+    """reference ..._roi_heads_eval.py:25-128: identical, except that the loss switches ignore ``self.training``."""
+    predictor_cls = SourceFreeFastRCNNOutputLayers
+
+    def _wants_loss(self, compute_loss: bool, compute_val_loss: bool) -> bool:
+        return bool(compute_loss or compute_val_loss)
+
+    def forward(self, images, features, proposals, targets=None, compute_loss=True, branch="", compute_val_loss=False):
+        del images
+        if compute_loss:
+            assert targets
+            proposals = self.label_and_sample_proposals(proposals, targets, branch=branch)
+        del targets
+        if self._wants_loss(compute_loss, compute_val_loss):
+            return (proposals,) + tuple(self._forward_box(features, proposals, compute_loss, compute_val_loss, branch))
+        return self._forward_box(features, proposals, compute_loss, compute_val_loss, branch)
+
+
+@ROI_HEADS_REGISTRY.register()
+class AdaptiveTeacherStandardROIHeads(_StandardROIHeadsBase):
+    """reference adaptive_teacher_roi_heads.py:22-187 (plain FastRCNNOutputLayers predictor)."""
+    predictor_cls = FastRCNNOutputLayers

@@ -27,6 +27,54 @@ _ws_cache: Dict[Tuple[str, int], Tensor] = {}
 _small_cache: Dict[Tuple, Tensor] = {}
 
 
+# ---- optional per-call device timing (bench.py's roofline numbers): CUDA events recorded on the launching stream
+# around the C-ABI call, so they measure exactly the kernels the call enqueues.  Off by default (zero overhead).
+class KernelTimers:
+    def __init__(self):
+        self.enabled = False
+        self.records: Dict[str, List[Tuple[torch.cuda.Event, torch.cuda.Event]]] = {}
+
+    def start(self) -> None:
+        self.records = {}
+        self.enabled = True
+
+    def stop(self) -> Dict[str, Tuple[int, float]]:
+        """-> {tag: (number of calls, total milliseconds)}; synchronises."""
+        self.enabled = False
+        torch.cuda.synchronize()
+        out = {t: (len(ev), sum(a.elapsed_time(b) for a, b in ev)) for t, ev in self.records.items()}
+        self.records = {}
+        return out
+
+
+timers = KernelTimers()
+
+
+class _timed:
+    __slots__ = ("tag", "ev")
+
+    def __init__(self, tag: str):
+        self.tag = tag
+        self.ev = None
+
+    def __enter__(self):
+        if timers.enabled:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
+            timers.records.setdefault(self.tag, []).append(self.ev)
+        return False
+
+
+def launch_count() -> int:
+    """Kernel launches issued by libsfod_b200 in this process so far."""
+    return int(_lib.lib().sfod_debug_launch_count())
+
+
 def _stream(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
@@ -159,9 +207,10 @@ class _RoIAlignFn(torch.autograd.Function):
         if R > 0:
             with torch.cuda.device(dev):
                 ws = _workspace(dev, "roi", L.sfod_roi_align_fwd_workspace_bytes(N, Cc, H, W, layout, int(exact)))
-                check(L.sfod_roi_align_fwd(xin.data_ptr(), layout, r.data_ptr(), N, Cc, H, W, R, ph, pw, float(scale), int(sr),
-                                           int(aligned), int(exact), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
-                      "sfod_roi_align_fwd")
+                with _timed("roi_align_fwd"):
+                    check(L.sfod_roi_align_fwd(xin.data_ptr(), layout, r.data_ptr(), N, Cc, H, W, R, ph, pw, float(scale), int(sr),
+                                               int(aligned), int(exact), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
+                          "sfod_roi_align_fwd")
         ctx.save_for_backward(r)
         ctx.meta = (N, Cc, H, W, ph, pw, float(scale), int(sr), int(aligned), layout, x.dtype)
         return out.to(x.dtype)
@@ -177,8 +226,9 @@ class _RoIAlignFn(torch.autograd.Function):
         L = _lib.lib()
         with torch.cuda.device(dev):
             ws = _workspace(dev, "roi", L.sfod_roi_align_bwd_workspace_bytes(N, Cc, H, W, layout))
-            check(L.sfod_roi_align_bwd(g.data_ptr(), r.data_ptr(), N, Cc, H, W, r.shape[0], ph, pw, scale, sr, aligned,
-                                       gin.data_ptr(), layout, ws.data_ptr(), ws.numel(), _stream(dev)), "sfod_roi_align_bwd")
+            with _timed("roi_align_bwd"):
+                check(L.sfod_roi_align_bwd(g.data_ptr(), r.data_ptr(), N, Cc, H, W, r.shape[0], ph, pw, scale, sr, aligned,
+                                           gin.data_ptr(), layout, ws.data_ptr(), ws.numel(), _stream(dev)), "sfod_roi_align_bwd")
         return gin.to(dtype), None, None, None, None, None, None, None
 
 
@@ -330,9 +380,10 @@ def rpn_select(logits: Tensor, deltas: Tensor, image_sizes: Sequence[Tuple[int, 
         out_cnt = torch.empty((N,), dtype=torch.int32, device=dev)
         invalid = torch.empty((N,), dtype=torch.int32, device=dev)
         ws = _workspace(dev, "rpn", L.sfod_rpn_select_workspace_bytes(C.byref(p)))
-        check(L.sfod_rpn_select(C.byref(p), lg.data_ptr(), dl.data_ptr(), anc.data_ptr() if anc is not None else None,
-                                hw.data_ptr(), out_boxes.data_ptr(), out_logits.data_ptr(), out_src.data_ptr(),
-                                out_cnt.data_ptr(), invalid.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)), "sfod_rpn_select")
+        with _timed("rpn_select"):
+            check(L.sfod_rpn_select(C.byref(p), lg.data_ptr(), dl.data_ptr(), anc.data_ptr() if anc is not None else None,
+                                    hw.data_ptr(), out_boxes.data_ptr(), out_logits.data_ptr(), out_src.data_ptr(),
+                                    out_cnt.data_ptr(), invalid.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)), "sfod_rpn_select")
     return out_boxes, out_logits, out_src, out_cnt, invalid
 
 
@@ -381,12 +432,13 @@ def frcnn_postprocess(cls_logits: Tensor, deltas: Tensor, proposals: Tensor, row
         probs = torch.empty((R, K1), dtype=torch.float32, device=dev) if want_probs else None
         boxes = torch.empty((R, dl.shape[1]), dtype=torch.float32, device=dev) if want_boxes else None
         ws = _workspace(dev, "frcnn", L.sfod_frcnn_postprocess_workspace_bytes(C.byref(p)))
-        check(L.sfod_frcnn_postprocess(C.byref(p), cl.data_ptr(), dl.data_ptr(), pr.data_ptr(), row_off.data_ptr(), hw.data_ptr(),
-                                       det_boxes.data_ptr(), det_scores.data_ptr(), det_classes.data_ptr(), det_rows.data_ptr(),
-                                       det_count.data_ptr(), pseudo_count.data_ptr(),
-                                       probs.data_ptr() if probs is not None else None,
-                                       boxes.data_ptr() if boxes is not None else None, ws.data_ptr(), ws.numel(), _stream(dev)),
-              "sfod_frcnn_postprocess")
+        with _timed("frcnn_postprocess"):
+            check(L.sfod_frcnn_postprocess(C.byref(p), cl.data_ptr(), dl.data_ptr(), pr.data_ptr(), row_off.data_ptr(), hw.data_ptr(),
+                                           det_boxes.data_ptr(), det_scores.data_ptr(), det_classes.data_ptr(), det_rows.data_ptr(),
+                                           det_count.data_ptr(), pseudo_count.data_ptr(),
+                                           probs.data_ptr() if probs is not None else None,
+                                           boxes.data_ptr() if boxes is not None else None, ws.data_ptr(), ws.numel(), _stream(dev)),
+                  "sfod_frcnn_postprocess")
     return dict(boxes=det_boxes, scores=det_scores, classes=det_classes, rows=det_rows, count=det_count,
                 pseudo_count=pseudo_count, probs=probs, decoded=boxes)
 
@@ -432,7 +484,7 @@ class EmaPlan:
         self.plan = host.to(dev, non_blocking=False)
 
     def step(self, keep_rate: float) -> None:
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _timed("ema_multi_tensor"):
             check(_lib.lib().sfod_ema_multi_tensor(self.plan.data_ptr(), self.n_chunks, float(keep_rate), _stream(self.device)),
                   "sfod_ema_multi_tensor")
 
@@ -454,7 +506,8 @@ def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor]
     L = _lib.lib()
     with torch.cuda.device(dev):
         stats = torch.empty((L.sfod_bn_stats_bytes(Cc) // 8,), dtype=torch.float64, device=dev)
-        check(L.sfod_bn_partial_stats(xin.data_ptr(), layout, N, Cc, H * W, stats.data_ptr(), _stream(dev)), "sfod_bn_partial_stats")
+        with _timed("bn_partial_stats"):
+            check(L.sfod_bn_partial_stats(xin.data_ptr(), layout, N, Cc, H * W, stats.data_ptr(), _stream(dev)), "sfod_bn_partial_stats")
         total = float(N * H * W)
         if group is not None:
             import torch.distributed as dist
@@ -465,13 +518,14 @@ def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor]
         y = None
         if compute_output:
             y = xin if inplace else torch.empty_like(xin)
-        check(L.sfod_bn_finalize_apply(xin.data_ptr() if compute_output else None, y.data_ptr() if y is not None else None, layout,
-                                       N, Cc, H * W, stats.data_ptr(), total,
-                                       weight.data_ptr() if weight is not None else None,
-                                       bias.data_ptr() if bias is not None else None,
-                                       running_mean.data_ptr() if running_mean is not None else None,
-                                       running_var.data_ptr() if running_var is not None else None,
-                                       num_batches_tracked.data_ptr() if num_batches_tracked is not None else None,
-                                       float(momentum), float(eps), int(fuse_relu), None, None, _stream(dev)),
-              "sfod_bn_finalize_apply")
+        with _timed("bn_finalize_apply"):
+            check(L.sfod_bn_finalize_apply(xin.data_ptr() if compute_output else None, y.data_ptr() if y is not None else None, layout,
+                                           N, Cc, H * W, stats.data_ptr(), total,
+                                           weight.data_ptr() if weight is not None else None,
+                                           bias.data_ptr() if bias is not None else None,
+                                           running_mean.data_ptr() if running_mean is not None else None,
+                                           running_var.data_ptr() if running_var is not None else None,
+                                           num_batches_tracked.data_ptr() if num_batches_tracked is not None else None,
+                                           float(momentum), float(eps), int(fuse_relu), None, None, _stream(dev)),
+                  "sfod_bn_finalize_apply")
     return y

@@ -1,0 +1,236 @@
+"""GPU parity tests of the host-side mirror of the reference interface (registries, PseudoLabRPN, ROIPooler,
+FastRCNNOutputLayers.inference, threshold_bbox / process_pseudo_label, _update_teacher_model, AdaBN) against the CPU oracle.
+They read like the reference's call sites: the plugin objects are built from the VGG source-free config and called
+with the reference's argument lists."""
+import copy
+
+import pytest
+import torch
+
+from oracle import d2_cpu as o
+from oracle import teacher_cpu
+import sfod_b200  # noqa: F401
+from sfod_b200 import config, engine, modeling, registry, synth
+from sfod_b200.structures import Boxes, ImageList, Instances
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cfg():
+    c = config.vgg_source_free_cfg()
+    c.MODEL.DEVICE = "cuda"
+    return c
+
+
+@pytest.fixture(scope="module")
+def teacher(cfg, cuda_device):
+    torch.manual_seed(42)
+    m = registry.build_model(cfg)
+    m.train()
+    return m
+
+
+def test_registries_resolve_reference_names(cfg, teacher):
+    assert type(teacher.proposal_generator).__name__ == cfg.MODEL.PROPOSAL_GENERATOR.NAME == "PseudoLabRPN"
+    assert type(teacher.roi_heads).__name__ == cfg.MODEL.ROI_HEADS.NAME == "SourceFreeAdaptiveTeacherStandardROIHeads"
+    for name in ("PseudoLabRPN", "DARPN"):
+        assert name in registry.PROPOSAL_GENERATOR_REGISTRY
+    for name in ("SourceFreeAdaptiveTeacherStandardROIHeads", "SourceFreeAdaptiveTeacherEvalStandardROIHeads", "AdaptiveTeacherStandardROIHeads"):
+        assert name in registry.ROI_HEADS_REGISTRY
+    assert "build_vgg_backbone" in registry.BACKBONE_REGISTRY
+    assert sum(v.numel() for v in teacher.state_dict().values()) == 47636547
+
+
+def test_pseudolab_rpn_predict_proposals_matches_oracle(teacher, cuda_device):
+    rpn = teacher.proposal_generator
+    assert rpn.training  # teacher in train mode -> (12000, 2000)
+    cfgv = synth.V
+    N = 2
+    logits, deltas, cell, anchors = synth.rpn_head_outputs(cfgv, N, 4321)
+    sizes = [(600, 1200), (576, 1184)]
+    ref = o.rpn_predict_proposals([anchors], [logits], [deltas], sizes, 0.7, 12000, 2000, 0.0, True, exp=o.exp_correctly_rounded)
+    for kw in (dict(feat_hw=[(18, 37)]), dict()):   # closed-form anchors and the explicit anchor tensor (detectron2's signature)
+        got = rpn.predict_proposals([Boxes(anchors.to(cuda_device))], [logits.to(cuda_device)], [deltas.to(cuda_device)], sizes, **kw)
+        for g, r in zip(got, ref):
+            assert g.image_size == r["image_size"]
+            assert torch.equal(g.proposal_boxes.tensor.cpu(), r["proposal_boxes"])
+            assert torch.equal(g.objectness_logits.cpu(), r["objectness_logits"])
+    rpn.eval()
+    try:
+        ref = o.rpn_predict_proposals([anchors], [logits], [deltas], sizes, 0.7, 6000, 1000, 0.0, False, exp=o.exp_correctly_rounded)
+        got = rpn.predict_proposals([Boxes(anchors.to(cuda_device))], [logits.to(cuda_device)], [deltas.to(cuda_device)], sizes, feat_hw=[(18, 37)])
+        for g, r in zip(got, ref):
+            assert torch.equal(g.proposal_boxes.tensor.cpu(), r["proposal_boxes"])
+    finally:
+        rpn.train()
+
+
+def test_pseudolab_rpn_forward_signature_and_flatten(teacher, cuda_device):
+    """forward(images, features, gt_instances=None, compute_loss=True, compute_val_loss=False) -> (List[Instances], {})."""
+    rpn = teacher.proposal_generator
+    feat = synth.features(synth.V, 2, 77)
+    images = ImageList(torch.zeros(2, 3, 600, 1200), [(600, 1200), (600, 1200)])
+    with torch.no_grad():
+        props, losses = rpn(images, {"vgg4": feat.to(cuda_device)}, None, compute_loss=False)
+        # oracle: same head weights on the CPU, reference rpn.py:27-41 flatten, d2 predict_proposals
+        head = copy.deepcopy(rpn.rpn_head).cpu()
+        obj, dl = head([feat])
+    lg, dd = o.rpn_flatten_head_outputs(obj, dl)
+    anchors = o.grid_anchors((18, 37), 32, o.generate_cell_anchors())
+    ref = o.rpn_predict_proposals([anchors], lg, dd, images.image_sizes, 0.7, 12000, 2000, 0.0, True)
+    assert losses == {}
+    for g, r in zip(props, ref):
+        # cuDNN vs ATen-CPU convolutions differ in the last bits, so compare as sets of near-identical boxes
+        assert abs(len(g) - len(r["proposal_boxes"])) <= max(3, len(r["proposal_boxes"]) // 100)
+        k = min(len(g), len(r["proposal_boxes"]), 50)
+        assert torch.allclose(g.proposal_boxes.tensor[:k].cpu(), r["proposal_boxes"][:k], rtol=1e-3, atol=1e-2) or k == 0
+    with pytest.raises(NotImplementedError):
+        rpn(images, {"vgg4": feat.to(cuda_device)}, None, compute_loss=True)
+
+
+def test_roi_pooler_matches_oracle(teacher, cuda_device):
+    pooler = teacher.roi_heads.box_pooler
+    assert pooler.pooler_type == "ROIAlignV2" and pooler.output_size == (7, 7) and pooler.sampling_ratio == 0
+    feat = synth.features(synth.V, 2, 5)
+    rois = synth.random_rois(2, 400, 6)
+    lists = [rois[rois[:, 0] == i][:, 1:].contiguous() for i in range(2)]
+    got = pooler([feat.to(cuda_device)], [Boxes(b.to(cuda_device)) for b in lists]).cpu()
+    ref = o.roi_pooler(feat, lists, 7, 1 / 32, 0, "ROIAlignV2")
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-5 * ref.abs().max().item(), err      # 1e-5 relative fp32 (BASELINE.json)
+    for ptype in ("ROIAlign", "ROIPool"):
+        p2 = modeling.ROIPooler(7, (1 / 32,), 0, ptype)
+        got = p2([feat.to(cuda_device)], [Boxes(b.to(cuda_device)) for b in lists]).cpu()
+        ref = o.roi_pooler(feat, lists, 7, 1 / 32, 0, ptype)
+        assert (got - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    with pytest.raises(ValueError):
+        modeling.ROIPooler(7, (1 / 32,), 0, "ROIAlignRotated")
+
+
+def test_box_predictor_inference_and_threshold_bbox(teacher, cuda_device):
+    pred = teacher.roi_heads.box_predictor
+    rows = [700, 0, 1300]
+    sizes = [(600, 1200)] * 3
+    R = sum(rows)
+    cls, dl = synth.box_head_outputs(R, 8, 91, 4.0)
+    props = synth.random_rois(1, R, 92)[:, 1:].contiguous()
+    plist = list(props.split(rows))
+    proposals = []
+    for b, s in zip(plist, sizes):
+        inst = Instances(s)
+        inst.proposal_boxes = Boxes(b.to(cuda_device))
+        inst.objectness_logits = torch.zeros(len(b), device=cuda_device)
+        proposals.append(inst)
+    instances, kept = pred.inference((cls.to(cuda_device), dl.to(cuda_device)), proposals)
+    ref = o.box_predictor_inference(cls, dl, plist, sizes, 0.05, 0.5, 100, exp=o.exp_correctly_rounded, softmax=o.softmax_defined)
+    for g, k, r in zip(instances, kept, ref):
+        assert torch.equal(g.pred_classes.cpu(), r["pred_classes"]) and torch.equal(k.cpu(), r["kept_rows"])
+        assert torch.equal(g.scores.cpu(), r["scores"]) and torch.equal(g.pred_boxes.tensor.cpu(), r["pred_boxes"])
+    # pseudo-label filter: fused prefix (thres == cfg threshold) and the generic kernel path (any other threshold / rpn type)
+    for thres in (0.8, 0.5):
+        got, avg = engine.process_pseudo_label(instances, thres, "roih", "thresholding")
+        want, avg_ref = o.process_pseudo_label(ref, thres, "roih", "thresholding")
+        assert avg == avg_ref
+        for g, w in zip(got, want):
+            assert torch.equal(g.gt_boxes.tensor.cpu(), w["gt_boxes"]) and torch.equal(g.gt_classes.cpu(), w["gt_classes"])
+            assert torch.equal(g.scores.cpu(), w["scores"])
+    rp = Instances((600, 1200))
+    rp.proposal_boxes = Boxes(props[:500].to(cuda_device))
+    rp.objectness_logits = torch.randn(500, generator=torch.Generator().manual_seed(3)).to(cuda_device)
+    g = engine.threshold_bbox(rp, 0.3, "rpn")
+    w = o.threshold_bbox(dict(image_size=(600, 1200), proposal_boxes=props[:500], objectness_logits=rp.objectness_logits.cpu()), 0.3, "rpn")
+    assert torch.equal(g.gt_boxes.tensor.cpu(), w["gt_boxes"]) and torch.equal(g.objectness_logits.cpu(), w["objectness_logits"])
+    with pytest.raises(ValueError):
+        engine.process_pseudo_label(instances, 0.8, "roih", "no_such_method")
+
+
+def test_convert_bbox_scores_matches_oracle(teacher, cuda_device):
+    pred = teacher.roi_heads.box_predictor
+    R = 300
+    cls, dl = synth.box_head_outputs(R, 8, 17, 2.0)
+    props = synth.random_rois(1, R, 18)[:, 1:].contiguous()
+    inst = Instances((600, 1200))
+    inst.proposal_boxes = Boxes(props.to(cuda_device))
+    res, kept = pred.convert_bbox_scores((cls.to(cuda_device), dl.to(cuda_device)), [inst])
+    bx = o.predict_boxes(dl, [props], exp=o.exp_correctly_rounded)
+    ref = o.convert_bbox_scores_single_image(bx[0], o.softmax_defined(cls), (600, 1200))
+    assert torch.equal(res[0].pred_boxes.tensor.cpu(), ref["pred_boxes"]) and torch.equal(res[0].scores.cpu(), ref["scores"])
+    assert torch.equal(res[0].pred_classes.cpu(), ref["pred_classes"]) and torch.equal(kept[0].cpu(), ref["kept_rows"])
+
+
+@pytest.mark.parametrize("world_size", [1, 2])
+def test_update_teacher_model_bit_exact(cfg, cuda_device, world_size):
+    torch.manual_seed(7)
+    c = cfg.clone(); c.MODEL.DEVICE = "cpu"
+    t_cpu = modeling.SourceFreeAdaptiveTeacherGeneralizedRCNN(c)
+    s_cpu = modeling.SourceFreeAdaptiveTeacherGeneralizedRCNN(c)
+    with torch.no_grad():
+        for b in s_cpu.buffers():
+            if b.dtype == torch.int64:
+                b.fill_(1234)
+    t_gpu, s_gpu = copy.deepcopy(t_cpu).to(cuda_device), copy.deepcopy(s_cpu).to(cuda_device)
+    student_gpu = torch.nn.Sequential()
+    student_gpu.add_module("module", s_gpu)            # DDP-style 'module.' prefix
+    model = student_gpu if world_size > 1 else s_gpu
+    for keep in (0.9996, 0.0):
+        engine.update_teacher_model(model, t_gpu, keep, world_size)
+        ssd = {("module." + k if world_size > 1 else k): v for k, v in s_cpu.state_dict().items()}
+        tsd = t_cpu.state_dict()
+        o.load_state_dict_like(tsd, o.update_teacher_model(ssd, tsd, keep, ddp_prefix=world_size > 1))
+        for k, v in t_gpu.state_dict().items():
+            assert torch.equal(v.cpu(), tsd[k]), k
+    bad = torch.nn.Linear(3, 3).to(cuda_device)
+    with pytest.raises(Exception, match="is not found in student model"):
+        engine.update_teacher_model(bad, t_gpu, 0.9996, 1)
+
+
+def test_adabn_refinement_matches_oracle(cuda_device):
+    """reset -> train-mode no_grad forwards -> running statistics (momentum 0.1 recursion), vs nn.BatchNorm2d on the CPU."""
+    torch.manual_seed(3)
+
+    def make():
+        return torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, padding=1), torch.nn.BatchNorm2d(16), torch.nn.ReLU(inplace=True),
+                                   torch.nn.Conv2d(16, 32, 3, padding=1), torch.nn.BatchNorm2d(32), torch.nn.ReLU(inplace=True))
+    ref = make()
+    got = copy.deepcopy(ref).to(cuda_device)
+    with torch.no_grad():
+        for m in (ref, got):
+            m[1].running_mean.fill_(5.0); m[4].running_var.fill_(9.0)
+    g = torch.Generator().manual_seed(11)
+    batches = [torch.randn(2, 3, 40, 56, generator=g) * (i + 1) for i in range(5)]
+    n_ref = o.adabn_recompute(ref, batches, max_iters=3)
+    n_got = engine.adabn_refinement(got, [b.to(cuda_device) for b in batches], max_iters=3)
+    assert n_ref == n_got == 4          # the reference breaks when i > max_iters, after running batch i
+    assert isinstance(got[1], modeling.SfodBatchNorm2d) and isinstance(got[1].running_mean, torch.nn.Parameter)
+    for i in (1, 4):
+        assert got[i].num_batches_tracked.item() == ref[i].num_batches_tracked.item() == 4
+        for name in ("running_mean", "running_var"):
+            a, b = getattr(got[i], name).cpu(), getattr(ref[i], name)
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (i, name, (a - b).abs().max())
+    assert set(got.state_dict().keys()) == set(ref.state_dict().keys())
+
+
+def test_teacher_end_to_end_against_cpu_pipeline(teacher, cuda_device):
+    """Whole teacher branch vs the CPU restatement on one image.  cuDNN and ATen-CPU convolutions differ in the last bits,
+    so discrete outcomes are compared loosely here; the bit-exact checks live in the kernel/plugin tests above."""
+    img = torch.randint(0, 256, (1, 3, 600, 1200), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
+    sd = {k: v.detach().cpu().clone() for k, v in teacher.state_dict().items()}
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            _, p_rpn, p_roih = teacher(img.to(cuda_device), branch="unsup_data_weak")
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    r_rpn, r_roih, r_pl = teacher_cpu.teacher_pseudo_label(sd, img, training=True)
+    assert abs(len(p_rpn[0]) - len(r_rpn[0]["proposal_boxes"])) <= max(5, len(r_rpn[0]["proposal_boxes"]) // 50)
+    assert abs(len(p_roih[0]) - len(r_roih[0]["scores"])) <= 10
+    pl, avg = engine.process_pseudo_label(p_roih, 0.8, "roih", "thresholding")
+    assert len(pl[0]) == len(r_pl[0]["gt_boxes"]) == 0          # random-init heads: ~1/9 scores, empty pseudo-label set
+    # BN running statistics were updated by the forward (train mode), like the CPU path
+    for k, v in teacher.state_dict().items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert torch.allclose(v.cpu(), sd[k], rtol=2e-4, atol=1e-4), k
+        if k.endswith("num_batches_tracked"):
+            assert v.item() == sd[k].item()
