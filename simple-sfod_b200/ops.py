@@ -469,8 +469,11 @@ class EmaPlan:
                 code = 1
             else:
                 raise TypeError(f"EMA supports float32 and int64 state tensors, got {s.dtype}")
-            if not s.is_contiguous() or not t.is_contiguous():
-                raise ValueError("EMA tensors must be contiguous (state_dict tensors are)")
+            # elementwise over the storage: any dense layout works as long as both tensors share it (e.g. channels_last weights)
+            if not (s.is_contiguous() and t.is_contiguous()):
+                dense = getattr(t, "is_non_overlapping_and_dense", lambda: False)() and getattr(s, "is_non_overlapping_and_dense", lambda: False)()
+                if not dense or s.stride() != t.stride():
+                    raise ValueError(f"EMA pair {i}: tensors must be dense and share one memory layout")
             arr[i].student, arr[i].teacher = s.data_ptr(), t.data_ptr()
             arr[i].numel, arr[i].dtype = s.numel(), code
             self._keepalive.append((s, t))
@@ -510,11 +513,9 @@ def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor]
             check(L.sfod_bn_partial_stats(xin.data_ptr(), layout, N, Cc, H * W, stats.data_ptr(), _stream(dev)), "sfod_bn_partial_stats")
         total = float(N * H * W)
         if group is not None:
-            import torch.distributed as dist
-            payload = stats[: 2 * Cc + 1]
-            payload[2 * Cc] = total
-            dist.all_reduce(payload, group=group if group is not True else None)
-            total = float(payload[2 * Cc].item())
+            from .engine.adabn_dist import allreduce_bn_stats
+            stats[2 * Cc] = total
+            total = allreduce_bn_stats(stats, Cc, group=group if group is not True else None)
         y = None
         if compute_output:
             y = xin if inplace else torch.empty_like(xin)

@@ -16,6 +16,16 @@ from sfod_b200.structures import Boxes, ImageList, Instances
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _strict_fp32_library_math():
+    """cuDNN/cuBLAS in strict fp32 so that library convolutions / FCs are comparable with the ATen-CPU ones."""
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
 @pytest.fixture(scope="module")
 def cfg():
     c = config.vgg_source_free_cfg()
@@ -216,13 +226,8 @@ def test_teacher_end_to_end_against_cpu_pipeline(teacher, cuda_device):
     so discrete outcomes are compared loosely here; the bit-exact checks live in the kernel/plugin tests above."""
     img = torch.randint(0, 256, (1, 3, 600, 1200), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
     sd = {k: v.detach().cpu().clone() for k, v in teacher.state_dict().items()}
-    tf32 = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    try:
-        with torch.no_grad():
-            _, p_rpn, p_roih = teacher(img.to(cuda_device), branch="unsup_data_weak")
-    finally:
-        torch.backends.cudnn.allow_tf32 = tf32
+    with torch.no_grad():
+        _, p_rpn, p_roih = teacher(img.to(cuda_device), branch="unsup_data_weak")
     r_rpn, r_roih, r_pl = teacher_cpu.teacher_pseudo_label(sd, img, training=True)
     assert abs(len(p_rpn[0]) - len(r_rpn[0]["proposal_boxes"])) <= max(5, len(r_rpn[0]["proposal_boxes"]) // 50)
     assert abs(len(p_roih[0]) - len(r_roih[0]["scores"])) <= 10

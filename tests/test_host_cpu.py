@@ -1,0 +1,188 @@
+"""CPU tests (no GPU) of the C-ABI library surface and of the host-side logic.
+
+* libsfod_b200.so loads and exports every symbol include/sfod_b200.h declares; its host-only entry points (version, status
+  strings, workspace-size queries, EMA plan builder) behave; no kernel is launched.
+* The product never imports ``oracle/`` and refuses CPU tensors (no fallback).
+* detectron2-shaped structures, registries, config and the trainer-level host logic (state-dict key matching, sharding).
+* world_size-2 ``gloo`` run of the multi-GPU host logic: image sharding and the AdaBN (sum, sum^2, count) reduction.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import sfod_b200  # noqa: F401
+from sfod_b200 import _lib, config, engine, modeling, ops, registry
+from sfod_b200.engine.ema import match_state_dicts
+from sfod_b200.structures import Boxes, ImageList, Instances, pairwise_iou
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "sfod_b200.h")).read()
+    declared = set(re.findall(r"\b(sfod_[a-z0-9_]+)\s*\(", header))
+    declared -= {"sfod_status", "sfod_layout", "sfod_dtype"}
+    assert len(declared) >= 24
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/sfod_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    # exported symbols are exactly the ABI (everything else is hidden)
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert {e for e in exported if e.startswith("sfod_")} == declared
+
+
+def test_host_only_entry_points():
+    L = _lib.lib()
+    assert L.sfod_abi_version() == 1
+    assert L.sfod_status_string(0) == b"ok" and L.sfod_status_string(2) == b"workspace too small"
+    assert L.sfod_nms_workspace_bytes(0) == 256 and L.sfod_nms_workspace_bytes(9990) > 9990 * 157 * 8
+    assert L.sfod_roi_align_fwd_workspace_bytes(8, 512, 18, 37, 0, 0) >= 8 * 512 * 18 * 37 * 4     # NCHW in -> NHWC copy
+    assert L.sfod_roi_align_fwd_workspace_bytes(8, 512, 18, 37, 1, 0) == 256
+    assert L.sfod_bn_stats_bytes(512) >= 512 * 4 * 8
+    p = _lib.RpnParams(); p.N, p.HWA, p.pre_nms_topk, p.post_nms_topk = 8, 9990, 12000, 2000
+    assert L.sfod_rpn_select_workspace_bytes(C.byref(p)) > 8 * 9990 * 157 * 8
+    # EMA plan: 16384-element chunks, built on the host
+    arr = (_lib.EmaTensor * 2)()
+    arr[0].student, arr[0].teacher, arr[0].numel, arr[0].dtype = 0x1000, 0x2000, 40000, 0
+    arr[1].student, arr[1].teacher, arr[1].numel, arr[1].dtype = 0x9000, 0xA000, 1, 1
+    n = L.sfod_ema_plan_chunks(arr, 2)
+    assert n == 4
+    buf = (C.c_char * L.sfod_ema_plan_bytes(n))()
+    assert L.sfod_ema_plan_build(arr, 2, buf, len(buf)) == 0
+    assert L.sfod_ema_plan_build(arr, 2, buf, 8) == 2           # SFOD_ERR_WORKSPACE_TOO_SMALL
+    arr[1].dtype = 7
+    assert L.sfod_ema_plan_build(arr, 2, buf, len(buf)) == 3    # SFOD_ERR_UNSUPPORTED
+    assert L.sfod_debug_launch_count() == 0                     # nothing was launched by any of the above
+
+
+def test_product_never_imports_oracle_and_has_no_cpu_fallback():
+    pkg = os.path.join(ROOT, "simple-sfod_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.nms(torch.zeros(3, 4), torch.zeros(3), 0.5)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.roi_align(torch.zeros(1, 4, 8, 8), torch.zeros(1, 5), 7)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        modeling.Box2BoxTransform((1, 1, 1, 1)).apply_deltas(torch.zeros(2, 4), torch.zeros(2, 4))
+
+
+# ------------------------------------------------------------------------------------------------ structures / registries / config
+def test_structures_follow_detectron2():
+    b = Boxes(torch.tensor([[-5.0, 2.0, 30.0, 50.0], [4.0, 4.0, 4.0, 9.0]]))
+    b.clip((40, 20))
+    assert b.tensor.tolist() == [[0.0, 2.0, 20.0, 40.0], [4.0, 4.0, 4.0, 9.0]]
+    assert b.nonempty().tolist() == [True, False] and b.area().tolist() == [760.0, 0.0]
+    assert len(Boxes.cat([b, b])) == 4 and len(Boxes(torch.zeros(0))) == 0
+    inst = Instances((40, 20))
+    inst.pred_boxes = b
+    inst.scores = torch.tensor([0.9, 0.1])
+    assert len(inst) == 2 and inst.has("scores") and inst[inst.scores > 0.5].pred_boxes.tensor.shape == (1, 4)
+    with pytest.raises(AssertionError):
+        inst.pred_classes = torch.zeros(3)
+    with pytest.raises(AttributeError):
+        inst.nope
+    assert len(Instances.cat([inst, inst])) == 4
+    il = ImageList.from_tensors([torch.ones(3, 10, 12), torch.ones(3, 8, 16)], size_divisibility=32)
+    assert il.tensor.shape == (2, 3, 32, 32) and il.image_sizes == [(10, 12), (8, 16)] and il[1].shape == (3, 8, 16)
+    iou = pairwise_iou(Boxes(torch.tensor([[0.0, 0, 10, 10]])), Boxes(torch.tensor([[0.0, 0, 10, 5], [20.0, 20, 30, 30]])))
+    assert iou.tolist() == [[0.5, 0.0]]
+
+
+def test_registries_and_config():
+    cfg = config.vgg_source_free_cfg()
+    assert cfg.MODEL.PROPOSAL_GENERATOR.NAME == "PseudoLabRPN" and cfg.MODEL.RPN.PRE_NMS_TOPK_TRAIN == 12000
+    assert cfg.MODEL.RPN.POST_NMS_TOPK_TEST == 1000 and cfg.SEMISUPNET.BBOX_THRESHOLD == 0.8 and cfg.MODEL.ROI_HEADS.NUM_CLASSES == 8
+    assert registry.PROPOSAL_GENERATOR_REGISTRY.get("PseudoLabRPN") is modeling.PseudoLabRPN
+    assert registry.ROI_HEADS_REGISTRY.get("SourceFreeAdaptiveTeacherStandardROIHeads") is modeling.SourceFreeAdaptiveTeacherStandardROIHeads
+    with pytest.raises(KeyError):
+        registry.ROI_HEADS_REGISTRY.get("NoSuchHeads")
+    cfg.MODEL.DEVICE = "cpu"
+    m = registry.build_model(cfg)
+    sd = m.state_dict()
+    assert sum(v.numel() for v in sd.values()) == 47636547 and sum(p.numel() for p in m.parameters()) == 47628086
+    # reference state_dict keys (vgg.py stage slicing, d2 module names)
+    for k in ("backbone.vgg0.0.weight", "backbone.vgg4.7.running_var", "proposal_generator.rpn_head.anchor_deltas.bias",
+              "roi_heads.box_head.fc2.weight", "roi_heads.box_predictor.bbox_pred.weight", "DC_img.classifier.bias",
+              "DC_ins.da_ins_fc3_level_vgg4.weight"):
+        assert k in sd, k
+    assert m.backbone.output_shape()["vgg4"].stride == 32 and m.proposal_generator.anchor_generator.num_anchors == [15]
+    assert m.roi_heads.box_predictor.bbox_pred.out_features == 32 and m.roi_heads.box_head.fc1.in_features == 25088
+    r = config.r101_c4_source_free_cfg()
+    assert r.MODEL.ANCHOR_GENERATOR.SIZES == [[64, 128, 256, 512]] and r.MODEL.ROI_BOX_HEAD.FC_DIM == 2048
+    # CPU forward of the BN module defers to nn.BatchNorm2d (native path only for CUDA train/no_grad)
+    bn = modeling.SfodBatchNorm2d(4)
+    ref = torch.nn.BatchNorm2d(4)
+    x = torch.randn(2, 4, 5, 5)
+    assert torch.equal(bn(x), ref(x)) and torch.equal(bn.running_var, ref.running_var)
+
+
+def test_ema_key_matching_and_sharding_host_logic():
+    t = {"a": torch.zeros(2), "b": torch.zeros(1)}
+    s = {"module.a": torch.ones(2), "module.b": torch.ones(1), "module.extra": torch.ones(1)}
+    pairs = match_state_dicts(s, t, strip_module_prefix=True)
+    assert [k for k, _, _ in pairs] == ["a", "b"] and pairs[0][1] is s["module.a"] and pairs[0][2] is t["a"]
+    with pytest.raises(Exception, match="b is not found in student model"):
+        match_state_dicts({"a": torch.ones(2)}, t, False)
+    assert engine.images_per_rank(8, 4) == 2
+    with pytest.raises(AssertionError):
+        engine.images_per_rank(8, 3)
+    cover = []
+    for r in range(3):
+        b, e = engine.shard_range(10, r, 3)
+        cover += list(range(b, e))
+    assert cover == list(range(10))
+    # reset_bn_stats semantics (reference base.py:318-323)
+    m = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 1), torch.nn.BatchNorm2d(4))
+    m[1].running_mean.fill_(3.0)
+    engine.recursive_traversal(m)
+    assert isinstance(m[1].running_mean, torch.nn.Parameter) and not m[1].running_mean.requires_grad
+    assert m[1].running_mean.sum() == 0 and m[1].running_var.sum() == 4 and "1.running_mean" in m.state_dict()
+    modeling.convert_batchnorm(m)
+    assert isinstance(m[1], modeling.SfodBatchNorm2d) and isinstance(m[1].running_mean, torch.nn.Parameter)
+
+
+# ------------------------------------------------------------------------------------------------ world_size 2 (gloo)
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SFOD_ROOT"])
+import sfod_b200
+from sfod_b200 import engine
+from sfod_b200.engine.adabn_dist import allreduce_bn_stats, finalize_stats_host
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+g = torch.Generator().manual_seed(123)
+full = torch.randn(6, 5, 7, 9, generator=g, dtype=torch.float64) * 3 + 2       # the concatenated batch of both ranks
+b, e = engine.shard_range(full.shape[0], rank, world)
+mine = full[b:e]
+stats = torch.stack([mine.sum(dim=(0, 2, 3)), (mine * mine).sum(dim=(0, 2, 3))], dim=1).reshape(-1)   # (C, 2) layout of the kernel
+payload = torch.cat([stats, torch.tensor([float(mine.numel() // 5)], dtype=torch.float64)])
+total = allreduce_bn_stats(payload, 5)
+mean, var = finalize_stats_host(payload, 5, total)
+ref_mean = full.mean(dim=(0, 2, 3)); ref_var = full.var(dim=(0, 2, 3), unbiased=False)
+assert total == 6 * 7 * 9, total
+assert torch.allclose(mean, ref_mean, rtol=1e-12, atol=1e-12) and torch.allclose(var, ref_var, rtol=1e-10), (mean, ref_mean)
+dist.barrier()
+if rank == 0:
+    print("GLOO_OK")
+'''
+
+
+def test_world_size_2_gloo_sharding_and_bn_stat_reduction(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, SFOD_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", str(script)], capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
