@@ -211,12 +211,20 @@ int sfod_threshold_select(const float *values, const int32_t *counts_dev, int S,
  *   r = (1-m) r + m stat with the unbiased variance n/(n-1), num_batches_tracked += 1,
  *   y = (x-mean)*invstd*weight+bias (optionally fused ReLU); y may alias x. */
 size_t sfod_bn_stats_bytes(int C);
-int sfod_bn_partial_stats(const float *x, int layout, int N, int C, int64_t HW, double *stats_dev,
+/* pre_bias (C floats, may be NULL): a per-channel bias added to x before everything else -- the bias of the
+ * convolution that feeds the BatchNorm (reference daod/modeling/meta_arch/vgg.py:17-19: Conv2d(bias=True) -> BatchNorm2d),
+ * so that the convolution can run bias-free and its separate elementwise pass over the activation disappears.
+ * Statistics, running statistics and output are those of fl(x + pre_bias[c]), bit-identical to adding the bias first. */
+int sfod_bn_partial_stats(const float *x, const float *pre_bias, int layout, int N, int C, int64_t HW, double *stats_dev,
                           sfod_stream_t stream);
-int sfod_bn_finalize_apply(const float *x, float *y, int layout, int N, int C, int64_t HW, const double *stats_dev,
-                           double total_count, const float *weight, const float *bias, float *running_mean,
-                           float *running_var, int64_t *num_batches_tracked, double momentum, double eps,
-                           int fuse_relu, float *save_mean, float *save_invstd, sfod_stream_t stream);
+/* fuse_maxpool2 != 0: y is the (N,C,H/2,W/2) result of MaxPool2d(kernel_size=2, stride=2) applied to the normalised
+ * (+ReLU) activation (vgg.py:15), written directly (x is read once, the full-resolution activation is never stored);
+ * y must not alias x in that mode. */
+int sfod_bn_finalize_apply(const float *x, const float *pre_bias, float *y, int layout, int N, int C, int H, int W,
+                           const double *stats_dev, double total_count, const float *weight, const float *bias,
+                           float *running_mean, float *running_var, int64_t *num_batches_tracked, double momentum,
+                           double eps, int fuse_relu, int fuse_maxpool2, float *save_mean, float *save_invstd,
+                           sfod_stream_t stream);
 
 #ifdef __cplusplus
 }

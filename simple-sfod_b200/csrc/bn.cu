@@ -26,8 +26,8 @@ __device__ __forceinline__ void flush_channel(double *stats, int c, double sd, d
   atomicAdd(stats + 2 * c + 1, sd2 + 2.0 * K * sd + m * K * K);
 }
 
-__global__ void __launch_bounds__(kThreads) bn_stats_nchw_kernel(const float *__restrict__ x, int C, long long HW,
-                                                                 double *__restrict__ stats) {
+__global__ void __launch_bounds__(kThreads) bn_stats_nchw_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
+                                                                 int C, long long HW, double *__restrict__ stats) {
   __shared__ double red[2][kThreads / 32];
   const int plane = blockIdx.y;          // n * C + c
   const int c = plane % C;
@@ -35,23 +35,26 @@ __global__ void __launch_bounds__(kThreads) bn_stats_nchw_kernel(const float *__
   const long long len = min((long long)kChunk, HW - start);
   if (len <= 0) return;
   const float *p = x + (size_t)plane * HW + start;
-  const float K = x[(size_t)c * HW];     // pivot: first element of the channel in image 0
+  // The statistics are those of v = fl(x + pre_bias[c]) (the conv bias the reference adds before BatchNorm, fused here);
+  // the pivot is expressed in x-space: (x + b) - (x0 + b) is evaluated as fl(fl(x + b) - K) with K = fl(x0 + b).
+  const float pb = pre_bias ? pre_bias[c] : 0.f;
+  const float K = x[(size_t)c * HW] + pb;     // pivot: first element of the channel in image 0
   float s = 0.f, s2 = 0.f;
   // peel to 16-byte alignment, then 128-bit loads
   const int mis = (int)((reinterpret_cast<uintptr_t>(p) >> 2) & 3);
   const int head = mis ? min((long long)(4 - mis), len) : 0;
-  if (threadIdx.x < head) { const float d = p[threadIdx.x] - K; s += d; s2 = fmaf(d, d, s2); }
+  if (threadIdx.x < head) { const float d = (p[threadIdx.x] + pb) - K; s += d; s2 = fmaf(d, d, s2); }
   const float4 *p4 = reinterpret_cast<const float4 *>(p + head);
   const int n4 = (int)((len - head) >> 2);
 #pragma unroll 4
   for (int i = threadIdx.x; i < n4; i += kThreads) {
     const float4 v = __ldg(p4 + i);
-    const float d0 = v.x - K, d1 = v.y - K, d2 = v.z - K, d3 = v.w - K;
+    const float d0 = (v.x + pb) - K, d1 = (v.y + pb) - K, d2 = (v.z + pb) - K, d3 = (v.w + pb) - K;
     s += (d0 + d1) + (d2 + d3);
     s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
   }
   const int tail0 = head + (n4 << 2);
-  if (tail0 + (int)threadIdx.x < len) { const float d = p[tail0 + threadIdx.x] - K; s += d; s2 = fmaf(d, d, s2); }
+  if (tail0 + (int)threadIdx.x < len) { const float d = (p[tail0 + threadIdx.x] + pb) - K; s += d; s2 = fmaf(d, d, s2); }
   double ds = warp_sum((double)s), ds2 = warp_sum((double)s2);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) { red[0][warp] = ds; red[1][warp] = ds2; }
@@ -66,8 +69,9 @@ __global__ void __launch_bounds__(kThreads) bn_stats_nchw_kernel(const float *__
 
 // NHWC: x viewed as (M = N*HW rows, C columns).  A CTA covers `cols` float4 column groups x `rowlanes`
 // row lanes; each thread walks up to 64 rows with 128-bit loads (4 channels per load).
-__global__ void __launch_bounds__(kThreads) bn_stats_nhwc_kernel(const float *__restrict__ x, long long M, int C, int cols,
-                                                                 int rowlanes, double *__restrict__ stats) {
+__global__ void __launch_bounds__(kThreads) bn_stats_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
+                                                                 long long M, int C, int cols, int rowlanes,
+                                                                 double *__restrict__ stats) {
   extern __shared__ double sred[];  // rowlanes * cols * 8 doubles
   const int G = C >> 2;
   const int col = threadIdx.x % cols, rl = threadIdx.x / cols;
@@ -75,17 +79,19 @@ __global__ void __launch_bounds__(kThreads) bn_stats_nhwc_kernel(const float *__
   const long long row0 = (long long)blockIdx.x * rowlanes * 64;
   const bool on = rl < rowlanes && g < G;
   float4 K = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 s = K, s2 = K;
+  float4 s = K, s2 = K, pb = K;
   int cnt = 0;
   if (on) {
+    if (pre_bias) pb = __ldg(reinterpret_cast<const float4 *>(pre_bias) + g);
     K = __ldg(reinterpret_cast<const float4 *>(x) + g);  // pivot: row 0
+    K = make_float4(K.x + pb.x, K.y + pb.y, K.z + pb.z, K.w + pb.w);
     const float4 *p = reinterpret_cast<const float4 *>(x) + g;
 #pragma unroll 4
     for (int i = 0; i < 64; ++i) {
       const long long r = row0 + (long long)i * rowlanes + rl;
       if (r < M) {
         const float4 v = __ldg(p + (size_t)r * G);
-        const float d0 = v.x - K.x, d1 = v.y - K.y, d2 = v.z - K.z, d3 = v.w - K.w;
+        const float d0 = (v.x + pb.x) - K.x, d1 = (v.y + pb.y) - K.y, d2 = (v.z + pb.z) - K.z, d3 = (v.w + pb.w) - K.w;
         s.x += d0; s.y += d1; s.z += d2; s.w += d3;
         s2.x = fmaf(d0, d0, s2.x); s2.y = fmaf(d1, d1, s2.y); s2.z = fmaf(d2, d2, s2.z); s2.w = fmaf(d3, d3, s2.w);
         ++cnt;
@@ -114,11 +120,12 @@ __global__ void __launch_bounds__(kThreads) bn_stats_nhwc_kernel(const float *__
 }
 
 // scalar fallback for NHWC with C % 4 != 0 (not used by any shipped config)
-__global__ void __launch_bounds__(kThreads) bn_stats_nhwc_scalar_kernel(const float *__restrict__ x, long long M, int C,
-                                                                        double *__restrict__ stats) {
+__global__ void __launch_bounds__(kThreads) bn_stats_nhwc_scalar_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
+                                                                        long long M, int C, double *__restrict__ stats) {
   const int c = blockIdx.x;
+  const float pb = pre_bias ? pre_bias[c] : 0.f;
   double s = 0.0, s2 = 0.0;
-  for (long long r = threadIdx.x; r < M; r += kThreads) { const double v = x[(size_t)r * C + c]; s += v; s2 += v * v; }
+  for (long long r = threadIdx.x; r < M; r += kThreads) { const double v = x[(size_t)r * C + c] + pb; s += v; s2 += v * v; }
   __shared__ double red[2][kThreads / 32];
   s = warp_sum(s); s2 = warp_sum(s2);
   if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = s2; }
@@ -156,60 +163,129 @@ __global__ void bn_finalize_kernel(const double *__restrict__ stats, int C, doub
 }
 
 template <bool kRelu>
-__device__ __forceinline__ float bn1(float v, float sc, float sh) {
-  const float y = fmaf(v, sc, sh);
+__device__ __forceinline__ float bn1(float v, float pb, float sc, float sh) {
+  const float y = fmaf(v + pb, sc, sh);   // fl(x + conv_bias) first, exactly the tensor the reference normalises
   return kRelu ? fmaxf(y, 0.f) : y;
 }
 
 template <bool kRelu>
-__global__ void __launch_bounds__(kThreads) bn_apply_nchw_kernel(const float *__restrict__ x, float *__restrict__ y, int C,
-                                                                 long long HW, const float *__restrict__ scale,
-                                                                 const float *__restrict__ shift) {
+__global__ void __launch_bounds__(kThreads) bn_apply_nchw_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
+                                                                 float *__restrict__ y, int C, long long HW,
+                                                                 const float *__restrict__ scale, const float *__restrict__ shift) {
   const int plane = blockIdx.y;
   const int c = plane % C;
   const long long start = (long long)blockIdx.x * kChunk;
   const long long len = min((long long)kChunk, HW - start);
   if (len <= 0) return;
-  const float sc = scale[c], sh = shift[c];
+  const float sc = scale[c], sh = shift[c], pb = pre_bias ? pre_bias[c] : 0.f;
   const float *p = x + (size_t)plane * HW + start;
   float *q = y + (size_t)plane * HW + start;
   const int mis = (int)((reinterpret_cast<uintptr_t>(p) >> 2) & 3);
   const int head = mis ? min((long long)(4 - mis), len) : 0;
-  if (threadIdx.x < head) q[threadIdx.x] = bn1<kRelu>(p[threadIdx.x], sc, sh);
+  if (threadIdx.x < head) q[threadIdx.x] = bn1<kRelu>(p[threadIdx.x], pb, sc, sh);
   const float4 *p4 = reinterpret_cast<const float4 *>(p + head);
   float4 *q4 = reinterpret_cast<float4 *>(q + head);
   const int n4 = (int)((len - head) >> 2);
 #pragma unroll 4
   for (int i = threadIdx.x; i < n4; i += kThreads) {
     const float4 v = p4[i];
-    q4[i] = make_float4(bn1<kRelu>(v.x, sc, sh), bn1<kRelu>(v.y, sc, sh), bn1<kRelu>(v.z, sc, sh), bn1<kRelu>(v.w, sc, sh));
+    q4[i] = make_float4(bn1<kRelu>(v.x, pb, sc, sh), bn1<kRelu>(v.y, pb, sc, sh), bn1<kRelu>(v.z, pb, sc, sh), bn1<kRelu>(v.w, pb, sc, sh));
   }
   const int tail0 = head + (n4 << 2);
-  if (tail0 + (int)threadIdx.x < len) q[tail0 + threadIdx.x] = bn1<kRelu>(p[tail0 + threadIdx.x], sc, sh);
+  if (tail0 + (int)threadIdx.x < len) q[tail0 + threadIdx.x] = bn1<kRelu>(p[tail0 + threadIdx.x], pb, sc, sh);
+}
+
+// Normalise (+ReLU) fused with the 2x2 / stride-2 max-pool that follows the last BN of every VGG stage
+// (reference daod/modeling/meta_arch/vgg.py:10-24): reads x once (4 B/element), writes the pooled map (1 B/element).
+// The affine map may have a negative scale, so it is applied per element BEFORE the max.
+// kVec: W % 4 == 0 and 16-byte aligned planes -> one float4 per input row and thread, two outputs (float2 store).
+constexpr int kPoolOutPerCta = 4096;  // pooled outputs per CTA
+template <bool kRelu, bool kVec>
+__global__ void __launch_bounds__(kThreads) bn_apply_pool_nchw_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
+                                                                      float *__restrict__ y, int C, int H, int W, int H2, int W2,
+                                                                      const float *__restrict__ scale, const float *__restrict__ shift) {
+  const int plane = blockIdx.y;
+  const int c = plane % C;
+  const float sc = scale[c], sh = shift[c], pb = pre_bias ? pre_bias[c] : 0.f;
+  const float *p = x + (size_t)plane * H * W;
+  float *q = y + (size_t)plane * H2 * W2;
+  const int total = H2 * W2;
+  const int o0 = blockIdx.x * kPoolOutPerCta;
+  const int o1 = min(o0 + kPoolOutPerCta, total);
+  if (kVec) {
+    const int W2h = W2 >> 1;  // output pairs per row
+    for (int i = (o0 >> 1) + threadIdx.x; i < (o1 >> 1); i += kThreads) {
+      const int oy = i / W2h, oxp = i - oy * W2h;
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(p + (size_t)(2 * oy) * W) + oxp);
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(p + (size_t)(2 * oy + 1) * W) + oxp);
+      float2 r;
+      r.x = fmaxf(fmaxf(bn1<kRelu>(a.x, pb, sc, sh), bn1<kRelu>(a.y, pb, sc, sh)), fmaxf(bn1<kRelu>(b.x, pb, sc, sh), bn1<kRelu>(b.y, pb, sc, sh)));
+      r.y = fmaxf(fmaxf(bn1<kRelu>(a.z, pb, sc, sh), bn1<kRelu>(a.w, pb, sc, sh)), fmaxf(bn1<kRelu>(b.z, pb, sc, sh), bn1<kRelu>(b.w, pb, sc, sh)));
+      reinterpret_cast<float2 *>(q + (size_t)oy * W2)[oxp] = r;
+    }
+  } else {
+    for (int o = o0 + threadIdx.x; o < o1; o += kThreads) {
+      const int oy = o / W2, ox = o - oy * W2;
+      const float *r0 = p + (size_t)(2 * oy) * W + 2 * ox;
+      const float *r1 = r0 + W;
+      const float v = fmaxf(fmaxf(bn1<kRelu>(__ldg(r0), pb, sc, sh), bn1<kRelu>(__ldg(r0 + 1), pb, sc, sh)),
+                            fmaxf(bn1<kRelu>(__ldg(r1), pb, sc, sh), bn1<kRelu>(__ldg(r1 + 1), pb, sc, sh)));
+      q[o] = v;
+    }
+  }
 }
 
 template <bool kRelu>
-__global__ void __launch_bounds__(kThreads) bn_apply_nhwc_kernel(const float *__restrict__ x, float *__restrict__ y, long long total4,
-                                                                 int G, const float *__restrict__ scale,
-                                                                 const float *__restrict__ shift) {
+__global__ void __launch_bounds__(kThreads) bn_apply_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
+                                                                 float *__restrict__ y, long long total4, int G,
+                                                                 const float *__restrict__ scale, const float *__restrict__ shift) {
   const float4 *x4 = reinterpret_cast<const float4 *>(x);
   float4 *y4 = reinterpret_cast<float4 *>(y);
   const float4 *sc4 = reinterpret_cast<const float4 *>(scale), *sh4 = reinterpret_cast<const float4 *>(shift);
+  const float4 *pb4 = reinterpret_cast<const float4 *>(pre_bias);
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total4; i += (long long)gridDim.x * kThreads) {
     const int g = (int)(i % G);
     const float4 v = x4[i], sc = __ldg(sc4 + g), sh = __ldg(sh4 + g);
-    y4[i] = make_float4(bn1<kRelu>(v.x, sc.x, sh.x), bn1<kRelu>(v.y, sc.y, sh.y), bn1<kRelu>(v.z, sc.z, sh.z),
-                        bn1<kRelu>(v.w, sc.w, sh.w));
+    const float4 pb = pre_bias ? __ldg(pb4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    y4[i] = make_float4(bn1<kRelu>(v.x, pb.x, sc.x, sh.x), bn1<kRelu>(v.y, pb.y, sc.y, sh.y), bn1<kRelu>(v.z, pb.z, sc.z, sh.z),
+                        bn1<kRelu>(v.w, pb.w, sc.w, sh.w));
+  }
+}
+
+// NHWC normalise(+ReLU)+max-pool: one thread per (n, oy, ox, channel group of 4): four float4 loads, one float4 store.
+template <bool kRelu>
+__global__ void __launch_bounds__(kThreads) bn_apply_pool_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
+                                                                      float *__restrict__ y, int N, int H, int W, int H2, int W2, int G,
+                                                                      const float *__restrict__ scale, const float *__restrict__ shift) {
+  const float4 *x4 = reinterpret_cast<const float4 *>(x);
+  float4 *y4 = reinterpret_cast<float4 *>(y);
+  const long long total = (long long)N * H2 * W2 * G;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int g = (int)(i % G);
+    long long r = i / G;
+    const int ox = (int)(r % W2); r /= W2;
+    const int oy = (int)(r % H2);
+    const int n = (int)(r / H2);
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + g), sh = __ldg(reinterpret_cast<const float4 *>(shift) + g);
+    const float4 pb = pre_bias ? __ldg(reinterpret_cast<const float4 *>(pre_bias) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t base = (((size_t)n * H + 2 * oy) * W + 2 * ox) * G + g;
+    const float4 a = __ldg(x4 + base), b = __ldg(x4 + base + G), c = __ldg(x4 + base + (size_t)W * G), d = __ldg(x4 + base + (size_t)W * G + G);
+    float4 o;
+    o.x = fmaxf(fmaxf(bn1<kRelu>(a.x, pb.x, sc.x, sh.x), bn1<kRelu>(b.x, pb.x, sc.x, sh.x)), fmaxf(bn1<kRelu>(c.x, pb.x, sc.x, sh.x), bn1<kRelu>(d.x, pb.x, sc.x, sh.x)));
+    o.y = fmaxf(fmaxf(bn1<kRelu>(a.y, pb.y, sc.y, sh.y), bn1<kRelu>(b.y, pb.y, sc.y, sh.y)), fmaxf(bn1<kRelu>(c.y, pb.y, sc.y, sh.y), bn1<kRelu>(d.y, pb.y, sc.y, sh.y)));
+    o.z = fmaxf(fmaxf(bn1<kRelu>(a.z, pb.z, sc.z, sh.z), bn1<kRelu>(b.z, pb.z, sc.z, sh.z)), fmaxf(bn1<kRelu>(c.z, pb.z, sc.z, sh.z), bn1<kRelu>(d.z, pb.z, sc.z, sh.z)));
+    o.w = fmaxf(fmaxf(bn1<kRelu>(a.w, pb.w, sc.w, sh.w), bn1<kRelu>(b.w, pb.w, sc.w, sh.w)), fmaxf(bn1<kRelu>(c.w, pb.w, sc.w, sh.w), bn1<kRelu>(d.w, pb.w, sc.w, sh.w)));
+    y4[i] = o;
   }
 }
 
 template <bool kRelu>
-__global__ void __launch_bounds__(kThreads) bn_apply_nhwc_scalar_kernel(const float *__restrict__ x, float *__restrict__ y,
-                                                                        long long total, int C, const float *__restrict__ scale,
-                                                                        const float *__restrict__ shift) {
+__global__ void __launch_bounds__(kThreads) bn_apply_nhwc_scalar_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
+                                                                        float *__restrict__ y, long long total, int C,
+                                                                        const float *__restrict__ scale, const float *__restrict__ shift) {
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
     const int c = (int)(i % C);
-    y[i] = bn1<kRelu>(x[i], scale[c], shift[c]);
+    y[i] = bn1<kRelu>(x[i], pre_bias ? pre_bias[c] : 0.f, scale[c], shift[c]);
   }
 }
 
@@ -219,7 +295,8 @@ SFOD_API size_t sfod_bn_stats_bytes(int C) { return C > 0 ? sfod_align_up((size_
 // stats_dev layout: [0, 2C) doubles = (sum x, sum x^2) per channel (the all-reduce payload);
 // [2C, 4C) reused by phase 2 as float scale/shift scratch.
 
-SFOD_API int sfod_bn_partial_stats(const float *x, int layout, int N, int C, int64_t HW, double *stats_dev, sfod_stream_t stream) {
+SFOD_API int sfod_bn_partial_stats(const float *x, const float *pre_bias, int layout, int N, int C, int64_t HW, double *stats_dev,
+                                   sfod_stream_t stream) {
   if (!x || !stats_dev || N <= 0 || C <= 0 || HW <= 0) return SFOD_ERR_INVALID_ARG;
   if (layout != SFOD_NCHW && layout != SFOD_NHWC) return SFOD_ERR_INVALID_ARG;
   cudaStream_t st = sfod_cu(stream);
@@ -231,14 +308,14 @@ SFOD_API int sfod_bn_partial_stats(const float *x, int layout, int N, int C, int
     for (long long p0 = 0; p0 < planes; p0 += step) {
       const long long np = planes - p0 < step ? planes - p0 : step;
       dim3 grid((unsigned)((HW + kChunk - 1) / kChunk), (unsigned)np);
-      bn_stats_nchw_kernel<<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, C, HW, stats_dev);
+      bn_stats_nchw_kernel<<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, pre_bias, C, HW, stats_dev);
       SFOD_LAUNCH_CHECK();
     }
     return SFOD_OK;
   }
   const long long M = (long long)N * HW;
-  if ((C & 3) || !sfod_aligned16(x)) {
-    bn_stats_nhwc_scalar_kernel<<<C, kThreads, 0, st>>>(x, M, C, stats_dev);
+  if ((C & 3) || !sfod_aligned16(x) || (pre_bias && !sfod_aligned16(pre_bias))) {
+    bn_stats_nhwc_scalar_kernel<<<C, kThreads, 0, st>>>(x, pre_bias, M, C, stats_dev);
     SFOD_LAUNCH_CHECK();
     return SFOD_OK;
   }
@@ -247,18 +324,20 @@ SFOD_API int sfod_bn_partial_stats(const float *x, int layout, int N, int C, int
   const int rowlanes = kThreads / cols;
   dim3 grid((unsigned)((M + (long long)rowlanes * 64 - 1) / ((long long)rowlanes * 64)), (unsigned)((G + cols - 1) / cols));
   const size_t smem = (size_t)rowlanes * cols * 9 * sizeof(double);
-  bn_stats_nhwc_kernel<<<grid, kThreads, smem, st>>>(x, M, C, cols, rowlanes, stats_dev);
+  bn_stats_nhwc_kernel<<<grid, kThreads, smem, st>>>(x, pre_bias, M, C, cols, rowlanes, stats_dev);
   SFOD_LAUNCH_CHECK();
   return SFOD_OK;
 }
 
-SFOD_API int sfod_bn_finalize_apply(const float *x, float *y, int layout, int N, int C, int64_t HW, const double *stats_dev,
-                                    double total_count, const float *weight, const float *bias, float *running_mean,
-                                    float *running_var, int64_t *num_batches_tracked, double momentum, double eps, int fuse_relu,
-                                    float *save_mean, float *save_invstd, sfod_stream_t stream) {
-  if (!stats_dev || N <= 0 || C <= 0 || HW <= 0 || total_count <= 0) return SFOD_ERR_INVALID_ARG;
+SFOD_API int sfod_bn_finalize_apply(const float *x, const float *pre_bias, float *y, int layout, int N, int C, int H, int W,
+                                    const double *stats_dev, double total_count, const float *weight, const float *bias,
+                                    float *running_mean, float *running_var, int64_t *num_batches_tracked, double momentum,
+                                    double eps, int fuse_relu, int fuse_maxpool2, float *save_mean, float *save_invstd,
+                                    sfod_stream_t stream) {
+  if (!stats_dev || N <= 0 || C <= 0 || H <= 0 || W <= 0 || total_count <= 0) return SFOD_ERR_INVALID_ARG;
   if (layout != SFOD_NCHW && layout != SFOD_NHWC) return SFOD_ERR_INVALID_ARG;
   cudaStream_t st = sfod_cu(stream);
+  const long long HW = (long long)H * W;
   float *scale = reinterpret_cast<float *>(const_cast<double *>(stats_dev) + 2 * (size_t)C);
   float *shift = scale + sfod_align_up((size_t)C, 4);
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_dev, C, total_count, weight, bias, running_mean, running_var,
@@ -266,6 +345,39 @@ SFOD_API int sfod_bn_finalize_apply(const float *x, float *y, int layout, int N,
                                                       save_mean, save_invstd, scale, shift);
   SFOD_LAUNCH_CHECK();
   if (!x || !y) return SFOD_OK;  // statistics-only mode (AdaBN does not need the normalised output of the last layer)
+  if (fuse_maxpool2) {
+    const int H2 = H / 2, W2 = W / 2;
+    if (H2 == 0 || W2 == 0) return SFOD_OK;  // empty pooled map
+    if (x == y) return SFOD_ERR_INVALID_ARG;  // the pooled output cannot alias the input
+    if (layout == SFOD_NCHW) {
+      const long long planes = (long long)N * C;
+      const long long step = 65535 / C * (long long)C;
+      if (step == 0) return SFOD_ERR_UNSUPPORTED;
+      const bool vec = (W % 4 == 0) && (HW % 4 == 0) && sfod_aligned16(x) && ((reinterpret_cast<uintptr_t>(y) & 7u) == 0);
+      for (long long p0 = 0; p0 < planes; p0 += step) {
+        const long long np = planes - p0 < step ? planes - p0 : step;
+        dim3 grid((unsigned)((H2 * W2 + kPoolOutPerCta - 1) / kPoolOutPerCta), (unsigned)np);
+        const float *xp = x + (size_t)p0 * HW;
+        float *yp = y + (size_t)p0 * H2 * W2;
+        if (vec) {
+          if (fuse_relu) bn_apply_pool_nchw_kernel<true, true><<<grid, kThreads, 0, st>>>(xp, pre_bias, yp, C, H, W, H2, W2, scale, shift);
+          else bn_apply_pool_nchw_kernel<false, true><<<grid, kThreads, 0, st>>>(xp, pre_bias, yp, C, H, W, H2, W2, scale, shift);
+        } else {
+          if (fuse_relu) bn_apply_pool_nchw_kernel<true, false><<<grid, kThreads, 0, st>>>(xp, pre_bias, yp, C, H, W, H2, W2, scale, shift);
+          else bn_apply_pool_nchw_kernel<false, false><<<grid, kThreads, 0, st>>>(xp, pre_bias, yp, C, H, W, H2, W2, scale, shift);
+        }
+        SFOD_LAUNCH_CHECK();
+      }
+      return SFOD_OK;
+    }
+    if ((C & 3) || !sfod_aligned16(x) || !sfod_aligned16(y) || (pre_bias && !sfod_aligned16(pre_bias))) return SFOD_ERR_UNSUPPORTED;
+    const long long total = (long long)N * H2 * W2 * (C >> 2);
+    const unsigned grid = (unsigned)min((long long)SFOD_NUM_SMS * 16, (total + kThreads - 1) / kThreads);
+    if (fuse_relu) bn_apply_pool_nhwc_kernel<true><<<grid, kThreads, 0, st>>>(x, pre_bias, y, N, H, W, H2, W2, C >> 2, scale, shift);
+    else bn_apply_pool_nhwc_kernel<false><<<grid, kThreads, 0, st>>>(x, pre_bias, y, N, H, W, H2, W2, C >> 2, scale, shift);
+    SFOD_LAUNCH_CHECK();
+    return SFOD_OK;
+  }
   if (layout == SFOD_NCHW) {
     const long long planes = (long long)N * C;
     const long long step = 65535 / C * (long long)C;
@@ -273,22 +385,22 @@ SFOD_API int sfod_bn_finalize_apply(const float *x, float *y, int layout, int N,
     for (long long p0 = 0; p0 < planes; p0 += step) {
       const long long np = planes - p0 < step ? planes - p0 : step;
       dim3 grid((unsigned)((HW + kChunk - 1) / kChunk), (unsigned)np);
-      if (fuse_relu) bn_apply_nchw_kernel<true><<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, y + (size_t)p0 * HW, C, HW, scale, shift);
-      else bn_apply_nchw_kernel<false><<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, y + (size_t)p0 * HW, C, HW, scale, shift);
+      if (fuse_relu) bn_apply_nchw_kernel<true><<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, pre_bias, y + (size_t)p0 * HW, C, HW, scale, shift);
+      else bn_apply_nchw_kernel<false><<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, pre_bias, y + (size_t)p0 * HW, C, HW, scale, shift);
       SFOD_LAUNCH_CHECK();
     }
     return SFOD_OK;
   }
   const long long total = (long long)N * HW * C;
-  if ((C & 3) || !sfod_aligned16(x) || !sfod_aligned16(y)) {
+  if ((C & 3) || !sfod_aligned16(x) || !sfod_aligned16(y) || (pre_bias && !sfod_aligned16(pre_bias))) {
     const unsigned grid = (unsigned)min((long long)SFOD_NUM_SMS * 8, (total + kThreads - 1) / kThreads);
-    if (fuse_relu) bn_apply_nhwc_scalar_kernel<true><<<grid, kThreads, 0, st>>>(x, y, total, C, scale, shift);
-    else bn_apply_nhwc_scalar_kernel<false><<<grid, kThreads, 0, st>>>(x, y, total, C, scale, shift);
+    if (fuse_relu) bn_apply_nhwc_scalar_kernel<true><<<grid, kThreads, 0, st>>>(x, pre_bias, y, total, C, scale, shift);
+    else bn_apply_nhwc_scalar_kernel<false><<<grid, kThreads, 0, st>>>(x, pre_bias, y, total, C, scale, shift);
   } else {
     const long long total4 = total >> 2;
     const unsigned grid = (unsigned)min((long long)SFOD_NUM_SMS * 16, (total4 + kThreads - 1) / kThreads);
-    if (fuse_relu) bn_apply_nhwc_kernel<true><<<grid, kThreads, 0, st>>>(x, y, total4, C >> 2, scale, shift);
-    else bn_apply_nhwc_kernel<false><<<grid, kThreads, 0, st>>>(x, y, total4, C >> 2, scale, shift);
+    if (fuse_relu) bn_apply_nhwc_kernel<true><<<grid, kThreads, 0, st>>>(x, pre_bias, y, total4, C >> 2, scale, shift);
+    else bn_apply_nhwc_kernel<false><<<grid, kThreads, 0, st>>>(x, pre_bias, y, total4, C >> 2, scale, shift);
   }
   SFOD_LAUNCH_CHECK();
   return SFOD_OK;

@@ -155,23 +155,37 @@ __global__ void __launch_bounds__(256) roi_align_bwd_generic_kernel(const float 
 }
 
 // --------------------------------------------------------------------------- separable fast path (7x7, NHWC)
+// Bilinear sampling + bin averaging is separable: out = A . F . B^T per channel, A (7 x H) and B (7 x W) built once per
+// ROI in shared memory.  The kernel is bound by instruction issue and L2 latency, not by DRAM (the feature map is
+// L2-resident and the 100 KB/ROI output is the only HBM traffic), so it is organised to minimise instructions per pixel:
+//   * one CTA = one ROI x 256 consecutive channels, 2 channels per thread (one LDG.64 per pixel, a warp reads 256
+//     contiguous bytes); the weight tables are warp-uniform shared-memory broadcasts (2 LDS.128 per pixel);
+//   * the channel stride is a template constant for the common C, so the <= 8 pixel loads of a batch are LDG.64 with
+//     immediate offsets from one base pointer (no per-load address arithmetic), issued before any FMA consumes them,
+//     and partial batches execute exactly their valid pixels (warp-uniform branches, no padded work);
+//   * the 7 bin rows are produced in two passes (bins 0-3, then 4-6), which halves the accumulator registers
+//     (28 pairs instead of 49) and lifts occupancy to 4 CTAs/SM; only rows shared by bins 3 and 4 are visited twice;
+//   * the (256 x 49) output tile is staged in shared memory with a conflict-free lane permutation and leaves the SM
+//     as ONE 50 176 B cp.async.bulk (TMA) store.
 constexpr int kPH = 7, kPW = 7, kBins = kPH * kPW;
 constexpr int kSepThreads = 128;           // 2 channels per thread
 constexpr int kCT = 2 * kSepThreads;       // 256 channels per CTA
 constexpr int kTileFloats = kCT * kBins;   // 12 544 floats = 50 176 B
+constexpr int kXB = 8;                     // pixels per load batch
 
 struct SepSmem {
-  float *tile;  // kTileFloats
-  float *Ad;    // H * 8 : Ad[y*8 + ph] = sum of y-weights of bin ph on row y, divided by grid_h
-  float *Bd;    // W * 8
-  int *lim;     // ymin, ymax, xmin, xmax
+  float *tile;   // kTileFloats
+  float *Ad;     // H * 8: Ad[y*8 + ph] = sum of y-weights of bin ph on row y, divided by grid_h
+  float *Bd;     // W * 8
+  int *lim;      // [0..3] ymin, ymax, xmin, xmax; [4..10] first row of bin ph; [11..17] last row of bin ph
 };
 __host__ __device__ inline size_t sep_smem_bytes(int H, int W) {
-  return (size_t)kTileFloats * 4 + (size_t)(H + W) * 8 * 4 + 16;
+  return (size_t)kTileFloats * 4 + (size_t)(H + W) * 8 * 4 + 32 * 4;
 }
 __device__ __forceinline__ SepSmem sep_carve(float *base, int H, int W) {
   SepSmem s;
-  s.tile = base; s.Ad = base + kTileFloats; s.Bd = s.Ad + H * 8; s.lim = reinterpret_cast<int *>(s.Bd + W * 8);
+  s.tile = base; s.Ad = base + kTileFloats; s.Bd = s.Ad + H * 8;
+  s.lim = reinterpret_cast<int *>(s.Bd + W * 8);
   return s;
 }
 
@@ -190,6 +204,7 @@ __device__ __forceinline__ void sep_build_tables(const SepSmem &s, const RoiGeom
       s.Ad[lo * 8 + ph] += h * inv; s.Ad[hi * 8 + ph] += l * inv;
       mn = min(mn, lo); mx = max(mx, hi);
     }
+    s.lim[4 + ph] = mn; s.lim[11 + ph] = mx;
     if (mx >= 0) { atomicMin(&s.lim[0], mn); atomicMax(&s.lim[1], mx); }
   } else if (tid >= 32 && tid < 32 + kPW) {
     const int pw = tid - 32; int mn = W, mx = -1;
@@ -205,13 +220,78 @@ __device__ __forceinline__ void sep_build_tables(const SepSmem &s, const RoiGeom
   __syncthreads();
 }
 
-__device__ __forceinline__ float2 ldg_f2(const float *p) {
-  float2 r;
-  asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-  return r;
+// T[b] += B[x][b] * f for the two channels of this thread (weights are scalar, warp-uniform shared-memory broadcasts).
+__device__ __forceinline__ void sep_row_fma(float2 (&T)[kPW], const float *__restrict__ bw, float2 f) {
+  const float4 w0 = *reinterpret_cast<const float4 *>(bw), w1 = *reinterpret_cast<const float4 *>(bw + 4);
+  T[0].x = fmaf(w0.x, f.x, T[0].x); T[0].y = fmaf(w0.x, f.y, T[0].y);
+  T[1].x = fmaf(w0.y, f.x, T[1].x); T[1].y = fmaf(w0.y, f.y, T[1].y);
+  T[2].x = fmaf(w0.z, f.x, T[2].x); T[2].y = fmaf(w0.z, f.y, T[2].y);
+  T[3].x = fmaf(w0.w, f.x, T[3].x); T[3].y = fmaf(w0.w, f.y, T[3].y);
+  T[4].x = fmaf(w1.x, f.x, T[4].x); T[4].y = fmaf(w1.x, f.y, T[4].y);
+  T[5].x = fmaf(w1.y, f.x, T[5].x); T[5].y = fmaf(w1.y, f.y, T[5].y);
+  T[6].x = fmaf(w1.z, f.x, T[6].x); T[6].y = fmaf(w1.z, f.y, T[6].y);
 }
 
-__global__ void __launch_bounds__(kSepThreads, 3) roi_align_fwd_sep_kernel(const float *__restrict__ feat /* NHWC */,
+// One pass over the rows feeding bins [PH0, PH0 + NPH): accumulates and writes those bin rows of the output tile.
+// fbase2: float2 pointer to (image, pixel 0, this thread's channel pair); cs2: channel stride in float2 units.
+template <int PH0, int NPH, int kC>
+__device__ __forceinline__ void sep_fwd_pass(const SepSmem &s, const float2 *__restrict__ fbase2, int C, int W, int xmin, int xmax,
+                                             float *__restrict__ t0, float *__restrict__ t1, int half) {
+  const int cs2 = (kC ? kC : C) >> 1;
+  int y0 = s.lim[4 + PH0], y1 = s.lim[11 + PH0];
+#pragma unroll
+  for (int a = 1; a < NPH; ++a) { y0 = min(y0, s.lim[4 + PH0 + a]); y1 = max(y1, s.lim[11 + PH0 + a]); }
+  float2 acc[NPH][kPW];
+#pragma unroll
+  for (int a = 0; a < NPH; ++a)
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) acc[a][b] = make_float2(0.f, 0.f);
+  for (int y = y0; y <= y1; ++y) {
+    float2 T[kPW];
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) T[b] = make_float2(0.f, 0.f);
+    const float2 *prow = fbase2 + (size_t)y * W * cs2;
+    for (int x0 = xmin; x0 <= xmax; x0 += kXB) {
+      const float2 *p = prow + (size_t)x0 * cs2;
+      const float *bw = s.Bd + x0 * 8;
+      const int nv = xmax - x0 + 1;   // warp-uniform
+      float2 f[kXB];
+      if (nv >= kXB) {
+#pragma unroll
+        for (int i = 0; i < kXB; ++i) f[i] = __ldg(p + (size_t)i * cs2);
+#pragma unroll
+        for (int i = 0; i < kXB; ++i) sep_row_fma(T, bw + 8 * i, f[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kXB - 1; ++i) if (i < nv) f[i] = __ldg(p + (size_t)i * cs2);
+#pragma unroll
+        for (int i = 0; i < kXB - 1; ++i) if (i < nv) sep_row_fma(T, bw + 8 * i, f[i]);
+      }
+    }
+    const float4 av4 = *reinterpret_cast<const float4 *>(s.Ad + y * 8 + PH0);   // PH0 in {0, 4}: 16-byte aligned
+    const float av[4] = {av4.x, av4.y, av4.z, av4.w};
+#pragma unroll
+    for (int a = 0; a < NPH; ++a) {
+      if (av[a] != 0.f) {  // warp-uniform (broadcast shared-memory value)
+#pragma unroll
+        for (int b = 0; b < kPW; ++b) { acc[a][b].x = fmaf(av[a], T[b].x, acc[a][b].x); acc[a][b].y = fmaf(av[a], T[b].y, acc[a][b].y); }
+      }
+    }
+  }
+  // registers -> shared tile (flat [channel][49], the global layout).  Lanes 0-15 write their even channel while lanes
+  // 16-31 write their odd channel (and vice versa): word index (2*tid + j)*49 + k hits 32 distinct banks per instruction.
+#pragma unroll
+  for (int a = 0; a < NPH; ++a)
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) {
+      const float v0 = acc[a][b].x, v1 = acc[a][b].y;
+      t0[(PH0 + a) * kPW + b] = half ? v1 : v0;
+      t1[(PH0 + a) * kPW + b] = half ? v0 : v1;
+    }
+}
+
+template <int kC>
+__global__ void __launch_bounds__(kSepThreads, 4) roi_align_fwd_sep_kernel(const float *__restrict__ feat /* NHWC */,
                                                                            const float *__restrict__ rois, int N, int C, int H,
                                                                            int W, float scale, int sampling_ratio, int aligned,
                                                                            float *__restrict__ output) {
@@ -225,64 +305,18 @@ __global__ void __launch_bounds__(kSepThreads, 3) roi_align_fwd_sep_kernel(const
   const int ymin = s.lim[0], ymax = s.lim[1], xmin = s.lim[2], xmax = s.lim[3];
   const int c0 = cbase + 2 * tid;
   const bool active = c0 < C;
-
-  float acc[kPH][kPW][2];
-#pragma unroll
-  for (int a = 0; a < kPH; ++a)
-#pragma unroll
-    for (int b = 0; b < kPW; ++b) { acc[a][b][0] = 0.f; acc[a][b][1] = 0.f; }
-
-  if (active && ymax >= ymin && xmax >= xmin) {
-    const float *fbase = feat + (size_t)g.n * H * W * C + c0;
-    for (int y = ymin; y <= ymax; ++y) {
-      float T[kPW][2];
-#pragma unroll
-      for (int b = 0; b < kPW; ++b) { T[b][0] = 0.f; T[b][1] = 0.f; }
-      const float *frow = fbase + (size_t)y * W * C;
-#pragma unroll 4
-      for (int x = xmin; x <= xmax; ++x) {
-        const float2 f = ldg_f2(frow + (size_t)x * C);
-        const float4 b0 = *reinterpret_cast<const float4 *>(s.Bd + x * 8);
-        const float4 b1 = *reinterpret_cast<const float4 *>(s.Bd + x * 8 + 4);
-        T[0][0] = fmaf(b0.x, f.x, T[0][0]); T[0][1] = fmaf(b0.x, f.y, T[0][1]);
-        T[1][0] = fmaf(b0.y, f.x, T[1][0]); T[1][1] = fmaf(b0.y, f.y, T[1][1]);
-        T[2][0] = fmaf(b0.z, f.x, T[2][0]); T[2][1] = fmaf(b0.z, f.y, T[2][1]);
-        T[3][0] = fmaf(b0.w, f.x, T[3][0]); T[3][1] = fmaf(b0.w, f.y, T[3][1]);
-        T[4][0] = fmaf(b1.x, f.x, T[4][0]); T[4][1] = fmaf(b1.x, f.y, T[4][1]);
-        T[5][0] = fmaf(b1.y, f.x, T[5][0]); T[5][1] = fmaf(b1.y, f.y, T[5][1]);
-        T[6][0] = fmaf(b1.z, f.x, T[6][0]); T[6][1] = fmaf(b1.z, f.y, T[6][1]);
-      }
-      const float4 a0 = *reinterpret_cast<const float4 *>(s.Ad + y * 8);
-      const float4 a1 = *reinterpret_cast<const float4 *>(s.Ad + y * 8 + 4);
-      const float av[kPH] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z};
-#pragma unroll
-      for (int a = 0; a < kPH; ++a) {
-        if (av[a] != 0.f) {  // warp-uniform (broadcast shared-memory value)
-#pragma unroll
-          for (int b = 0; b < kPW; ++b) {
-            acc[a][b][0] = fmaf(av[a], T[b][0], acc[a][b][0]);
-            acc[a][b][1] = fmaf(av[a], T[b][1], acc[a][b][1]);
-          }
-        }
-      }
-    }
-  }
-
-  // ---- epilogue: registers -> shared tile (flat [channel][49], the global layout) -> one bulk store.
-  // Lanes 0-15 write their even channel while lanes 16-31 write their odd channel (and vice versa):
-  // word index (2*tid + j)*49 + k hits 32 distinct banks per instruction.
   if (active) {
     const int half = (tid >> 4) & 1;
     float *t0 = s.tile + (size_t)(2 * tid + half) * kBins;
     float *t1 = s.tile + (size_t)(2 * tid + 1 - half) * kBins;
+    if (ymax >= ymin && xmax >= xmin) {
+      const float2 *fbase2 = reinterpret_cast<const float2 *>(feat + (size_t)g.n * H * W * C + c0);
+      sep_fwd_pass<0, 4, kC>(s, fbase2, C, W, xmin, xmax, t0, t1, half);
+      sep_fwd_pass<4, 3, kC>(s, fbase2, C, W, xmin, xmax, t0, t1, half);
+    } else {
 #pragma unroll
-    for (int a = 0; a < kPH; ++a)
-#pragma unroll
-      for (int b = 0; b < kPW; ++b) {
-        const float v0 = acc[a][b][0], v1 = acc[a][b][1];
-        t0[a * kPW + b] = half ? v1 : v0;
-        t1[a * kPW + b] = half ? v0 : v1;
-      }
+      for (int k = 0; k < kBins; ++k) { t0[k] = 0.f; t1[k] = 0.f; }
+    }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -297,9 +331,56 @@ __global__ void __launch_bounds__(kSepThreads, 3) roi_align_fwd_sep_kernel(const
   }
 }
 
-// Backward of the separable form: gF = A^T . gOut . B per channel, accumulated into an NHWC gradient
-// with 8-byte vector atomics (red.global.add.v2.f32): one coalesced 256 B reduction per warp and pixel.
-__global__ void __launch_bounds__(kSepThreads, 3) roi_align_bwd_sep_kernel(const float *__restrict__ grad_out,
+// Backward of the separable form: gF = A^T . gOut . B per channel pair, accumulated into an NHWC gradient with 8-byte
+// vector reductions (red.global.add.v2.f32): one coalesced 256 B reduction per warp and pixel; same two-pass structure.
+template <int PH0, int NPH, int kC>
+__device__ __forceinline__ void sep_bwd_pass(const SepSmem &s, float2 *__restrict__ gbase2, int C, int W, int xmin, int xmax,
+                                             const float *__restrict__ t0, const float *__restrict__ t1, int half) {
+  const int cs2 = (kC ? kC : C) >> 1;
+  int y0 = s.lim[4 + PH0], y1 = s.lim[11 + PH0];
+#pragma unroll
+  for (int a = 1; a < NPH; ++a) { y0 = min(y0, s.lim[4 + PH0 + a]); y1 = max(y1, s.lim[11 + PH0 + a]); }
+  float2 go[NPH][kPW];
+#pragma unroll
+  for (int a = 0; a < NPH; ++a)
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) {
+      const float u0 = t0[(PH0 + a) * kPW + b], u1 = t1[(PH0 + a) * kPW + b];
+      go[a][b] = half ? make_float2(u1, u0) : make_float2(u0, u1);
+    }
+  for (int y = y0; y <= y1; ++y) {
+    const float4 av4 = *reinterpret_cast<const float4 *>(s.Ad + y * 8 + PH0);
+    const float av[4] = {av4.x, av4.y, av4.z, av4.w};
+    float2 U[kPW];
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) U[b] = make_float2(0.f, 0.f);
+    bool any = false;
+#pragma unroll
+    for (int a = 0; a < NPH; ++a) {
+      if (av[a] != 0.f) {
+        any = true;
+#pragma unroll
+        for (int b = 0; b < kPW; ++b) { U[b].x = fmaf(av[a], go[a][b].x, U[b].x); U[b].y = fmaf(av[a], go[a][b].y, U[b].y); }
+      }
+    }
+    if (!any) continue;
+    float2 *grow = gbase2 + (size_t)y * W * cs2;
+    for (int x = xmin; x <= xmax; ++x) {
+      const float4 w0 = *reinterpret_cast<const float4 *>(s.Bd + x * 8), w1 = *reinterpret_cast<const float4 *>(s.Bd + x * 8 + 4);
+      float2 v = make_float2(w0.x * U[0].x, w0.x * U[0].y);
+      v.x = fmaf(w0.y, U[1].x, v.x); v.y = fmaf(w0.y, U[1].y, v.y);
+      v.x = fmaf(w0.z, U[2].x, v.x); v.y = fmaf(w0.z, U[2].y, v.y);
+      v.x = fmaf(w0.w, U[3].x, v.x); v.y = fmaf(w0.w, U[3].y, v.y);
+      v.x = fmaf(w1.x, U[4].x, v.x); v.y = fmaf(w1.x, U[4].y, v.y);
+      v.x = fmaf(w1.y, U[5].x, v.x); v.y = fmaf(w1.y, U[5].y, v.y);
+      v.x = fmaf(w1.z, U[6].x, v.x); v.y = fmaf(w1.z, U[6].y, v.y);
+      atomicAdd(grow + (size_t)x * cs2, v);   // result unused -> RED.E.ADD.F32x2
+    }
+  }
+}
+
+template <int kC>
+__global__ void __launch_bounds__(kSepThreads, 4) roi_align_bwd_sep_kernel(const float *__restrict__ grad_out,
                                                                            const float *__restrict__ rois, int N, int C, int H,
                                                                            int W, float scale, int sampling_ratio, int aligned,
                                                                            float *__restrict__ grad_nhwc) {
@@ -315,59 +396,18 @@ __global__ void __launch_bounds__(kSepThreads, 3) roi_align_bwd_sep_kernel(const
     const float4 *src = reinterpret_cast<const float4 *>(grad_out + ((size_t)r * C + cbase) * kBins);
     float4 *dst = reinterpret_cast<float4 *>(s.tile);
     const int n4 = nch * kBins / 4;
-    for (int i = tid; i < n4; i += kSepThreads) dst[i] = src[i];
+    for (int i = tid; i < n4; i += kSepThreads) dst[i] = __ldg(src + i);
   }
   sep_build_tables(s, g, H, W);  // contains the barriers that also publish the tile
   const int ymin = s.lim[0], ymax = s.lim[1], xmin = s.lim[2], xmax = s.lim[3];
   const int c0 = cbase + 2 * tid;
   if (c0 >= C || ymax < ymin || xmax < xmin) return;
-  float go[kPH][kPW][2];
-  {
-    const int half = (tid >> 4) & 1;
-    const float *t0 = s.tile + (size_t)(2 * tid + half) * kBins;
-    const float *t1 = s.tile + (size_t)(2 * tid + 1 - half) * kBins;
-#pragma unroll
-    for (int a = 0; a < kPH; ++a)
-#pragma unroll
-      for (int b = 0; b < kPW; ++b) {
-        const float u0 = t0[a * kPW + b], u1 = t1[a * kPW + b];
-        go[a][b][0] = half ? u1 : u0;
-        go[a][b][1] = half ? u0 : u1;
-      }
-  }
-  float *gbase = grad_nhwc + (size_t)g.n * H * W * C + c0;
-  for (int y = ymin; y <= ymax; ++y) {
-    const float4 a0 = *reinterpret_cast<const float4 *>(s.Ad + y * 8);
-    const float4 a1 = *reinterpret_cast<const float4 *>(s.Ad + y * 8 + 4);
-    const float av[kPH] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z};
-    float U[kPW][2];
-#pragma unroll
-    for (int b = 0; b < kPW; ++b) { U[b][0] = 0.f; U[b][1] = 0.f; }
-#pragma unroll
-    for (int a = 0; a < kPH; ++a) {
-      if (av[a] != 0.f) {
-#pragma unroll
-        for (int b = 0; b < kPW; ++b) {
-          U[b][0] = fmaf(av[a], go[a][b][0], U[b][0]);
-          U[b][1] = fmaf(av[a], go[a][b][1], U[b][1]);
-        }
-      }
-    }
-    float *grow = gbase + (size_t)y * W * C;
-    for (int x = xmin; x <= xmax; ++x) {
-      const float4 b0 = *reinterpret_cast<const float4 *>(s.Bd + x * 8);
-      const float4 b1 = *reinterpret_cast<const float4 *>(s.Bd + x * 8 + 4);
-      float2 v;
-      v.x = b0.x * U[0][0]; v.y = b0.x * U[0][1];
-      v.x = fmaf(b0.y, U[1][0], v.x); v.y = fmaf(b0.y, U[1][1], v.y);
-      v.x = fmaf(b0.z, U[2][0], v.x); v.y = fmaf(b0.z, U[2][1], v.y);
-      v.x = fmaf(b0.w, U[3][0], v.x); v.y = fmaf(b0.w, U[3][1], v.y);
-      v.x = fmaf(b1.x, U[4][0], v.x); v.y = fmaf(b1.x, U[4][1], v.y);
-      v.x = fmaf(b1.y, U[5][0], v.x); v.y = fmaf(b1.y, U[5][1], v.y);
-      v.x = fmaf(b1.z, U[6][0], v.x); v.y = fmaf(b1.z, U[6][1], v.y);
-      atomicAdd(reinterpret_cast<float2 *>(grow + (size_t)x * C), v);
-    }
-  }
+  const int half = (tid >> 4) & 1;
+  const float *t0 = s.tile + (size_t)(2 * tid + half) * kBins;
+  const float *t1 = s.tile + (size_t)(2 * tid + 1 - half) * kBins;
+  float2 *gbase2 = reinterpret_cast<float2 *>(grad_nhwc + (size_t)g.n * H * W * C + c0);
+  sep_bwd_pass<0, 4, kC>(s, gbase2, C, W, xmin, xmax, t0, t1, half);
+  sep_bwd_pass<4, 3, kC>(s, gbase2, C, W, xmin, xmax, t0, t1, half);
 }
 
 // --------------------------------------------------------------------------- ROIPool
@@ -417,7 +457,7 @@ __global__ void __launch_bounds__(256) roi_pool_bwd_kernel(const float *__restri
 }
 
 bool sep_supported(int C, int H, int W, int PH, int PW) {
-  return PH == kPH && PW == kPW && (C % 4) == 0 && sep_smem_bytes(H, W) <= 72 * 1024;
+  return PH == kPH && PW == kPW && (C % 4) == 0 && sep_smem_bytes(H, W) <= 100 * 1024;
 }
 
 }  // namespace
@@ -458,9 +498,20 @@ SFOD_API int sfod_roi_align_fwd(const float *input, int layout, const float *roi
     }
     if (!sfod_aligned16(feat)) return SFOD_ERR_ALIGNMENT;
     const size_t smem = sep_smem_bytes(H, W);
-    SFOD_CUDA_TRY(cudaFuncSetAttribute(roi_align_fwd_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(R, (C + kCT - 1) / kCT);
-    roi_align_fwd_sep_kernel<<<grid, kSepThreads, smem, st>>>(feat, rois, N, C, H, W, spatial_scale, sampling_ratio, aligned, output);
+#define SFOD_ROI_FWD(KC)                                                                                                     \
+    do {                                                                                                                     \
+      SFOD_CUDA_TRY(cudaFuncSetAttribute(roi_align_fwd_sep_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      roi_align_fwd_sep_kernel<KC><<<grid, kSepThreads, smem, st>>>(feat, rois, N, C, H, W, spatial_scale, sampling_ratio, aligned, output); \
+    } while (0)
+    switch (C) {
+      case 256: SFOD_ROI_FWD(256); break;
+      case 512: SFOD_ROI_FWD(512); break;
+      case 1024: SFOD_ROI_FWD(1024); break;
+      case 2048: SFOD_ROI_FWD(2048); break;
+      default: SFOD_ROI_FWD(0); break;
+    }
+#undef SFOD_ROI_FWD
     SFOD_LAUNCH_CHECK();
     return SFOD_OK;
   }
@@ -500,9 +551,20 @@ SFOD_API int sfod_roi_align_bwd(const float *grad_out, const float *rois, int N,
     }
     SFOD_CUDA_TRY(cudaMemsetAsync(acc, 0, fbytes, st));
     const size_t smem = sep_smem_bytes(H, W);
-    SFOD_CUDA_TRY(cudaFuncSetAttribute(roi_align_bwd_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(R, (C + kCT - 1) / kCT);
-    roi_align_bwd_sep_kernel<<<grid, kSepThreads, smem, st>>>(grad_out, rois, N, C, H, W, spatial_scale, sampling_ratio, aligned, acc);
+#define SFOD_ROI_BWD(KC)                                                                                                     \
+    do {                                                                                                                     \
+      SFOD_CUDA_TRY(cudaFuncSetAttribute(roi_align_bwd_sep_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      roi_align_bwd_sep_kernel<KC><<<grid, kSepThreads, smem, st>>>(grad_out, rois, N, C, H, W, spatial_scale, sampling_ratio, aligned, acc); \
+    } while (0)
+    switch (C) {
+      case 256: SFOD_ROI_BWD(256); break;
+      case 512: SFOD_ROI_BWD(512); break;
+      case 1024: SFOD_ROI_BWD(1024); break;
+      case 2048: SFOD_ROI_BWD(2048); break;
+      default: SFOD_ROI_BWD(0); break;
+    }
+#undef SFOD_ROI_BWD
     SFOD_LAUNCH_CHECK();
     if (layout == SFOD_NCHW) return launch_transpose(acc, grad_in, N, H * W, C, st);
     return SFOD_OK;

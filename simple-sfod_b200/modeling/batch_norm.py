@@ -33,13 +33,20 @@ class SfodBatchNorm2d(nn.BatchNorm2d):
         return (self.training and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
                 and self.track_running_stats and self.momentum is not None)
 
-    def forward(self, x: Tensor, fuse_relu: bool = False, inplace: bool = False) -> Tensor:
+    def forward(self, x: Tensor, fuse_relu: bool = False, inplace: bool = False, pre_bias: Optional[Tensor] = None,
+                fuse_maxpool: bool = False) -> Tensor:
+        """``pre_bias`` / ``fuse_relu`` / ``fuse_maxpool`` let a caller that owns the surrounding ``conv -> BN -> ReLU
+        [-> MaxPool2d(2, 2)]`` chain (``modeling/vgg.py``) hand the neighbours' elementwise work to the BN kernels."""
         if self._native_ok(x):
             return ops.bn_train_forward(x, self.weight, self.bias, self.running_mean, self.running_var,
                                         self.num_batches_tracked, self.momentum, self.eps, fuse_relu=fuse_relu,
-                                        inplace=inplace, group=self.process_group)
+                                        inplace=inplace, group=self.process_group, pre_bias=pre_bias, fuse_maxpool=fuse_maxpool)
+        if pre_bias is not None:
+            x = x + pre_bias.view(1, -1, 1, 1)
         y = super().forward(x)
-        return torch.relu_(y) if fuse_relu else y
+        if fuse_relu:
+            y = torch.relu_(y)
+        return torch.nn.functional.max_pool2d(y, 2, 2) if fuse_maxpool else y
 
 
 def convert_batchnorm(module: nn.Module, process_group=None) -> nn.Module:

@@ -35,17 +35,34 @@ def make_layers(cfg: List[Union[str, int]], batch_norm: bool = False) -> List[nn
     return layers
 
 
+def _is_pool2(m: nn.Module) -> bool:
+    def two(v):
+        return v == 2 or v == (2, 2)
+    return (isinstance(m, nn.MaxPool2d) and two(m.kernel_size) and two(m.stride) and m.padding in (0, (0, 0))
+            and m.dilation in (1, (1, 1)) and not m.ceil_mode and not m.return_indices)
+
+
 class _Stage(nn.Sequential):
-    """nn.Sequential (same child names, hence the reference's state_dict keys) whose forward fuses BN+ReLU pairs
-    into one in-place kernel call when the BN runs on the native path."""
+    """nn.Sequential (same child names, hence the reference's state_dict keys) whose forward hands the elementwise
+    neighbours of a natively executed BatchNorm to the BN kernels: the bias of the preceding convolution (which then
+    runs bias-free on cuDNN), the following ReLU and, at the end of a stage, the 2x2 max-pool.  Per element the
+    arithmetic is unchanged: fl(conv + bias) -> normalise -> ReLU -> max."""
 
     def forward(self, x: Tensor) -> Tensor:
         mods = list(self)
-        i = 0
-        while i < len(mods):
+        i, n = 0, len(mods)
+        while i < n:
             m = mods[i]
-            if isinstance(m, SfodBatchNorm2d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU) and m._native_ok(x):
-                x = m(x, fuse_relu=True, inplace=True)  # x is the conv output: private to this forward
+            nxt = mods[i + 1] if i + 1 < n else None
+            if isinstance(m, nn.Conv2d) and isinstance(nxt, SfodBatchNorm2d) and nxt._native_ok(x):
+                z = nn.functional.conv2d(x, m.weight, None, m.stride, m.padding, m.dilation, m.groups)  # bias goes to the BN kernels
+                relu = i + 2 < n and isinstance(mods[i + 2], nn.ReLU)
+                pool = relu and i + 3 < n and _is_pool2(mods[i + 3])
+                x = nxt(z, fuse_relu=relu, inplace=True, pre_bias=m.bias, fuse_maxpool=pool)  # z is private to this forward
+                i += 2 + int(relu) + int(pool)
+                continue
+            if isinstance(m, SfodBatchNorm2d) and isinstance(nxt, nn.ReLU) and m._native_ok(x):
+                x = m(x, fuse_relu=True, inplace=i > 0)  # in place only on an intermediate produced inside this stage
                 i += 2
                 continue
             x = m(x)

@@ -496,21 +496,28 @@ class EmaPlan:
 def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], running_mean: Optional[Tensor],
                      running_var: Optional[Tensor], num_batches_tracked: Optional[Tensor], momentum: float = 0.1,
                      eps: float = 1e-5, fuse_relu: bool = False, inplace: bool = False, group=None,
-                     compute_output: bool = True) -> Optional[Tensor]:
+                     compute_output: bool = True, pre_bias: Optional[Tensor] = None, fuse_maxpool: bool = False) -> Optional[Tensor]:
     """Train-mode BatchNorm2d forward without autograd (the AdaBN / no_grad-teacher case): batch statistics,
-    running-stat update, normalise(+ReLU).  With ``group`` (a torch.distributed process group) the per-channel
-    (sum, sum^2, count) triple is all-reduced so that all ranks normalise with the statistics of the
+    running-stat update, normalise(+ReLU)(+2x2 max-pool).  ``pre_bias`` (C) is added to ``x`` first (the bias of the
+    convolution feeding the BN, so the convolution itself can run bias-free).  With ``group`` (a torch.distributed process
+    group) the per-channel (sum, sum^2, count) triple is all-reduced so that all ranks normalise with the statistics of the
     concatenated batch."""
-    dev = _require_cuda(x)
+    dev = _require_cuda(x, pre_bias)
     xin, layout = _layout_of(x.detach())
     if xin.dtype != torch.float32:
         raise TypeError("bn_train_forward computes in float32")
     N, Cc, H, W = xin.shape
+    pb = None
+    if pre_bias is not None:
+        pb = pre_bias.detach()
+        if pb.dtype != torch.float32 or pb.numel() != Cc or not pb.is_contiguous():
+            raise ValueError("pre_bias must be a contiguous float32 tensor with one entry per channel")
     L = _lib.lib()
     with torch.cuda.device(dev):
         stats = torch.empty((L.sfod_bn_stats_bytes(Cc) // 8,), dtype=torch.float64, device=dev)
         with _timed("bn_partial_stats"):
-            check(L.sfod_bn_partial_stats(xin.data_ptr(), layout, N, Cc, H * W, stats.data_ptr(), _stream(dev)), "sfod_bn_partial_stats")
+            check(L.sfod_bn_partial_stats(xin.data_ptr(), pb.data_ptr() if pb is not None else None, layout, N, Cc, H * W,
+                                          stats.data_ptr(), _stream(dev)), "sfod_bn_partial_stats")
         total = float(N * H * W)
         if group is not None:
             from .engine.adabn_dist import allreduce_bn_stats
@@ -518,15 +525,19 @@ def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor]
             total = allreduce_bn_stats(stats, Cc, group=group if group is not True else None)
         y = None
         if compute_output:
-            y = xin if inplace else torch.empty_like(xin)
-        with _timed("bn_finalize_apply"):
-            check(L.sfod_bn_finalize_apply(xin.data_ptr() if compute_output else None, y.data_ptr() if y is not None else None, layout,
-                                           N, Cc, H * W, stats.data_ptr(), total,
+            if fuse_maxpool:
+                fmt = torch.channels_last if layout == NHWC else torch.contiguous_format
+                y = torch.empty((N, Cc, H // 2, W // 2), dtype=torch.float32, device=dev, memory_format=fmt)
+            else:
+                y = xin if inplace else torch.empty_like(xin)
+        with _timed("bn_finalize_apply_pool" if fuse_maxpool else "bn_finalize_apply"):
+            check(L.sfod_bn_finalize_apply(xin.data_ptr() if compute_output else None, pb.data_ptr() if pb is not None else None,
+                                           y.data_ptr() if y is not None else None, layout, N, Cc, H, W, stats.data_ptr(), total,
                                            weight.data_ptr() if weight is not None else None,
                                            bias.data_ptr() if bias is not None else None,
                                            running_mean.data_ptr() if running_mean is not None else None,
                                            running_var.data_ptr() if running_var is not None else None,
                                            num_batches_tracked.data_ptr() if num_batches_tracked is not None else None,
-                                           float(momentum), float(eps), int(fuse_relu), None, None, _stream(dev)),
+                                           float(momentum), float(eps), int(fuse_relu), int(fuse_maxpool), None, None, _stream(dev)),
                   "sfod_bn_finalize_apply")
     return y

@@ -378,3 +378,77 @@ def test_bn_train_forward(ops, cuda_device, shape, layout):
     assert nbt.item() == 1
     yr = ops.bn_train_forward(xd, bn.weight.detach().to(d), bn.bias.detach().to(d), None, None, None, 0.1, 1e-5, fuse_relu=True)
     _close(yr, torch.relu(yref), rtol=1e-5, atol_scale=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 76, 152), (2, 32, 75, 150), (1, 16, 37, 75), (2, 8, 5, 3)])
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_bn_fused_conv_bias_relu_maxpool(ops, cuda_device, shape, layout):
+    """conv bias + BN(train) + ReLU + MaxPool2d(2, 2) in the two BN kernels vs the unfused torch-CPU chain
+    (reference vgg.py:15-19).  Running statistics must be those of fl(x + bias)."""
+    g = torch.Generator().manual_seed(81)
+    N, C, H, W = shape
+    x = torch.randn(shape, generator=g) * 2
+    cb = torch.randn(C, generator=g) * 5
+    bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.uniform_(-1.5, 1.5, generator=g); bn.bias.uniform_(-1, 1, generator=g)     # negative scales: max must follow the affine map
+        bn.running_mean.normal_(generator=g); bn.running_var.uniform_(0.5, 2.0, generator=g)
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    bn.train()
+    with torch.no_grad():
+        full = torch.relu(bn(x + cb.view(1, -1, 1, 1)))
+        pooled = torch.nn.functional.max_pool2d(full, 2, 2)
+    d = cuda_device
+    xd = x.to(d)
+    if layout == "nhwc":
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    for pool, want in ((False, full), (True, pooled)):
+        rm, rv = rm0.to(d), rv0.to(d); nbt = torch.zeros((), dtype=torch.int64, device=d)
+        y = ops.bn_train_forward(xd, bn.weight.detach().to(d), bn.bias.detach().to(d), rm, rv, nbt, 0.1, 1e-5, fuse_relu=True,
+                                 pre_bias=cb.to(d), fuse_maxpool=pool)
+        assert y.shape == want.shape
+        _close(y, want, rtol=1e-5, atol_scale=1e-5)
+        _close(rm, bn.running_mean, rtol=1e-5, atol_scale=1e-6)
+        _close(rv, bn.running_var, rtol=1e-5, atol_scale=0)
+    # pre_bias == None must equal pre_bias == 0 bit for bit
+    y0 = ops.bn_train_forward(xd, None, None, None, None, None, fuse_relu=False)
+    y1 = ops.bn_train_forward(xd, None, None, None, None, None, fuse_relu=False, pre_bias=torch.zeros(C, device=d))
+    assert torch.equal(y0, y1)
+
+
+def test_vgg_stage_fusion_matches_unfused_modules(cuda_device):
+    """modeling/vgg.py::_Stage hands conv-bias / ReLU / max-pool to the BN kernels; the result must match the plain
+    nn.Sequential evaluation of the same modules (cuDNN BN) within fp32 tolerance, including the state_dict side effects."""
+    import copy
+    import sfod_b200
+    from sfod_b200 import config, modeling
+    torch.manual_seed(5)
+    cfg = config.vgg_source_free_cfg(); cfg.MODEL.DEVICE = "cpu"
+    bb = modeling.vgg_backbone(cfg)
+    with torch.no_grad():
+        for m in bb.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                m.bias.normal_(0, 0.5)
+    ref = copy.deepcopy(bb).to(cuda_device).train()
+    bb = bb.to(cuda_device).train()
+    x = torch.randn(2, 3, 96, 160, device=cuda_device)
+    tf = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            got = bb(x)                                   # native path (train + no_grad)
+            want = {}
+            h = x
+            for name, stage in zip(ref._stage_names, ref.stages):
+                h = torch.nn.Sequential.forward(stage, h)  # plain module-by-module evaluation
+                want[name] = h
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf
+    for k in want:
+        assert got[k].shape == want[k].shape
+        _close(got[k], want[k], rtol=1e-4, atol_scale=1e-4)
+    for (k, a), (_, b) in zip(bb.state_dict().items(), ref.state_dict().items()):
+        if "running" in k:
+            _close(a, b, rtol=1e-4, atol_scale=1e-5)
+        if k.endswith("num_batches_tracked"):
+            assert a.item() == b.item() == 1
