@@ -205,7 +205,8 @@ def run_b200(args):
     teacher.to(dev).train()   # the reference never .eval()s the teacher
     student.to(dev).train()
     if args.channels_last:
-        teacher.backbone.to(memory_format=torch.channels_last)
+        teacher.to(memory_format=torch.channels_last)
+        student.to(memory_format=torch.channels_last)
     ema = engine.TeacherEMA(student, teacher, world_size=1)
     thr = cfg.SEMISUPNET.BBOX_THRESHOLD
     B = args.batch
@@ -291,12 +292,16 @@ def run_b200(args):
     # activation elements entering the 13 BN layers of VGG16 at 600x1200 (per image): SURVEY.md App. C = 194 342 400
     hw = [(600, 1200)] * 2 + [(300, 600)] * 2 + [(150, 300)] * 3 + [(75, 150)] * 3 + [(37, 75)] * 3
     ch = [64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512]
-    bn_elems = sum(c * h * w for c, (h, w) in zip(ch, hw)) * B
+    per_layer = [c * h * w for c, (h, w) in zip(ch, hw)]
+    pooled = {1, 3, 6, 9, 12}                 # the BN layer that closes each VGG stage feeds MaxPool2d(2, 2) (fused)
+    bn_elems = sum(per_layer) * B
+    bn_elems_pool = sum(e for i, e in enumerate(per_layer) if i in pooled) * B
     R = sum(len(p) for p in out[0])          # proposals actually pooled / post-processed in the last step
     Cf, Hf, Wf = 512, IMAGE_HW[0] // 32, IMAGE_HW[1] // 32
     hwa = Hf * Wf * 15
     alg = {
-        "bn_finalize_apply": 8.0 * bn_elems,                                  # read x + write y
+        "bn_finalize_apply": 8.0 * (bn_elems - bn_elems_pool),                # read x + write y (normalise + ReLU, in place)
+        "bn_finalize_apply_pool": 5.0 * bn_elems_pool,                        # read x + write the 2x2-pooled y (1/4 of the elements)
         "bn_partial_stats": 4.0 * bn_elems,                                   # read x
         "ema_multi_tensor": 12.0 * ema.numel,                                 # read student, read teacher, write teacher
         "roi_align_fwd": 4.0 * (B * Cf * Hf * Wf + 5 * R + 49 * R * Cf),      # feature map + rois in, (R, C, 7, 7) out
