@@ -111,9 +111,8 @@ SFOD_API int sfod_nms(const float *boxes, const float *scores, const int64_t *id
                                                                  b.maxkey, b.sboxes, b.scls, b.seg);
   SFOD_LAUNCH_CHECK();
   const int *cls = (idxs && !use_trick) ? b.scls : nullptr;
-  rc = nmsk::launch_mask(b.sboxes, cls, b.seg, 1, (int)n, (int)n, b.wstride, iou_threshold, b.mask, st);
-  if (rc) return rc;
-  rc = nmsk::launch_scan(b.mask, b.seg, 1, (int)n, b.wstride, (int)n, (int)n, b.keep_rank, b.keep_count, st);
+  rc = nmsk::run_segmented(b.sboxes, cls, b.seg, 1, (int)n, (int)n, b.wstride, iou_threshold, (int)n, (int)n, b.mask,
+                           b.keep_rank, b.keep_count, st);
   if (rc) return rc;
   nms_emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.keys, b.keep_rank, b.keep_count, n,
                                                                reinterpret_cast<long long *>(keep_out),
@@ -159,10 +158,8 @@ SFOD_API int sfod_rpn_select(const sfod_rpn_params *p, const float *logits, cons
       p->HWA, p->A, p->Wf, p->stride, p->anchor_offset, p->weights[0], p->weights[1], p->weights[2], p->weights[3],
       p->scale_clamp, pl.topk, p->min_box_size, image_hw_dev, b.sboxes, b.sscores, b.ssrc, b.segs, invalid_count_dev);
   SFOD_LAUNCH_CHECK();
-  rc = nmsk::launch_mask(b.sboxes, nullptr, b.segs, N, pl.topk, pl.topk, pl.wstride, p->nms_thresh, b.mask, st);
-  if (rc) return rc;
-  rc = nmsk::launch_scan(b.mask, b.segs, N, pl.topk, pl.wstride, p->post_nms_topk, p->post_nms_topk, b.keep_rank,
-                             b.keep_count, st);
+  rc = nmsk::run_segmented(b.sboxes, nullptr, b.segs, N, pl.topk, pl.topk, pl.wstride, p->nms_thresh, p->post_nms_topk,
+                           p->post_nms_topk, b.mask, b.keep_rank, b.keep_count, st);
   if (rc) return rc;
   {
     dim3 grid((p->post_nms_topk + 255) / 256, N);
@@ -220,9 +217,8 @@ SFOD_API int sfod_frcnn_postprocess(const sfod_frcnn_params *p, const float *cls
                                                                  p->coord_trick_max_n, b.sboxes);
     SFOD_LAUNCH_CHECK();
   }
-  rc = nmsk::launch_mask(b.sboxes, nullptr, b.segs, N * K, pl.Rmax, pl.Rmax, pl.wstride, p->nms_thresh, b.mask, st);
-  if (rc) return rc;
-  rc = nmsk::launch_scan(b.mask, b.segs, N * K, pl.Rmax, pl.wstride, p->topk, p->topk, b.keep_rank, b.keep_count, st);
+  rc = nmsk::run_segmented(b.sboxes, nullptr, b.segs, N * K, pl.Rmax, pl.Rmax, pl.wstride, p->nms_thresh, p->topk, p->topk,
+                           b.mask, b.keep_rank, b.keep_count, st);
   if (rc) return rc;
   frk::frcnn_merge_keys_kernel<<<N, 256, 0, st>>>(b.keys, pl.P, K, b.segs, b.keep_rank, b.keep_count, p->topk, pl.P2,
                                                          b.keys2, b.total_kept);

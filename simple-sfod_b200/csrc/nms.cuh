@@ -167,7 +167,279 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const unsigned l
   if (tid == 0) keep_count[s] = count_sh < max_keep ? count_sh : max_keep;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Lazy-row cluster NMS (the default path).  Greedy NMS only ever needs the IoU rows of boxes that end up KEPT, and a
+// box stops being tested the moment something suppresses it; the mask kernel above computes all n^2/2 pairs (50 M for
+// the 9 990 RPN candidates of one VGG image) although at most max_keep * n of them matter.  Here one thread-block
+// CLUSTER owns one segment (image, or image x class) and evaluates pairs on the fly from shared memory:
+//   * the sorted boxes are dealt to the CL CTAs of the cluster tile-cyclically (tile t = 64 boxes -> CTA t % CL); each CTA
+//     keeps its own boxes, areas, a `removed` bitmap and the 64x64 intra-tile suppression bits of its tiles (computed
+//     once, up front) in shared memory -- the n x n/64 bitmask never exists;
+//   * tile t is resolved by its owner with a warp-parallel fixed-point iteration (kept_j = alive_j and no kept
+//     suppressor among the lower bits; converges in (suppression-chain depth + 1) ballots instead of a 64-step serial
+//     chain), and the compacted kept boxes of the tile are PUSHED into every CTA's shared memory (DSMEM stores);
+//   * one split cluster barrier per tile: the owner of tile t+1 applies the kept list of tile t to that tile first,
+//     resolves and publishes it, ARRIVES, and only then tests its remaining boxes, so the serial resolve of the next
+//     tile overlaps the parallel apply phase of the current one; kept lists are triple-buffered;
+//   * every CTA tests its own later, still-alive boxes against the kept list (early exit on the first hit; when few
+//     boxes remain several threads share one box and split the list).
+// The scan stops as soon as max_keep boxes are kept.  IoU arithmetic and tie order are those of the mask kernel.
+constexpr int kLazyThreads = 1024;
+
+struct LazyPub {           // kept boxes of one tile, compacted in rank order
+  float4 box[64];
+  float area[64];
+  int cls[64];
+  int count;
+  int pad[3];
+};
+
+// `thr` is the largest float <= the caller's double threshold: for a float q, (double)q > thr_double <=> q > thr, so the
+// comparison stays in fp32 with the result of torchvision's float-vs-double compare.
+__device__ __forceinline__ bool lazy_iou_sup(const float4 a, const float aa, const float4 b, const float ab, const float thr,
+                                             const bool neg_thr) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  if (inter > 0.0f || neg_thr) {  // inter == 0 => iou is 0, -0 or NaN: never > thr for thr >= 0
+    const float uni = __fsub_rn(__fadd_rn(aa, ab), inter);
+    return __fdiv_rn(inter, uni) > thr;
+  }
+  return false;
+}
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// generic address of `p` (a shared-memory address of this CTA) in CTA `rank` of the cluster
+template <typename T> __device__ __forceinline__ T *cluster_map(T *p, unsigned rank) {
+  unsigned long long out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(reinterpret_cast<unsigned long long>(p)), "r"(rank));
+  return reinterpret_cast<T *>(out);
+}
+
+__host__ __device__ inline size_t lazy_smem_bytes(int own_cap_tiles) {
+  // boxes + areas + classes + intra-tile suppressor words, removed words (padded to 16 B), three kept lists
+  return (size_t)own_cap_tiles * 64 * (16 + 4 + 4 + 8) + (((size_t)own_cap_tiles * 8 + 15) & ~(size_t)15) + 3 * sizeof(LazyPub);
+}
+
+template <bool kClassAware>
+__global__ void __launch_bounds__(kLazyThreads) nms_lazy_kernel(const float4 *__restrict__ boxes, const int *__restrict__ cls,
+                                                                const Seg *__restrict__ segs, float thr, int max_keep,
+                                                                int keep_stride, int own_cap, int *__restrict__ keep_rank,
+                                                                int *__restrict__ keep_count) {
+  extern __shared__ __align__(16) unsigned char lazy_raw[];
+  float4 *ob = reinterpret_cast<float4 *>(lazy_raw);
+  unsigned long long *col = reinterpret_cast<unsigned long long *>(ob + (size_t)own_cap * 64);   // suppressors (lower bits) per box
+  float *oa = reinterpret_cast<float *>(col + (size_t)own_cap * 64);
+  int *oc = reinterpret_cast<int *>(oa + (size_t)own_cap * 64);
+  unsigned long long *removed = reinterpret_cast<unsigned long long *>(oc + (size_t)own_cap * 64);
+  LazyPub *loc = reinterpret_cast<LazyPub *>(removed + ((own_cap + 1) & ~1));                    // 16-byte aligned
+
+  const int CL = (int)cluster_nctarank(), c = (int)cluster_ctarank();
+  const int s = blockIdx.y;
+  const Seg seg = segs[s];
+  const int n = seg.len;
+  const int W = (n + 63) >> 6;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool neg_thr = thr < 0.0f;
+  const int own_tiles = W > c ? (W - c + CL - 1) / CL : 0;   // tiles t = q*CL + c, q < own_tiles (<= own_cap by construction)
+  const int own_n = own_tiles * 64;
+  int *out = keep_rank + (size_t)s * keep_stride;
+
+  for (int idx = tid; idx < own_n; idx += kLazyThreads) {
+    const int q = idx >> 6, r = (q * CL + c) * 64 + (idx & 63);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cc = 0;
+    if (r < n) { b = boxes[seg.start + r]; if (kClassAware) cc = cls[seg.start + r]; }
+    ob[idx] = b; oa[idx] = sfod_box_area(b); oc[idx] = cc;
+  }
+  for (int q = tid; q < own_tiles; q += kLazyThreads) {
+    const int nvalid = min(64, n - (q * CL + c) * 64);
+    removed[q] = nvalid >= 64 ? 0ull : ~((1ull << nvalid) - 1ull);   // lanes beyond the segment never participate
+  }
+  __syncthreads();
+  // intra-tile suppressor words of every own tile: byte ic of col[q*64 + j] = { i in [8 ic, 8 ic + 8) : i < j, IoU(i, j) > thr }
+  for (int idx = tid; idx < own_n * 8; idx += kLazyThreads) {
+    const int q = idx >> 9, j = (idx >> 3) & 63, ic = idx & 7;
+    const int nvalid = min(64, n - (q * CL + c) * 64);
+    unsigned bits = 0;
+    if (j < nvalid && ic * 8 < j) {
+      const float4 bj = ob[q * 64 + j]; const float aj = oa[q * 64 + j];
+      const int cj = oc[q * 64 + j];
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const int i = ic * 8 + ii;
+        if (i < j && (!kClassAware || oc[q * 64 + i] == cj) && lazy_iou_sup(ob[q * 64 + i], oa[q * 64 + i], bj, aj, thr, neg_thr))
+          bits |= 1u << ii;
+      }
+    }
+    reinterpret_cast<unsigned char *>(col)[(size_t)(q * 64 + j) * 8 + ic] = (unsigned char)bits;
+  }
+  __syncthreads();
+
+  // Resolve own tile q (global tile t): fixed-point iteration in warp 0, compacted list into loc[slot] of EVERY CTA.
+  auto resolve_publish = [&](int q, int t, int slot, int base) {
+    LazyPub &mine = loc[slot];
+    if (warp == 0) {
+      const unsigned long long alive = ~removed[q];
+      const unsigned long long c0 = col[q * 64 + lane], c1 = col[q * 64 + 32 + lane];
+      const bool a0 = (alive >> lane) & 1ull, a1 = (alive >> (32 + lane)) & 1ull;
+      unsigned long long kept = alive;
+      for (;;) {   // kept_j = alive_j && no kept suppressor below j; bits 0..k-1 are final after k rounds
+        const unsigned lo = __ballot_sync(0xFFFFFFFFu, a0 && !(c0 & kept));
+        const unsigned hi = __ballot_sync(0xFFFFFFFFu, a1 && !(c1 & kept));
+        const unsigned long long nk = ((unsigned long long)hi << 32) | lo;
+        if (nk == kept) break;
+        kept = nk;
+      }
+      int nk = __popcll(kept);
+      if (base + nk > max_keep) {   // keep only the first (max_keep - base) survivors
+        const int allow = max_keep - base;
+        unsigned long long kk = kept, keep2 = 0;
+        for (int z = 0; z < allow; ++z) { const unsigned long long low = kk & (0ull - kk); keep2 |= low; kk ^= low; }
+        kept = keep2; nk = allow;
+      }
+      const unsigned klo = (unsigned)kept, khi = (unsigned)(kept >> 32);
+      if ((klo >> lane) & 1u) {
+        const int pos = __popc(klo & ((1u << lane) - 1u));
+        out[base + pos] = t * 64 + lane;
+        mine.box[pos] = ob[q * 64 + lane]; mine.area[pos] = oa[q * 64 + lane]; mine.cls[pos] = oc[q * 64 + lane];
+      }
+      if ((khi >> lane) & 1u) {
+        const int pos = __popc(klo) + __popc(khi & ((1u << lane) - 1u));
+        out[base + pos] = t * 64 + 32 + lane;
+        mine.box[pos] = ob[q * 64 + 32 + lane]; mine.area[pos] = oa[q * 64 + 32 + lane]; mine.cls[pos] = oc[q * 64 + 32 + lane];
+      }
+      if (lane == 0) mine.count = nk;
+    }
+    __syncthreads();
+    const int kc = mine.count;
+    for (int p = warp; p < CL; p += kLazyThreads / 32) {   // one warp per peer: push the list through DSMEM
+      if (p == c) continue;
+      LazyPub *remote = cluster_map(&mine, (unsigned)p);
+      for (int k = lane; k < kc; k += 32) {
+        remote->box[k] = mine.box[k]; remote->area[k] = mine.area[k];
+        if (kClassAware) remote->cls[k] = mine.cls[k];
+      }
+      if (lane == 0) remote->count = kc;
+    }
+  };
+
+  // test own boxes [b_lo, b_hi) that are still alive against the kc kept boxes of `L`: 8 lanes share one box and split
+  // the list (short dependent chains, balanced work); a lane stops at its own first hit
+  auto apply_range = [&](const LazyPub &L, int b_lo, int b_hi, int kc) {
+    if (kc <= 0) return;
+    const int sub = tid & 7;
+    for (int b = b_lo + (tid >> 3); b < b_hi; b += kLazyThreads / 8) {
+      const int q = b >> 6, bit = b & 63;
+      if ((removed[q] >> bit) & 1ull) continue;
+      const float4 bx = ob[b]; const float ab = oa[b];
+      const int cb = oc[b];
+      for (int k = sub; k < kc; k += 8) {
+        if (kClassAware && L.cls[k] != cb) continue;
+        if (lazy_iou_sup(L.box[k], L.area[k], bx, ab, thr, neg_thr)) { atomicOr(&removed[q], 1ull << bit); break; }
+      }
+    }
+  };
+
+  int total = 0;
+  if (c == 0 && W > 0) resolve_publish(0, 0, 0, 0);
+  cluster_arrive(); cluster_wait();
+  for (int t = 0; t < W; ++t) {
+    const int slot = t % 3;
+    const LazyPub &L = loc[slot];
+    const int kc = L.count;
+    total += kc;
+    const bool done = (total >= max_keep) || (t + 1 >= W);
+    int q_first = t < c ? 0 : (t - c) / CL + 1;       // first own tile with global index > t
+    if (!done && c == (t + 1) % CL) {                 // owner of the next tile: finish that tile first and publish it
+      const int qn = (t + 1) / CL;                    // == q_first
+      apply_range(L, qn * 64, qn * 64 + 64, kc);
+      __syncthreads();
+      resolve_publish(qn, t + 1, (t + 1) % 3, total);
+      q_first = qn + 1;
+    }
+    cluster_arrive();
+    if (!done) apply_range(L, q_first * 64, own_n, kc);
+    cluster_wait();
+    if (done) break;
+  }
+  if (c == 0 && tid == 0) keep_count[s] = total < max_keep ? total : max_keep;
+  cluster_arrive(); cluster_wait();   // no CTA may exit while a peer can still push into its shared memory
+}
+
 // host helpers
+static inline int lazy_cluster_size(int S, int max_len, size_t *smem_out, int *own_cap_out) {
+  int CL = 16;
+  while (CL > 1 && (long long)S * CL > 144) CL >>= 1;          // keep every cluster resident at once when possible
+  const int W = (max_len + 63) / 64;
+  while (CL > 1 && CL > W) CL >>= 1;
+  int own_cap = (W + CL - 1) / CL; if (own_cap < 1) own_cap = 1;
+  *smem_out = lazy_smem_bytes(own_cap); *own_cap_out = own_cap;
+  return CL;
+}
+
+// Largest cluster size the device will actually schedule for this kernel (probed once per process and kernel variant; an
+// idempotent capability cache, not state that any result depends on).  0 = the kernel cannot be launched as a cluster.
+template <bool kCls>
+static inline int lazy_max_cluster() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  auto kern = nms_lazy_kernel<kCls>;
+  (void)cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  int best = 0;
+  for (int CL = 16; CL >= 1; CL >>= 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL, 1, 1); cfg.blockDim = dim3(kLazyThreads, 1, 1); cfg.dynamicSmemBytes = lazy_smem_bytes(16);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0) { best = CL; break; }
+    (void)cudaGetLastError();
+  }
+  cached = best;
+  return best;
+}
+
+template <bool kCls>
+static inline int launch_lazy_t(const float4 *boxes, const int *cls, const Seg *segs, int S, int max_len, double thr, int max_keep,
+                                int keep_stride, int *keep_rank, int *keep_count, cudaStream_t stream, bool *launched) {
+  *launched = false;
+  const int max_cl = lazy_max_cluster<kCls>();
+  if (max_cl <= 0) return SFOD_OK;         // caller falls back to mask + scan
+  size_t smem; int own_cap;
+  int CL = lazy_cluster_size(S, max_len, &smem, &own_cap);
+  if (CL > max_cl) {
+    CL = max_cl;
+    const int W = (max_len + 63) / 64;
+    own_cap = (W + CL - 1) / CL; if (own_cap < 1) own_cap = 1;
+    smem = lazy_smem_bytes(own_cap);
+  }
+  if (smem > 200 * 1024) return SFOD_OK;   // segment too long for the shared-memory resident form: caller falls back
+  auto kern = nms_lazy_kernel<kCls>;
+  if (smem > 48 * 1024) SFOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL, S, 1); cfg.blockDim = dim3(kLazyThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  float thr_f = (float)thr;                                  // largest float <= thr (see lazy_iou_sup)
+  if ((double)thr_f > thr) thr_f = nextafterf(thr_f, -INFINITY);
+  if (cudaLaunchKernelEx(&cfg, kern, boxes, cls, segs, thr_f, max_keep, keep_stride, own_cap, keep_rank, keep_count) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return SFOD_OK;                        // not launchable in this configuration: caller falls back
+  }
+  sfod_count_launch();
+  *launched = true;
+  return SFOD_OK;
+}
+
 static inline int launch_mask(const float4 *boxes, const int *cls, const Seg *segs, int S, int max_len, int rows_per_slab,
                               int wstride, double thr, unsigned long long *mask, cudaStream_t stream) {
   if (S <= 0 || max_len <= 0) return SFOD_OK;
@@ -187,6 +459,23 @@ static inline int launch_scan(const unsigned long long *mask, const Seg *segs, i
                                                      keep_count);
   SFOD_LAUNCH_CHECK();
   return SFOD_OK;
+}
+
+// Segmented NMS entry used by every caller: lazy cluster kernel, or mask + scan when that cannot run.
+static inline int run_segmented(const float4 *boxes, const int *cls, const Seg *segs, int S, int max_len, int rows_per_slab,
+                                int wstride, double thr, int max_keep, int keep_stride, unsigned long long *mask,
+                                int *keep_rank, int *keep_count, cudaStream_t stream) {
+  if (S <= 0) return SFOD_OK;
+  if (max_len > 0) {
+    bool launched = false;
+    int rc = cls ? launch_lazy_t<true>(boxes, cls, segs, S, max_len, thr, max_keep, keep_stride, keep_rank, keep_count, stream, &launched)
+                 : launch_lazy_t<false>(boxes, cls, segs, S, max_len, thr, max_keep, keep_stride, keep_rank, keep_count, stream, &launched);
+    if (rc) return rc;
+    if (launched) return SFOD_OK;
+  }
+  int rc = launch_mask(boxes, cls, segs, S, max_len, rows_per_slab, wstride, thr, mask, stream);
+  if (rc) return rc;
+  return launch_scan(mask, segs, S, rows_per_slab, wstride, max_keep, keep_stride, keep_rank, keep_count, stream);
 }
 
 }  // namespace nmsk
