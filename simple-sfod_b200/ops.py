@@ -471,8 +471,8 @@ class EmaPlan:
                 raise TypeError(f"EMA supports float32 and int64 state tensors, got {s.dtype}")
             # elementwise over the storage: any dense layout works as long as both tensors share it (e.g. channels_last weights)
             if not (s.is_contiguous() and t.is_contiguous()):
-                dense = getattr(t, "is_non_overlapping_and_dense", lambda: False)() and getattr(s, "is_non_overlapping_and_dense", lambda: False)()
-                if not dense or s.stride() != t.stride():
+                cl = s.dim() == 4 and s.is_contiguous(memory_format=torch.channels_last) and t.is_contiguous(memory_format=torch.channels_last)
+                if not cl or s.stride() != t.stride():
                     raise ValueError(f"EMA pair {i}: tensors must be dense and share one memory layout")
             arr[i].student, arr[i].teacher = s.data_ptr(), t.data_ptr()
             arr[i].numel, arr[i].dtype = s.numel(), code
