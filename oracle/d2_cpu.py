@@ -445,3 +445,100 @@ def adabn_recompute(model: torch.nn.Module, batches, max_iters: int = 1400) -> i
         if i > max_iters:
             break
     return i
+
+
+# --------------------------------------------------------------------------- student-side labelling / losses
+def pairwise_iou(boxes1: torch.Tensor, boxes2: torch.Tensor) -> torch.Tensor:
+    """d2 structures.pairwise_iou on raw (M,4)/(N,4) tensors."""
+    a1 = (boxes1[:, 2] - boxes1[:, 0]) * (boxes1[:, 3] - boxes1[:, 1])
+    a2 = (boxes2[:, 2] - boxes2[:, 0]) * (boxes2[:, 3] - boxes2[:, 1])
+    wh = (torch.min(boxes1[:, None, 2:], boxes2[:, 2:]) - torch.max(boxes1[:, None, :2], boxes2[:, :2])).clamp(min=0)
+    inter = wh[..., 0] * wh[..., 1]
+    return torch.where(inter > 0, inter / (a1[:, None] + a2 - inter), torch.zeros(1))
+
+
+def matcher(mqm: torch.Tensor, thresholds: Sequence[float], labels: Sequence[int], allow_low_quality: bool):
+    """d2 Matcher.__call__ (A-9): RPN uses ([0.3, 0.7], [0, -1, 1], True), ROI heads ([0.5], [0, 1], False)."""
+    n = mqm.shape[1]
+    if mqm.numel() == 0:
+        return torch.zeros(n, dtype=torch.int64), torch.full((n,), labels[0], dtype=torch.int8)
+    vals, matches = mqm.max(dim=0)
+    out = torch.ones(n, dtype=torch.int8)
+    th = [-float("inf")] + list(thresholds) + [float("inf")]
+    for l, lo, hi in zip(labels, th[:-1], th[1:]):
+        out[(vals >= lo) & (vals < hi)] = l
+    if allow_low_quality:
+        best, _ = mqm.max(dim=1)
+        out[(mqm == best[:, None]).nonzero()[:, 1]] = 1
+    return matches, out
+
+
+def subsample_labels(labels, num_samples, positive_fraction, bg_label, randperm=torch.randperm):
+    positive = ((labels != -1) & (labels != bg_label)).nonzero().flatten()
+    negative = (labels == bg_label).nonzero().flatten()
+    num_pos = min(positive.numel(), int(num_samples * positive_fraction))
+    num_neg = min(negative.numel(), num_samples - num_pos)
+    return positive[randperm(positive.numel())[:num_pos]], negative[randperm(negative.numel())[:num_neg]]
+
+
+def rpn_label_and_sample_anchors(anchors: torch.Tensor, gt_boxes: List[torch.Tensor], batch_size_per_image=256,
+                                 positive_fraction=0.5, randperm=torch.randperm):
+    """d2 RPN.label_and_sample_anchors (called at reference rpn.py:45)."""
+    labels_out, boxes_out = [], []
+    for gt in gt_boxes:
+        idx, lab = matcher(pairwise_iou(gt, anchors), [0.3, 0.7], [0, -1, 1], True)
+        pos, neg = subsample_labels(lab, batch_size_per_image, positive_fraction, 0, randperm)
+        lab = torch.full_like(lab, -1)
+        lab[pos] = 1
+        lab[neg] = 0
+        labels_out.append(lab)
+        boxes_out.append(gt[idx] if len(gt) else torch.zeros_like(anchors))
+    return labels_out, boxes_out
+
+
+def rpn_losses(anchors, logits, gt_labels, deltas, gt_boxes, batch_size_per_image=256, weights=(1.0, 1.0, 1.0, 1.0)):
+    """d2 RPN.losses (smooth_l1 with beta 0 == L1), logits (N, R), deltas (N, R, 4)."""
+    lab = torch.stack(gt_labels)
+    pos = lab == 1
+    tgt = torch.stack([get_deltas(anchors, g, weights) for g in gt_boxes])
+    loc = F.l1_loss(deltas[pos], tgt[pos], reduction="sum")
+    valid = lab >= 0
+    cls = F.binary_cross_entropy_with_logits(logits[valid], lab[valid].float(), reduction="sum")
+    norm = batch_size_per_image * len(gt_labels)
+    return {"loss_rpn_cls": cls / norm, "loss_rpn_loc": loc / norm}
+
+
+def label_and_sample_proposals(proposals: List[dict], targets: List[dict], num_classes=8, batch_size_per_image=512,
+                               positive_fraction=0.25, append_gt=True, randperm=torch.randperm):
+    """reference source_free_adaptive_teacher_roi_heads.py:165-215 on dicts(proposal_boxes, objectness_logits) / dicts(gt_boxes, gt_classes)."""
+    out = []
+    gt_logit = math.log((1.0 - 1e-10) / (1 - (1.0 - 1e-10)))
+    for p, t in zip(proposals, targets):
+        boxes, logits = p["proposal_boxes"], p["objectness_logits"]
+        if append_gt:
+            boxes = torch.cat([boxes, t["gt_boxes"]])
+            logits = torch.cat([logits, gt_logit * torch.ones(len(t["gt_boxes"]))])
+        idx, lab = matcher(pairwise_iou(t["gt_boxes"], boxes), [0.5], [0, 1], False)
+        if t["gt_classes"].numel() > 0:
+            cls = t["gt_classes"][idx].clone()
+            cls[lab == 0] = num_classes
+            cls[lab == -1] = -1
+        else:
+            cls = torch.zeros_like(idx) + num_classes
+        fg, bg = subsample_labels(cls, batch_size_per_image, positive_fraction, num_classes, randperm)
+        sel = torch.cat([fg, bg])
+        gtb = t["gt_boxes"][idx[sel]] if len(t["gt_boxes"]) else torch.zeros((len(sel), 4))
+        out.append(dict(image_size=p.get("image_size"), proposal_boxes=boxes[sel], objectness_logits=logits[sel], gt_classes=cls[sel], gt_boxes=gtb))
+    return out
+
+
+def fast_rcnn_losses(scores, proposal_deltas, proposals: List[dict], num_classes=8, weights=(10.0, 10.0, 5.0, 5.0)):
+    """d2 FastRCNNOutputLayers.losses: mean CE + class-specific L1 (smooth_l1 beta 0) over the foreground / #proposals."""
+    gt_classes = torch.cat([p["gt_classes"] for p in proposals])
+    pb = torch.cat([p["proposal_boxes"] for p in proposals])
+    gb = torch.cat([p["gt_boxes"] for p in proposals])
+    loss_cls = F.cross_entropy(scores, gt_classes, reduction="mean")
+    fg = ((gt_classes >= 0) & (gt_classes < num_classes)).nonzero().flatten()
+    pred = proposal_deltas.view(-1, num_classes, 4)[fg, gt_classes[fg]]
+    loss_box = F.l1_loss(pred, get_deltas(pb[fg], gb[fg], weights), reduction="sum") / max(gt_classes.numel(), 1.0)
+    return {"loss_cls": loss_cls, "loss_box_reg": loss_box}

@@ -17,7 +17,9 @@ from torch import Tensor, nn
 
 from .. import ops
 from ..structures import Boxes, Instances, ShapeSpec
+from ..utils.events import get_event_storage
 from .box_regression import Box2BoxTransform
+from .matcher import cross_entropy, dense_box_regression_loss, nonzero_tuple
 
 
 class DetectionBatch:
@@ -64,12 +66,34 @@ class DetectionBatch:
         return res
 
 
+def _log_classification_stats(pred_logits: Tensor, gt_classes: Tensor, prefix: str = "fast_rcnn") -> None:
+    """d2 fast_rcnn._log_classification_stats."""
+    num_instances = gt_classes.numel()
+    if num_instances == 0:
+        return
+    pred_classes = pred_logits.argmax(dim=1)
+    bg_class_ind = pred_logits.shape[1] - 1
+    fg_inds = (gt_classes >= 0) & (gt_classes < bg_class_ind)
+    num_fg = fg_inds.nonzero().numel()
+    fg_gt_classes = gt_classes[fg_inds]
+    fg_pred_classes = pred_classes[fg_inds]
+    num_false_negative = (fg_pred_classes == bg_class_ind).nonzero().numel()
+    num_accurate = (pred_classes == gt_classes).nonzero().numel()
+    fg_num_accurate = (fg_pred_classes == fg_gt_classes).nonzero().numel()
+    storage = get_event_storage()
+    storage.put_scalar(f"{prefix}/cls_accuracy", num_accurate / num_instances)
+    if num_fg > 0:
+        storage.put_scalar(f"{prefix}/fg_cls_accuracy", fg_num_accurate / num_fg)
+        storage.put_scalar(f"{prefix}/false_negative", num_false_negative / num_fg)
+
+
 class FastRCNNOutputLayers(nn.Module):
     """detectron2.modeling.roi_heads.fast_rcnn.FastRCNNOutputLayers: two linear layers (K+1 scores, 4K deltas)."""
 
     def __init__(self, cfg_or_shape, input_shape: Optional[ShapeSpec] = None, *, box2box_transform: Box2BoxTransform = None,
                  num_classes: int = None, test_score_thresh: float = 0.0, test_nms_thresh: float = 0.5,
-                 test_topk_per_image: int = 100, cls_agnostic_bbox_reg: bool = False, pseudo_label_thresh: float = 0.8):
+                 test_topk_per_image: int = 100, cls_agnostic_bbox_reg: bool = False, pseudo_label_thresh: float = 0.8,
+                 smooth_l1_beta: float = 0.0, box_reg_loss_type: str = "smooth_l1", loss_weight=1.0):
         super().__init__()
         if hasattr(cfg_or_shape, "MODEL"):
             cfg = cfg_or_shape
@@ -80,6 +104,9 @@ class FastRCNNOutputLayers(nn.Module):
             test_nms_thresh = cfg.MODEL.ROI_HEADS.NMS_THRESH_TEST
             test_topk_per_image = cfg.TEST.DETECTIONS_PER_IMAGE
             pseudo_label_thresh = cfg.SEMISUPNET.BBOX_THRESHOLD
+            smooth_l1_beta = cfg.MODEL.ROI_BOX_HEAD.SMOOTH_L1_BETA
+            box_reg_loss_type = cfg.MODEL.ROI_BOX_HEAD.BBOX_REG_LOSS_TYPE
+            loss_weight = {"loss_box_reg": cfg.MODEL.ROI_BOX_HEAD.BBOX_REG_LOSS_WEIGHT}
         else:
             input_shape = cfg_or_shape
         if isinstance(input_shape, int):
@@ -99,14 +126,58 @@ class FastRCNNOutputLayers(nn.Module):
         self.test_nms_thresh = test_nms_thresh
         self.test_topk_per_image = test_topk_per_image
         self.pseudo_label_thresh = pseudo_label_thresh
+        self.smooth_l1_beta, self.box_reg_loss_type = smooth_l1_beta, box_reg_loss_type
+        if isinstance(loss_weight, float):
+            loss_weight = {"loss_cls": loss_weight, "loss_box_reg": loss_weight}
+        self.loss_weight = loss_weight
 
     def forward(self, x: Tensor) -> Tuple[Tensor, Tensor]:
         if x.dim() > 2:
             x = torch.flatten(x, start_dim=1)
         return self.cls_score(x), self.bbox_pred(x)
 
-    def losses(self, predictions, proposals):
-        raise NotImplementedError("Fast R-CNN losses belong to the student's training step (SURVEY.md 8f rank 1)")
+    # ------------------------------------------------------------------ training half (student): detectron2 0.6 in plain torch
+    def losses(self, predictions: Tuple[Tensor, Tensor], proposals: List[Instances]) -> Dict[str, Tensor]:
+        """d2 FastRCNNOutputLayers.losses: mean cross-entropy + class-specific smooth-L1 box regression on the foreground."""
+        scores, proposal_deltas = predictions
+        gt_classes = (torch.cat([p.gt_classes for p in proposals], dim=0) if len(proposals)
+                      else torch.empty(0, dtype=torch.int64, device=scores.device))
+        _log_classification_stats(scores, gt_classes)
+        if len(proposals):
+            proposal_boxes = torch.cat([p.proposal_boxes.tensor for p in proposals], dim=0)
+            assert not proposal_boxes.requires_grad, "Proposals should not require gradients!"
+            gt_boxes = torch.cat([(p.gt_boxes if p.has("gt_boxes") else p.proposal_boxes).tensor for p in proposals], dim=0)
+        else:
+            proposal_boxes = gt_boxes = torch.empty((0, 4), device=proposal_deltas.device)
+        losses = {"loss_cls": cross_entropy(scores, gt_classes, reduction="mean"),
+                  "loss_box_reg": self.box_reg_loss(proposal_boxes, gt_boxes, proposal_deltas, gt_classes)}
+        return {k: v * self.loss_weight.get(k, 1.0) for k, v in losses.items()}
+
+    def box_reg_loss(self, proposal_boxes: Tensor, gt_boxes: Tensor, pred_deltas: Tensor, gt_classes: Tensor) -> Tensor:
+        box_dim = proposal_boxes.shape[1]
+        fg_inds = nonzero_tuple((gt_classes >= 0) & (gt_classes < self.num_classes))[0]
+        if pred_deltas.shape[1] == box_dim:
+            fg_pred_deltas = pred_deltas[fg_inds]
+        else:
+            fg_pred_deltas = pred_deltas.view(-1, self.num_classes, box_dim)[fg_inds, gt_classes[fg_inds]]
+        loss_box_reg = dense_box_regression_loss([proposal_boxes[fg_inds]], self.box2box_transform, [fg_pred_deltas.unsqueeze(0)],
+                                                 [gt_boxes[fg_inds]], ..., self.box_reg_loss_type, self.smooth_l1_beta)
+        return loss_box_reg / max(gt_classes.numel(), 1.0)
+
+    @torch.no_grad()
+    def predict_boxes_for_gt_classes(self, predictions: Tuple[Tensor, Tensor], proposals: List[Instances]):
+        if not len(proposals):
+            return []
+        scores, proposal_deltas = predictions
+        proposal_boxes = torch.cat([p.proposal_boxes.tensor for p in proposals], dim=0)
+        N, B = proposal_boxes.shape
+        predict_boxes = self.box2box_transform.apply_deltas(proposal_deltas.detach(), proposal_boxes)
+        K = predict_boxes.shape[1] // B
+        if K > 1:
+            gt_classes = torch.cat([p.gt_classes for p in proposals], dim=0)
+            gt_classes = gt_classes.clamp_(0, K - 1)
+            predict_boxes = predict_boxes.view(N, K, B)[torch.arange(N, dtype=torch.long, device=predict_boxes.device), gt_classes]
+        return predict_boxes.split([len(p) for p in proposals])
 
     def predict_boxes(self, predictions: Tuple[Tensor, Tensor], proposals: List[Instances]) -> Tuple[Tensor, ...]:
         if not len(proposals):

@@ -2,8 +2,11 @@
 ``SourceFreeAdaptiveTeacherGeneralizedRCNN`` (reference daod/modeling/meta_arch/source_free_adaptive_teacher_rcnn.py:310-339)
 plus detectron2's ``GeneralizedRCNN.inference``.  This is the caller of the hot path: preprocess ->
 backbone (cuDNN convs + native BN) -> PseudoLabRPN -> ROI heads -> detections; the pseudo-label filter is fused in.
-The student-side branches (``supervised``, ``supervised_target``, ``domain_classifier``) are training-step
-orchestration (out of scope) and raise NotImplementedError.
+The student-side branches ``supervised`` / ``supervised_target`` (reference ...rcnn.py:233-300) are provided in their
+detector-loss form so that a student can train through the same plugins (RPN + ROI-head losses; ROIAlign forward and
+backward on the sm_100a kernels).  ``bpc_loss`` enters the reference's total with weight 0 (reference
+daod/engine/trainers/source_free_adaptive_teacher.py:549-550) and is returned as an exact zero; the ``domain_classifier``
+branch (DA baselines) is out of scope and raises NotImplementedError.
 """
 from __future__ import annotations
 
@@ -14,6 +17,19 @@ from torch import Tensor, nn
 
 from ..registry import META_ARCH_REGISTRY, build_backbone, build_proposal_generator, build_roi_heads
 from ..structures import ImageList, Instances
+
+
+class _GradientScalar(torch.autograd.Function):
+    """Gradient-reversal layer (reference daod/modeling/dann/dann.py:33-51): identity forward, grad * alpha backward."""
+
+    @staticmethod
+    def forward(ctx, x, alpha):
+        ctx.alpha = alpha
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output.clone() * ctx.alpha, None
 
 
 class _ImageDomainClassifier(nn.Module):
@@ -86,11 +102,26 @@ class SourceFreeAdaptiveTeacherGeneralizedRCNN(nn.Module):
     def forward(self, batched_inputs, branch: str = "supervised", given_proposals=None, val_mode: bool = False):
         if not self.training and not val_mode:
             return self.inference(batched_inputs)
-        if branch != "unsup_data_weak":
-            raise NotImplementedError(f"branch {branch!r} is the student's training step (out of scope, SURVEY.md section 2 row 6); "
-                                      "the B200 path implements the teacher's 'unsup_data_weak' branch")
+        if branch not in ("unsup_data_weak", "supervised", "supervised_target"):
+            raise NotImplementedError(f"branch {branch!r} (domain-adversarial baselines, SURVEY.md section 2 rows 8-9) is out of scope")
         images = self.preprocess_batch(batched_inputs) if isinstance(batched_inputs, Tensor) else self.preprocess_image(batched_inputs)
         features = self.backbone(images.tensor)
+        if branch in ("supervised", "supervised_target"):
+            gt_instances = [x["instances"].to(self.device) for x in batched_inputs] if "instances" in batched_inputs[0] else None
+            proposals_rpn, proposal_losses = self.proposal_generator(images, features, gt_instances)
+            out = self.roi_heads(images, features, proposals_rpn, compute_loss=True, targets=gt_instances, branch=branch)
+            detector_losses = out[1]
+            losses = {}
+            losses.update(detector_losses)
+            losses.update(proposal_losses)
+            if branch == "supervised":
+                if hasattr(self, "DC_img"):      # reference ...rcnn.py:234-236, :259
+                    d_out = self.DC_img(_GradientScalar.apply(features[self.dis_type], -1.0))
+                    losses["loss_DC_img_s"] = nn.functional.binary_cross_entropy_with_logits(d_out, torch.zeros_like(d_out)) * 0.001
+                return losses, [], []
+            proposals_roih, _ = self.roi_heads(images, features, proposals_rpn, targets=None, compute_loss=False, branch=branch)
+            losses["loss_bpc"] = next(iter(detector_losses.values())).new_zeros(())   # weight 0 in the reference's total
+            return losses, proposals_roih, [], []
         proposals_rpn, _ = self.proposal_generator(images, features, None, compute_loss=False)
         proposals_roih, _ = self.roi_heads(images, features, proposals_rpn, targets=None, compute_loss=False, branch=branch)
         return {}, proposals_rpn, proposals_roih

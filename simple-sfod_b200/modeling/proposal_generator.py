@@ -2,9 +2,9 @@
 on top of a detectron2-shaped ``RPN`` base whose ``predict_proposals`` is ONE fused call into libsfod_b200
 (decode + per-image top-k + clip + non-empty filter + NMS + post top-k for all images).
 
-The loss half of the reference's forward (``label_and_sample_anchors`` + ``losses``, rpn.py:43-50) belongs to the
-student's training step, which SURVEY.md 8(f) ranks as the first "next" row; it is not part of the pseudo-labelling
-path and raises ``NotImplementedError`` here.
+The loss half of the reference's forward (``label_and_sample_anchors`` + ``losses``, rpn.py:43-50) is the student's
+training step: it is restated from detectron2 0.6 in plain torch (``modeling/matcher.py``) so that
+a student can train through the same plugin; it launches no kernel of this library.
 """
 from __future__ import annotations
 
@@ -15,9 +15,11 @@ from torch import Tensor, nn
 
 from .. import ops
 from ..registry import PROPOSAL_GENERATOR_REGISTRY, RPN_HEAD_REGISTRY
-from ..structures import Boxes, ImageList, Instances, ShapeSpec
+from ..structures import Boxes, ImageList, Instances, ShapeSpec, pairwise_iou
+from ..utils.events import get_event_storage
 from .anchor_generator import DefaultAnchorGenerator
 from .box_regression import Box2BoxTransform
+from .matcher import Matcher, dense_box_regression_loss, subsample_labels
 
 
 @RPN_HEAD_REGISTRY.register()
@@ -60,9 +62,17 @@ class RPN(nn.Module):
     def __init__(self, cfg=None, input_shape: Dict[str, ShapeSpec] = None, *, in_features: List[str] = None, head: nn.Module = None,
                  anchor_generator: nn.Module = None, box2box_transform: Box2BoxTransform = None,
                  pre_nms_topk: Tuple[int, int] = (12000, 6000), post_nms_topk: Tuple[int, int] = (2000, 1000),
-                 nms_thresh: float = 0.7, min_box_size: float = 0.0, loss_weight=1.0):
+                 nms_thresh: float = 0.7, min_box_size: float = 0.0, loss_weight=1.0, anchor_matcher: Matcher = None,
+                 batch_size_per_image: int = 256, positive_fraction: float = 0.5, anchor_boundary_thresh: float = -1.0,
+                 box_reg_loss_type: str = "smooth_l1", smooth_l1_beta: float = 0.0):
         super().__init__()
         if cfg is not None:
+            anchor_matcher = Matcher(cfg.MODEL.RPN.IOU_THRESHOLDS, cfg.MODEL.RPN.IOU_LABELS, allow_low_quality_matches=True)
+            batch_size_per_image = cfg.MODEL.RPN.BATCH_SIZE_PER_IMAGE
+            positive_fraction = cfg.MODEL.RPN.POSITIVE_FRACTION
+            anchor_boundary_thresh = cfg.MODEL.RPN.BOUNDARY_THRESH
+            box_reg_loss_type = cfg.MODEL.RPN.BBOX_REG_LOSS_TYPE
+            smooth_l1_beta = cfg.MODEL.RPN.SMOOTH_L1_BETA
             in_features = cfg.MODEL.RPN.IN_FEATURES
             shapes = [input_shape[f] for f in in_features]
             anchor_generator = DefaultAnchorGenerator(cfg, shapes)
@@ -85,14 +95,58 @@ class RPN(nn.Module):
         if isinstance(loss_weight, float):
             loss_weight = {"loss_rpn_cls": loss_weight, "loss_rpn_loc": loss_weight}
         self.loss_weight = loss_weight
+        self.anchor_matcher = anchor_matcher or Matcher([0.3, 0.7], [0, -1, 1], allow_low_quality_matches=True)
+        self.batch_size_per_image, self.positive_fraction = batch_size_per_image, positive_fraction
+        self.anchor_boundary_thresh = anchor_boundary_thresh
+        self.box_reg_loss_type, self.smooth_l1_beta = box_reg_loss_type, smooth_l1_beta
 
-    # ------------------------------------------------------------------ training half: SURVEY.md 8(f) rank 1
-    def label_and_sample_anchors(self, anchors, gt_instances):
-        raise NotImplementedError("RPN anchor labelling/sampling belongs to the student's training step "
-                                  "(SURVEY.md 8f rank 1); the B200 path implements proposal prediction")
+    # ------------------------------------------------------------------ training half (student): detectron2 0.6 in plain torch
+    def _subsample_labels(self, label: Tensor) -> Tensor:
+        pos_idx, neg_idx = subsample_labels(label, self.batch_size_per_image, self.positive_fraction, 0)
+        label.fill_(-1)
+        label.scatter_(0, pos_idx, 1)
+        label.scatter_(0, neg_idx, 0)
+        return label
 
-    def losses(self, *args, **kwargs):
-        raise NotImplementedError("RPN losses belong to the student's training step (SURVEY.md 8f rank 1)")
+    @torch.no_grad()
+    def label_and_sample_anchors(self, anchors: List[Boxes], gt_instances: List[Instances]):
+        """d2 RPN.label_and_sample_anchors -> (gt_labels: List[(R,) in {-1, 0, 1}], matched_gt_boxes: List[(R, 4)])."""
+        anchors = Boxes.cat(anchors)
+        gt_boxes = [x.gt_boxes for x in gt_instances]
+        gt_labels, matched_gt_boxes = [], []
+        for gt_boxes_i in gt_boxes:
+            match_quality_matrix = pairwise_iou(gt_boxes_i, anchors)
+            matched_idxs, gt_labels_i = self.anchor_matcher(match_quality_matrix)
+            gt_labels_i = gt_labels_i.to(device=gt_boxes_i.device)
+            if self.anchor_boundary_thresh >= 0:
+                raise NotImplementedError("RPN.BOUNDARY_THRESH >= 0 is not used by any shipped config")
+            gt_labels_i = self._subsample_labels(gt_labels_i)
+            if len(gt_boxes_i) == 0:
+                matched_gt_boxes_i = torch.zeros_like(anchors.tensor)
+            else:
+                matched_gt_boxes_i = gt_boxes_i[matched_idxs].tensor
+            gt_labels.append(gt_labels_i)
+            matched_gt_boxes.append(matched_gt_boxes_i)
+        return gt_labels, matched_gt_boxes
+
+    def losses(self, anchors: List[Boxes], pred_objectness_logits: List[Tensor], gt_labels: List[Tensor],
+               pred_anchor_deltas: List[Tensor], gt_boxes: List[Tensor]) -> Dict[str, Tensor]:
+        """d2 RPN.losses: BCE-with-logits on the sampled anchors + box regression on the positives, both divided by
+        batch_size_per_image * num_images."""
+        num_images = len(gt_labels)
+        gt_labels = torch.stack(gt_labels)
+        pos_mask = gt_labels == 1
+        storage = get_event_storage()
+        storage.put_scalar("rpn/num_pos_anchors", pos_mask.sum().item() / num_images)
+        storage.put_scalar("rpn/num_neg_anchors", (gt_labels == 0).sum().item() / num_images)
+        localization_loss = dense_box_regression_loss(anchors, self.box2box_transform, pred_anchor_deltas, gt_boxes, pos_mask,
+                                                      box_reg_loss_type=self.box_reg_loss_type, smooth_l1_beta=self.smooth_l1_beta)
+        valid_mask = gt_labels >= 0
+        objectness_loss = torch.nn.functional.binary_cross_entropy_with_logits(
+            torch.cat(pred_objectness_logits, dim=1)[valid_mask], gt_labels[valid_mask].to(torch.float32), reduction="sum")
+        normalizer = self.batch_size_per_image * num_images
+        losses = {"loss_rpn_cls": objectness_loss / normalizer, "loss_rpn_loc": localization_loss / normalizer}
+        return {k: v * self.loss_weight.get(k, 1.0) for k, v in losses.items()}
 
     # ------------------------------------------------------------------ inference half: the hot path
     def _flatten_head_outputs(self, pred_objectness_logits: List[Tensor], pred_anchor_deltas: List[Tensor]):

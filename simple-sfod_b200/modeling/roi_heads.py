@@ -3,9 +3,10 @@
 ``SourceFreeAdaptiveTeacherStandardROIHeads`` (reference daod/modeling/roi_heads/source_free_adaptive_teacher_roi_heads.py:25-215),
 its eval sibling (``..._eval.py:25-128``) and ``AdaptiveTeacherStandardROIHeads`` (reference adaptive_teacher_roi_heads.py:22-187)
 share one body: ROIPooler -> box head -> predictor, then either ``box_predictor.inference`` (the pseudo-labelling
-path implemented here: pooling, decode, per-class NMS, top-k all run in libsfod_b200) or the training losses.  Proposal
-labelling/sampling and the losses are the student's training step and raise NotImplementedError.
-The box-head FCs stay on cuBLAS (dense GEMMs are library work per BASELINE.json north_star).
+path: pooling, decode, per-class NMS, top-k all run in libsfod_b200) or the training losses.  Proposal labelling /
+sampling and the losses (the student's training step) are restated from detectron2 0.6 and the
+reference in plain torch; in that mode the library contributes ROIAlign forward AND backward (autograd) and the decode
+kernels.  The box-head FCs stay on cuBLAS (dense GEMMs are library work per BASELINE.json north_star).
 """
 from __future__ import annotations
 
@@ -16,8 +17,10 @@ import torch
 from torch import Tensor, nn
 
 from ..registry import ROI_BOX_HEAD_REGISTRY, ROI_HEADS_REGISTRY
-from ..structures import Boxes, ImageList, Instances, ShapeSpec
+from ..structures import Boxes, ImageList, Instances, ShapeSpec, pairwise_iou
+from ..utils.events import get_event_storage
 from .fast_rcnn import FastRCNNOutputLayers, SourceFreeFastRCNNOutputLayers
+from .matcher import Matcher, add_ground_truth_to_proposals, subsample_labels
 from .poolers import ROIPooler
 
 
@@ -78,9 +81,10 @@ class _StandardROIHeadsBase(nn.Module):
     def __init__(self, cfg=None, input_shape: Dict[str, ShapeSpec] = None, *, box_in_features: List[str] = None,
                  box_pooler: ROIPooler = None, box_head: nn.Module = None, box_predictor: nn.Module = None,
                  num_classes: int = None, batch_size_per_image: int = 512, positive_fraction: float = 0.25,
-                 proposal_append_gt: bool = True, train_on_pred_boxes: bool = False):
+                 proposal_append_gt: bool = True, train_on_pred_boxes: bool = False, proposal_matcher: Matcher = None):
         super().__init__()
         if cfg is not None:
+            proposal_matcher = Matcher(cfg.MODEL.ROI_HEADS.IOU_THRESHOLDS, cfg.MODEL.ROI_HEADS.IOU_LABELS, allow_low_quality_matches=False)
             parts = self._init_box_head(cfg, input_shape)
             box_in_features, box_pooler = parts["box_in_features"], parts["box_pooler"]
             box_head, box_predictor = parts["box_head"], parts["box_predictor"]
@@ -94,6 +98,7 @@ class _StandardROIHeadsBase(nn.Module):
         self.num_classes = num_classes
         self.batch_size_per_image, self.positive_fraction = batch_size_per_image, positive_fraction
         self.proposal_append_gt, self.train_on_pred_boxes = proposal_append_gt, train_on_pred_boxes
+        self.proposal_matcher = proposal_matcher or Matcher([0.5], [0, 1], allow_low_quality_matches=False)
 
     @classmethod
     def _init_box_head(cls, cfg, input_shape):
@@ -115,8 +120,47 @@ class _StandardROIHeadsBase(nn.Module):
             raise ValueError("Unknown ROI head loss.")
         return {"box_in_features": in_features, "box_pooler": box_pooler, "box_head": box_head, "box_predictor": box_predictor}
 
-    def label_and_sample_proposals(self, proposals, targets, branch: str = ""):
-        raise NotImplementedError("proposal labelling/sampling belongs to the student's training step (SURVEY.md 8f rank 1)")
+    def _sample_proposals(self, matched_idxs: Tensor, matched_labels: Tensor, gt_classes: Tensor):
+        """d2 ROIHeads._sample_proposals."""
+        has_gt = gt_classes.numel() > 0
+        if has_gt:
+            gt_classes = gt_classes[matched_idxs]
+            gt_classes[matched_labels == 0] = self.num_classes   # background
+            gt_classes[matched_labels == -1] = -1                # ignore
+        else:
+            gt_classes = torch.zeros_like(matched_idxs) + self.num_classes
+        sampled_fg_idxs, sampled_bg_idxs = subsample_labels(gt_classes, self.batch_size_per_image, self.positive_fraction, self.num_classes)
+        sampled_idxs = torch.cat([sampled_fg_idxs, sampled_bg_idxs], dim=0)
+        return sampled_idxs, gt_classes[sampled_idxs]
+
+    @torch.no_grad()
+    def label_and_sample_proposals(self, proposals: List[Instances], targets: List[Instances], branch: str = "") -> List[Instances]:
+        """reference source_free_adaptive_teacher_roi_heads.py:165-215."""
+        gt_boxes = [x.gt_boxes for x in targets]
+        if self.proposal_append_gt:
+            proposals = add_ground_truth_to_proposals(gt_boxes, proposals)
+        proposals_with_gt, num_fg_samples, num_bg_samples = [], [], []
+        for proposals_per_image, targets_per_image in zip(proposals, targets):
+            has_gt = len(targets_per_image) > 0
+            match_quality_matrix = pairwise_iou(targets_per_image.gt_boxes, proposals_per_image.proposal_boxes)
+            matched_idxs, matched_labels = self.proposal_matcher(match_quality_matrix)
+            sampled_idxs, gt_classes = self._sample_proposals(matched_idxs, matched_labels, targets_per_image.gt_classes)
+            proposals_per_image = proposals_per_image[sampled_idxs]
+            proposals_per_image.gt_classes = gt_classes
+            if has_gt:
+                sampled_targets = matched_idxs[sampled_idxs]
+                for (trg_name, trg_value) in targets_per_image.get_fields().items():
+                    if trg_name.startswith("gt_") and not proposals_per_image.has(trg_name):
+                        proposals_per_image.set(trg_name, trg_value[sampled_targets])
+            else:
+                proposals_per_image.gt_boxes = Boxes(targets_per_image.gt_boxes.tensor.new_zeros((len(sampled_idxs), 4)))
+            num_bg_samples.append((gt_classes == self.num_classes).sum().item())
+            num_fg_samples.append(gt_classes.numel() - num_bg_samples[-1])
+            proposals_with_gt.append(proposals_per_image)
+        storage = get_event_storage()
+        storage.put_scalar("roi_head/num_target_fg_samples_" + branch, np.mean(num_fg_samples))
+        storage.put_scalar("roi_head/num_target_bg_samples_" + branch, np.mean(num_bg_samples))
+        return proposals_with_gt
 
     def _wants_loss(self, compute_loss: bool, compute_val_loss: bool) -> bool:
         return (self.training and compute_loss) or compute_val_loss
@@ -136,7 +180,8 @@ class _StandardROIHeadsBase(nn.Module):
             self.proposal_append_gt = tmp
         del targets
         if self._wants_loss(compute_loss, compute_val_loss):
-            return (proposals,) + tuple(self._forward_box(features, proposals, compute_loss, compute_val_loss, branch))
+            out = self._forward_box(features, proposals, compute_loss, compute_val_loss, branch)
+            return (proposals, out[0]) + tuple(out[2:])      # (proposals, losses, box_features[, instance_proposals])
         pred_instances, predictions = self._forward_box(features, proposals, compute_loss, compute_val_loss, branch)
         return pred_instances, predictions
 
@@ -150,10 +195,23 @@ class _StandardROIHeadsBase(nn.Module):
                      compute_val_loss: bool = False, branch: str = ""):
         box_features, predictions = self._box_predictions(features, proposals)
         if self._wants_loss(compute_loss, compute_val_loss):
-            losses = self.box_predictor.losses(predictions, proposals)  # raises: SURVEY.md 8f rank 1
-            return losses, predictions, box_features
+            losses = self.box_predictor.losses(predictions, proposals)
+            return self._after_losses(losses, predictions, box_features, proposals)
         pred_instances, _ = self.box_predictor.inference(predictions, proposals)  # reference ...roi_heads.py:161
         return pred_instances, predictions
+
+    def _replace_proposals_by_predictions(self, predictions, proposals: List[Instances]) -> None:
+        with torch.no_grad():
+            pred_boxes = self.box_predictor.predict_boxes_for_gt_classes(predictions, proposals)
+            for proposals_per_image, pred_boxes_per_image in zip(proposals, pred_boxes):
+                proposals_per_image.proposal_boxes = Boxes(pred_boxes_per_image)
+
+    def _after_losses(self, losses, predictions, box_features, proposals):
+        """reference source_free_adaptive_teacher_roi_heads.py:139-158: proposals are replaced by the boxes predicted for
+        their GT class (unconditionally), then the dense per-class instances for bpc_loss are produced."""
+        self._replace_proposals_by_predictions(predictions, proposals)
+        instance_proposals, _ = self.box_predictor.convert_bbox_scores(predictions, proposals)
+        return losses, predictions, box_features, instance_proposals
 
 
 @ROI_HEADS_REGISTRY.register()
@@ -176,11 +234,18 @@ class SourceFreeAdaptiveTeacherEvalStandardROIHeads(_StandardROIHeadsBase):
             proposals = self.label_and_sample_proposals(proposals, targets, branch=branch)
         del targets
         if self._wants_loss(compute_loss, compute_val_loss):
-            return (proposals,) + tuple(self._forward_box(features, proposals, compute_loss, compute_val_loss, branch))
+            out = self._forward_box(features, proposals, compute_loss, compute_val_loss, branch)
+            return (proposals, out[0]) + tuple(out[2:])
         return self._forward_box(features, proposals, compute_loss, compute_val_loss, branch)
 
 
 @ROI_HEADS_REGISTRY.register()
 class AdaptiveTeacherStandardROIHeads(_StandardROIHeadsBase):
-    """reference adaptive_teacher_roi_heads.py:22-187 (plain FastRCNNOutputLayers predictor)."""
+    """reference adaptive_teacher_roi_heads.py:22-187 (plain FastRCNNOutputLayers predictor; the loss branch returns
+    ``(losses, predictions, box_features)`` and only replaces the proposals when ``train_on_pred_boxes``, :119-133)."""
     predictor_cls = FastRCNNOutputLayers
+
+    def _after_losses(self, losses, predictions, box_features, proposals):
+        if self.train_on_pred_boxes:
+            self._replace_proposals_by_predictions(predictions, proposals)
+        return losses, predictions, box_features

@@ -1,0 +1,53 @@
+"""detectron2.utils.events subset: the plugins log scalars through ``get_event_storage().put_scalar`` (reference
+daod/modeling/roi_heads/source_free_adaptive_teacher_roi_heads.py:207-213).  With detectron2 installed its storage is
+used; otherwise a minimal context-managed storage with the same calls (and a silent default one) stands in."""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Dict, List
+
+_CURRENT: List["EventStorage"] = []
+
+
+class EventStorage:
+    def __init__(self, start_iter: int = 0):
+        self.iter = start_iter
+        self._latest: Dict[str, float] = {}
+        self._history: Dict[str, List[float]] = defaultdict(list)
+
+    def put_scalar(self, name: str, value, smoothing_hint: bool = True) -> None:
+        value = float(value)
+        self._latest[name] = value
+        self._history[name].append(value)
+
+    def put_scalars(self, *, smoothing_hint: bool = True, **kwargs) -> None:
+        for k, v in kwargs.items():
+            self.put_scalar(k, v, smoothing_hint)
+
+    def latest(self) -> Dict[str, float]:
+        return dict(self._latest)
+
+    def history(self, name: str) -> List[float]:
+        return self._history[name]
+
+    def step(self) -> None:
+        self.iter += 1
+
+    def __enter__(self):
+        _CURRENT.append(self)
+        return self
+
+    def __exit__(self, *exc):
+        assert _CURRENT[-1] is self
+        _CURRENT.pop()
+
+
+_DEFAULT = EventStorage()
+
+
+def get_event_storage() -> EventStorage:
+    try:  # pragma: no cover - detectron2 is absent in the build environment
+        from detectron2.utils.events import get_event_storage as d2_get
+        return d2_get()
+    except Exception:
+        return _CURRENT[-1] if _CURRENT else _DEFAULT

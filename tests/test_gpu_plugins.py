@@ -95,8 +95,13 @@ def test_pseudolab_rpn_forward_signature_and_flatten(teacher, cuda_device):
         assert abs(len(g) - len(r["proposal_boxes"])) <= max(3, len(r["proposal_boxes"]) // 100)
         k = min(len(g), len(r["proposal_boxes"]), 50)
         assert torch.allclose(g.proposal_boxes.tensor[:k].cpu(), r["proposal_boxes"][:k], rtol=1e-3, atol=1e-2) or k == 0
-    with pytest.raises(NotImplementedError):
-        rpn(images, {"vgg4": feat.to(cuda_device)}, None, compute_loss=True)
+    gt = []
+    for _ in range(2):
+        i = Instances((600, 1200)); i.gt_boxes = Boxes(torch.tensor([[100.0, 100, 400, 300], [600, 200, 900, 560]], device=cuda_device))
+        i.gt_classes = torch.tensor([1, 3], device=cuda_device); gt.append(i)
+    props2, losses2 = rpn(images, {"vgg4": feat.to(cuda_device)}, gt, compute_loss=True)      # student mode: losses + proposals
+    assert set(losses2) == {"loss_rpn_cls", "loss_rpn_loc"} and all(torch.isfinite(v) for v in losses2.values())
+    assert len(props2) == 2
 
 
 def test_roi_pooler_matches_oracle(teacher, cuda_device):
@@ -239,3 +244,63 @@ def test_teacher_end_to_end_against_cpu_pipeline(teacher, cuda_device):
             assert torch.allclose(v.cpu(), sd[k], rtol=2e-4, atol=1e-4), k
         if k.endswith("num_batches_tracked"):
             assert v.item() == sd[k].item()
+
+
+def test_student_step_through_plugins_forward_backward(cfg, cuda_device):
+    """SURVEY.md 8f rank 1 + 8a-a6: a student training step through the same plugins -- RPN/ROI losses in plain torch,
+    ROIAlign forward AND backward on the sm_100a kernels -- produces finite losses and gradients, and its ROI-head losses
+    agree with the CPU oracle evaluated on the same features / sampled proposals."""
+    from sfod_b200 import ops
+    from sfod_b200.utils.events import EventStorage
+    import sfod_b200.modeling.matcher as M
+    torch.manual_seed(11)
+    student = registry.build_model(cfg)
+    student.train()
+    img = torch.randint(0, 256, (2, 3, 320, 480), dtype=torch.uint8, generator=torch.Generator().manual_seed(6)).float()
+    batched = []
+    for i in range(2):
+        inst = Instances((320, 480))
+        inst.gt_boxes = Boxes(torch.tensor([[30.0, 40, 200, 220], [250, 60, 460, 300]]))
+        inst.gt_classes = torch.tensor([2, 5])
+        batched.append({"image": img[i], "instances": inst})
+    ops.timers.start()
+    with EventStorage() as storage:
+        losses, proposals_roih, _, _ = student(batched, branch="supervised_target")
+        total = sum(losses.values())
+        total.backward()
+    times = ops.timers.stop()
+    assert set(losses) == {"loss_cls", "loss_box_reg", "loss_rpn_cls", "loss_rpn_loc", "loss_bpc"}
+    assert all(torch.isfinite(v) for v in losses.values()) and losses["loss_bpc"].item() == 0
+    assert "roi_align_bwd" in times and times["roi_align_fwd"][0] == 2       # sampled-proposal pass + all-proposal inference pass
+    for name in ("backbone.vgg0.0.weight", "backbone.vgg4.6.weight", "proposal_generator.rpn_head.conv.weight",
+                 "roi_heads.box_head.fc1.weight", "roi_heads.box_predictor.bbox_pred.weight"):
+        g = dict(student.named_parameters())[name].grad
+        assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0, name
+    assert len(proposals_roih) == 2 and "fast_rcnn/cls_accuracy" in storage.latest()
+    # ROI-head losses vs the oracle on identical inputs (features from the GPU backbone, same sampled proposals)
+    with torch.no_grad(), EventStorage():
+        images = student.preprocess_image(batched)
+        feats = student.backbone(images.tensor)          # grad-free train-mode forward: native BN path
+        props, _ = student.proposal_generator(images, feats, None, compute_loss=False)
+        gts = [b["instances"].to(cuda_device) for b in batched]
+        orig = M.subsample_labels
+        import sfod_b200.modeling.roi_heads as rh
+        rh.subsample_labels = lambda *a, **k: orig(*a, **{**k, "randperm": lambda n, device=None: torch.arange(n, device=device)})
+        try:
+            sampled = student.roi_heads.label_and_sample_proposals(props, gts, branch="t")
+        finally:
+            rh.subsample_labels = orig
+        box_features, predictions = student.roi_heads._box_predictions(feats, sampled)
+        got = student.roi_heads.box_predictor.losses(predictions, sampled)
+        f_cpu = feats["vgg4"].cpu()
+        osampled = [dict(proposal_boxes=s.proposal_boxes.tensor.cpu(), gt_classes=s.gt_classes.cpu(), gt_boxes=s.gt_boxes.tensor.cpu()) for s in sampled]
+        pooled = o.roi_pooler(f_cpu, [s["proposal_boxes"] for s in osampled], 7, 1 / 32, 0, "ROIAlignV2")
+        sd = {k: v.detach().cpu() for k, v in student.state_dict().items()}
+        F = torch.nn.functional
+        h = F.relu(F.linear(pooled.flatten(1), sd["roi_heads.box_head.fc1.weight"], sd["roi_heads.box_head.fc1.bias"]))
+        h = F.relu(F.linear(h, sd["roi_heads.box_head.fc2.weight"], sd["roi_heads.box_head.fc2.bias"]))
+        sc = F.linear(h, sd["roi_heads.box_predictor.cls_score.weight"], sd["roi_heads.box_predictor.cls_score.bias"])
+        dl = F.linear(h, sd["roi_heads.box_predictor.bbox_pred.weight"], sd["roi_heads.box_predictor.bbox_pred.bias"])
+        want = o.fast_rcnn_losses(sc, dl, osampled, 8)
+    for k in want:
+        assert torch.allclose(got[k].cpu(), want[k], rtol=1e-4, atol=1e-6), (k, got[k].item(), want[k].item())
