@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument("--tf32", type=int, default=0, help="1 = let cuDNN/cuBLAS use TF32 for the (library) convs/FCs")
     ap.add_argument("--channels-last", type=int, default=0, help="1 = run the backbone in NHWC")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sfod-step", type=int, default=1,
+                    help="1 = also time the full mean-teacher step of configs[2] (teacher pseudo-labelling, student forward/backward "
+                         "on the pseudo-labels through the same plugins, DDP gradient all-reduce for N > 1, SGD step, EMA); reported as "
+                         "the extra object `sfod_step`, it does not enter `value`")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`); "
                          "numbers printed under a profiler are not bench values")
@@ -287,6 +291,47 @@ def run_b200(args):
     value = world * B * args.steps / (ms / 1e3)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
+    # ---- optional: the full mean-teacher step of configs[2] (SURVEY.md 8d "also report full SFOD step/s")
+    sfod_step = None
+    if args.sfod_step:
+        try:
+            from sfod_b200.utils.events import EventStorage
+            stu = student
+            if world > 1:
+                stu = torch.nn.parallel.DistributedDataParallel(student, device_ids=[local_rank], broadcast_buffers=False)
+            opt = torch.optim.SGD(student.parameters(), lr=0.0025, momentum=0.9, weight_decay=1e-4)
+            ema_ddp = engine.TeacherEMA(stu, teacher, world_size=world)   # strips the DDP 'module.' prefix like the reference
+
+            def full_step(i):
+                imgs = dev_batches[i % n_rot]
+                _, _, pl = pseudo_label(imgs)
+                batch = [{"image": imgs[j].float(), "instances": Instances_for(pl[j])} for j in range(B)]
+                losses, _, _, _ = stu(batch, branch="supervised_target")
+                loss = sum(losses.values())
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                ema_ddp.step(cfg.SEMISUPNET.EMA_KEEP_RATE)
+                return loss
+
+            def Instances_for(p):
+                from sfod_b200.structures import Instances
+                t = Instances(p.image_size)
+                t.gt_boxes, t.gt_classes = p.gt_boxes, p.gt_classes
+                return t
+
+            n_full = max(3, min(args.steps, 5))
+            with EventStorage():
+                for i in range(2):
+                    full_step(i)
+                ms_full, launches_full, _, last_loss = timed(full_step, n_full)
+            sfod_step = {"ms_per_step": round(ms_full / n_full, 3), "steps": n_full, "images_per_s": round(world * B * n_full / (ms_full / 1e3), 2),
+                         "loss_last": round(float(last_loss), 5), "gpu_launches": int(launches_full),
+                         "what": "teacher pseudo-labelling + student supervised_target fwd/bwd on the pseudo-labels"
+                                 + (" + DDP all-reduce (NCCL)" if world > 1 else "") + " + SGD + EMA"}
+        except Exception as e:  # never lose the headline line to the optional measurement
+            sfod_step = {"error": repr(e)[:300]}
+
     # ---- per-kernel algorithmic bytes of one step (DESIGN.md "Algorithmic bytes"), fp32
     peak, peak_src = peaks()
     # activation elements entering the 13 BN layers of VGG16 at 600x1200 (per image): SURVEY.md App. C = 194 342 400
@@ -344,6 +389,7 @@ def run_b200(args):
             "kernels": kernels,
             "hot_path": {"ms_per_step": round(hot_ms, 3), "share_of_step": round(hot_ms / (ms / args.steps), 4),
                          "note": "sum of the event-timed C-ABI calls; the rest of the step is cuDNN conv / cuBLAS FC / torch glue"},
+            "sfod_step": sfod_step,
             "proposals_last_step": [len(p) for p in out[0]],
             "detections_last_step": [len(p) for p in out[1]],
             "pseudo_labels_last_step": [len(p) for p in out[2]]}
