@@ -363,14 +363,32 @@ def run_b200(args):
         kernels[tag] = rec
     hot_ms = sum(v["ms_per_step"] for v in kernels.values())
 
+    # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture of this same command
+    traffic_map = {"bn_finalize_apply": "bn_apply_nchw_kernel", "bn_finalize_apply_pool": "bn_apply_pool_nchw_kernel",
+                   "bn_partial_stats": "bn_stats_nchw_kernel", "roi_align_fwd": "roi_align_fwd_sep_kernel",
+                   "ema_multi_tensor": "ema_multi_tensor_kernel"}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ncu_traffic = json.load(f)
+    except Exception:
+        ncu_traffic = {}
     dominant = max((t for t in kernels if "GBps" in kernels[t]), key=lambda t: kernels[t]["ms_per_step"], default=None)
     roofline = None
     if dominant is not None:
         k = kernels[dominant]
         per_launch_ms = k["ms_per_step"] / k["calls_per_step"]
-        roofline = {"kernel": dominant, "bound": "hbm", "achieved": k["GBps"], "peak": peak, "unit": "GB/s", "frac": k["frac_of_peak"],
-                    "traffic": None, "peak_source": peak_src, "avg_call_ms": round(per_launch_ms, 4),
-                    "alg_bytes_per_step": alg[dominant], "note": "CUDA events around the C-ABI call, inside the timed region"}
+        tr = ncu_traffic.get(traffic_map.get(dominant, ""), {})
+        roofline = {"kernel": traffic_map.get(dominant, dominant), "call": dominant, "bound": "hbm", "achieved": k["GBps"], "peak": peak,
+                    "unit": "GB/s", "frac": k["frac_of_peak"], "traffic": tr.get("dram_bytes_per_launch"),
+                    "alg_bytes_per_launch": round(alg[dominant] / k["calls_per_step"]), "avg_launch_ms": round(per_launch_ms, 4),
+                    "launches_per_step": k["calls_per_step"], "peak_source": peak_src,
+                    "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)"
+                                      if tr else None,
+                    "note": "achieved = algorithmic bytes per launch / mean launch duration, CUDA events around the C-ABI call on the "
+                            "launching stream inside the timed region (each call = one bn_finalize (C threads) + one apply kernel)"}
+    for tag, kern in traffic_map.items():
+        if tag in kernels and kern in ncu_traffic:
+            kernels[tag]["ncu_dram_MB_per_launch"] = round(ncu_traffic[kern]["dram_bytes_per_launch"] / 1e6, 2)
 
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

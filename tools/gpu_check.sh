@@ -14,6 +14,6 @@ timeout 600 python bench.py --steps 10 --warmup 3 --tf32 1 --no-cpu-baseline > g
 timeout 600 python bench.py --steps 10 --warmup 3 --channels-last 1 --no-cpu-baseline > gpurun_out/bench_${TAG}_nhwc.json 2>> gpurun_out/bench_$TAG.err
 timeout 600 python bench.py --steps 10 --warmup 3 --channels-last 1 --tf32 1 --no-cpu-baseline > gpurun_out/bench_${TAG}_nhwc_tf32.json 2>> gpurun_out/bench_$TAG.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
-    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --profiler-range > gpurun_out/ncu_bench_$TAG.log 2>&1
+    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sfod-step 0 --profiler-range > gpurun_out/ncu_bench_$TAG.log 2>&1
 echo "ncu rc=$?"
 tail -3 gpurun_out/bench_$TAG.err

@@ -6,14 +6,14 @@ TAG=${1:-r1}
 mkdir -p gpurun_out
 cap() {  # name, kernel regex, launch count
   timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$2" -c $3 \
-      -o gpurun_out/prof_${TAG}_$1 -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --profiler-range > gpurun_out/ncu_full_${TAG}_$1.log 2>&1
+      -o gpurun_out/prof_${TAG}_$1 -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --sfod-step 0 --profiler-range > gpurun_out/ncu_full_${TAG}_$1.log 2>&1
   echo "ncu $1 rc=$?"
   ncu -i gpurun_out/prof_${TAG}_$1.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_$1.raw.csv 2>/dev/null
   ncu -i gpurun_out/prof_${TAG}_$1.ncu-rep --page source --csv > gpurun_out/prof_${TAG}_$1.source.csv 2>/dev/null
   gzip -f gpurun_out/prof_${TAG}_$1.source.csv
   sz=$(stat -c %s gpurun_out/prof_${TAG}_$1.ncu-rep)
-  if [ "$sz" -gt 12000000 ]; then rm -f gpurun_out/prof_${TAG}_$1.ncu-rep; fi
+  if [ "$sz" -gt 6000000 ]; then rm -f gpurun_out/prof_${TAG}_$1.ncu-rep; fi
 }
-cap det 'roi_align|ema_multi|nms_mask|nms_scan|bitonic|rpn_|frcnn_|transpose' 40
-cap bn 'bn_apply|bn_stats|bn_finalize' 9
+cap det 'roi_align|ema_multi|nms_|bitonic|rpn_|frcnn_|transpose' 40
+cap bn 'bn_apply|bn_stats|bn_finalize' 39
 du -sh gpurun_out
