@@ -170,7 +170,7 @@ def run_reference(args):
             "cpu_baseline": info,
             "e2e": {"value": info["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -298,7 +298,8 @@ def run_b200(args):
             from sfod_b200.utils.events import EventStorage
             stu = student
             if world > 1:
-                stu = torch.nn.parallel.DistributedDataParallel(student, device_ids=[local_rank], broadcast_buffers=False)
+                stu = torch.nn.parallel.DistributedDataParallel(student, device_ids=[local_rank], broadcast_buffers=False,
+                                                                find_unused_parameters=True)   # DC_img / DC_ins are idle in this branch
             opt = torch.optim.SGD(student.parameters(), lr=0.0025, momentum=0.9, weight_decay=1e-4)
             ema_ddp = engine.TeacherEMA(stu, teacher, world_size=world)   # strips the DDP 'module.' prefix like the reference
 
@@ -326,7 +327,7 @@ def run_b200(args):
                     full_step(i)
                 ms_full, launches_full, _, last_loss = timed(full_step, n_full)
             sfod_step = {"ms_per_step": round(ms_full / n_full, 3), "steps": n_full, "images_per_s": round(world * B * n_full / (ms_full / 1e3), 2),
-                         "loss_last": round(float(last_loss), 5), "gpu_launches": int(launches_full),
+                         "loss_last": round(float(last_loss.detach()), 5), "gpu_launches": int(launches_full),
                          "what": "teacher pseudo-labelling + student supervised_target fwd/bwd on the pseudo-labels"
                                  + (" + DDP all-reduce (NCCL)" if world > 1 else "") + " + SGD + EMA"}
         except Exception as e:  # never lose the headline line to the optional measurement
@@ -418,14 +419,31 @@ def run_b200(args):
         except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's real stdout; everything else any library prints (e.g. NCCL's version
+    banner, which goes to stdout at C level) has been redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)          # fd 1 -> stderr for the rest of the run
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
