@@ -199,6 +199,19 @@ int sfod_softmax_lastdim(const float *x, int64_t R, int K1, float *out, sfod_str
 int sfod_threshold_select(const float *values, const int32_t *counts_dev, int S, int stride, float thres,
                           int64_t *out_index, int32_t *out_count_dev, sfod_stream_t stream);
 
+/* Adaptive per-class threshold variant of the pseudo-label filter (reference
+ * daod/modeling/adaptive_thresh/adaptive_confidence.py:21-33 as used by adaptive_threshold_bbox / prediction_threshold_bbox,
+ * daod/engine/trainers/source_free_adaptive_teacher.py:185-254): same segment layout as sfod_threshold_select, entry j of
+ * segment s is kept iff values[s][j] >= class_thresh_dev[classes[s][j]] (K device floats; note >=).  classes outside
+ * [0, K) are dropped. */
+int sfod_class_threshold_select(const float *values, const int64_t *classes, const int32_t *counts_dev, int S, int stride,
+                                int K, const float *class_thresh_dev, int64_t *out_index, int32_t *out_count_dev,
+                                sfod_stream_t stream);
+/* count_label_prediction (source_free_adaptive_teacher.py:282-296) for the whole batch in one launch: hist_dev (K) int64
+ * receives, per class, the number of entries with value > thres over all S segments (zeroed by the call). */
+int sfod_class_histogram(const float *values, const int64_t *classes, const int32_t *counts_dev, int S, int stride, int K,
+                         float thres, int64_t *hist_dev, sfod_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * BatchNorm train-mode forward / AdaBN statistic recomputation.  Replaces the
  * nn.BatchNorm2d train-mode forwards driven by test_refinement

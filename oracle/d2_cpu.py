@@ -542,3 +542,36 @@ def fast_rcnn_losses(scores, proposal_deltas, proposals: List[dict], num_classes
     pred = proposal_deltas.view(-1, num_classes, 4)[fg, gt_classes[fg]]
     loss_box = F.l1_loss(pred, get_deltas(pb[fg], gb[fg], weights), reduction="sum") / max(gt_classes.numel(), 1.0)
     return {"loss_cls": loss_cls, "loss_box_reg": loss_box}
+
+
+# --------------------------------------------------------------------------- adaptive per-class threshold
+def adaptive_confidence_mask(confidence: torch.Tensor, pseudo_labels: torch.Tensor, threshold: float, classwise_acc: torch.Tensor):
+    """reference daod/modeling/adaptive_thresh/adaptive_confidence.py:21-33 ("convex" map)."""
+    return (confidence >= threshold * (classwise_acc[pseudo_labels] / (2. - classwise_acc[pseudo_labels]))).float()
+
+
+def adaptive_threshold_bbox(inst: dict, threshold: float, classwise_acc: torch.Tensor, as_gt: bool = True) -> dict:
+    """reference source_free_adaptive_teacher.py:185-228 (roih branch; as_gt=False: prediction_threshold_bbox :230-254)."""
+    mask = adaptive_confidence_mask(inst["scores"], inst["pred_classes"], threshold, classwise_acc)
+    valid = (mask == 1).nonzero().flatten()
+    kb, kc = ("gt_boxes", "gt_classes") if as_gt else ("pred_boxes", "pred_classes")
+    return {"image_size": inst.get("image_size"), kb: inst["pred_boxes"][valid, :], kc: inst["pred_classes"][valid], "scores": inst["scores"][valid]}
+
+
+def count_label_prediction(preds: List[dict], num_classes: int, bbox_threshold: float) -> torch.Tensor:
+    """reference source_free_adaptive_teacher.py:282-296."""
+    reserve = torch.zeros(num_classes)
+    for p in preds:
+        reserve += p["pred_classes"][p["scores"] > bbox_threshold].bincount(minlength=num_classes)
+    return reserve
+
+
+def update_adaptive_threshold(reserve_matrix: torch.Tensor) -> torch.Tensor:
+    """reference source_free_adaptive_teacher.py:298-310 -> new classwise_acc (classes 0 and 2 hard-coded, as in the reference)."""
+    counter = reserve_matrix.sum(dim=0)
+    counter[0] = 0
+    counter[2] = 0
+    acc = counter / max(counter.max(), 1)
+    acc[0] = 1
+    acc[2] = 1
+    return acc

@@ -282,6 +282,62 @@ __global__ void __launch_bounds__(kSelThreads) threshold_select_kernel(const flo
   if (tid == 0) out_count[s] = running;
 }
 
+
+// Per-class confidence filter of the adaptive-threshold pseudo-labelling variant (reference
+// daod/modeling/adaptive_thresh/adaptive_confidence.py:21-33 used by adaptive_threshold_bbox /
+// prediction_threshold_bbox, daod/engine/trainers/source_free_adaptive_teacher.py:185-254): keep entry j of segment s iff
+// values[s][j] >= class_thresh[classes[s][j]]  (note >=, the reference's `confidence >= threshold * ...`).
+__global__ void __launch_bounds__(kSelThreads) class_threshold_select_kernel(const float *__restrict__ values,
+                                                                             const long long *__restrict__ classes,
+                                                                             const int *__restrict__ counts, int stride, int K,
+                                                                             const float *__restrict__ class_thresh,
+                                                                             long long *__restrict__ out_index,
+                                                                             int *__restrict__ out_count) {
+  __shared__ int warp_tot[kSelThreads / 32];
+  __shared__ int running;
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(counts[s], stride);
+  if (tid == 0) running = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += kSelThreads) {
+    const int j = base + tid;
+    bool keep = false;
+    if (j < n) {
+      const long long c = classes[(size_t)s * stride + j];
+      keep = c >= 0 && c < K && values[(size_t)s * stride + j] >= class_thresh[c];
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = running;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (keep) out_index[(size_t)s * stride + off + __popc(bal & ((1u << lane) - 1u))] = j;
+    __syncthreads();
+    if (tid == 0) { int tot = 0; for (int w = 0; w < kSelThreads / 32; ++w) tot += warp_tot[w]; running += tot; }
+    __syncthreads();
+  }
+  if (tid == 0) out_count[s] = running;
+}
+
+// count_label_prediction (reference source_free_adaptive_teacher.py:282-296): per-class number of entries with
+// value > thres over ALL segments (one launch for the batch instead of a bincount per image); hist (K) int64, zeroed here.
+__global__ void __launch_bounds__(256) class_histogram_kernel(const float *__restrict__ values, const long long *__restrict__ classes,
+                                                              const int *__restrict__ counts, int S, int stride, int K, float thres,
+                                                              unsigned long long *__restrict__ hist) {
+  extern __shared__ unsigned int sh_hist[];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sh_hist[k] = 0;
+  __syncthreads();
+  for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    const int n = min(counts[s], stride);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const long long c = classes[(size_t)s * stride + j];
+      if (c >= 0 && c < K && values[(size_t)s * stride + j] > thres) atomicAdd(&sh_hist[c], 1u);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) if (sh_hist[k]) atomicAdd(&hist[k], (unsigned long long)sh_hist[k]);
+}
+
 }  // namespace
 
 SFOD_API int sfod_apply_deltas(const float *deltas, const float *boxes, int64_t R, int k, const float *weights4_host,
@@ -321,6 +377,34 @@ SFOD_API int sfod_threshold_select(const float *values, const int32_t *counts_de
 static unsigned long long g_sfod_launches = 0;
 void sfod_count_launch() { __atomic_fetch_add(&g_sfod_launches, 1ull, __ATOMIC_RELAXED); }
 SFOD_API uint64_t sfod_debug_launch_count(void) { return __atomic_load_n(&g_sfod_launches, __ATOMIC_RELAXED); }
+
+SFOD_API int sfod_class_threshold_select(const float *values, const int64_t *classes, const int32_t *counts_dev, int S, int stride,
+                                         int K, const float *class_thresh_dev, int64_t *out_index, int32_t *out_count_dev,
+                                         sfod_stream_t stream) {
+  if (S < 0 || stride < 0 || K <= 0) return SFOD_ERR_INVALID_ARG;
+  if (S == 0) return SFOD_OK;
+  if (!values || !classes || !counts_dev || !class_thresh_dev || !out_index || !out_count_dev) return SFOD_ERR_INVALID_ARG;
+  class_threshold_select_kernel<<<S, kSelThreads, 0, sfod_cu(stream)>>>(values, reinterpret_cast<const long long *>(classes),
+                                                                       counts_dev, stride, K, class_thresh_dev,
+                                                                       reinterpret_cast<long long *>(out_index), out_count_dev);
+  SFOD_LAUNCH_CHECK();
+  return SFOD_OK;
+}
+
+SFOD_API int sfod_class_histogram(const float *values, const int64_t *classes, const int32_t *counts_dev, int S, int stride, int K,
+                                  float thres, int64_t *hist_dev, sfod_stream_t stream) {
+  if (S < 0 || stride < 0 || K <= 0 || K > 8192 || !hist_dev) return SFOD_ERR_INVALID_ARG;
+  cudaStream_t st = sfod_cu(stream);
+  SFOD_CUDA_TRY(cudaMemsetAsync(hist_dev, 0, (size_t)K * sizeof(int64_t), st));
+  if (S == 0) return SFOD_OK;
+  if (!values || !classes || !counts_dev) return SFOD_ERR_INVALID_ARG;
+  const int grid = S < SFOD_NUM_SMS ? S : SFOD_NUM_SMS;
+  class_histogram_kernel<<<grid, 256, (size_t)K * sizeof(unsigned int), st>>>(values, reinterpret_cast<const long long *>(classes),
+                                                                             counts_dev, S, stride, K, thres,
+                                                                             reinterpret_cast<unsigned long long *>(hist_dev));
+  SFOD_LAUNCH_CHECK();
+  return SFOD_OK;
+}
 
 SFOD_API int sfod_abi_version(void) { return 1; }
 

@@ -53,13 +53,19 @@ def threshold_bbox(proposal_bbox_inst: Instances, thres: float = 0.7, proposal_t
 
 
 def process_pseudo_label(proposals_rpn_unsup_k: List[Instances], cur_threshold: float, proposal_type: str,
-                         pseudo_label_method: str = "") -> Tuple[List[Instances], float]:
+                         pseudo_label_method: str = "", criterion=None) -> Tuple[List[Instances], float]:
     list_instances = []
     num_proposal_output = 0.0
     for proposal_bbox_inst in proposals_rpn_unsup_k:
         if pseudo_label_method == "thresholding":
             proposal_bbox_inst = threshold_bbox(proposal_bbox_inst, thres=cur_threshold, proposal_type=proposal_type)
-        else:  # adaptive_thresholding / prediction_thresholding: SURVEY.md 8f rank 2 (ADAPTIVE_THRESHOLD.ENABLED False everywhere)
+        elif pseudo_label_method in ("adaptive_thresholding", "prediction_thresholding"):
+            if criterion is None:
+                raise ValueError(f"{pseudo_label_method} needs the trainer's self_training_criterion (pass criterion=...)")
+            from .adaptive_threshold import adaptive_threshold_bbox, prediction_threshold_bbox
+            fn = adaptive_threshold_bbox if pseudo_label_method == "adaptive_thresholding" else prediction_threshold_bbox
+            proposal_bbox_inst = fn(criterion, proposal_bbox_inst, thres=cur_threshold, proposal_type=proposal_type)
+        else:
             raise ValueError("Unkown pseudo label boxes methods")
         num_proposal_output += len(proposal_bbox_inst)
         list_instances.append(proposal_bbox_inst)

@@ -331,6 +331,39 @@ def threshold_select(values: Tensor, counts: Tensor, thres: float) -> Tuple[Tens
     return idx, cnt
 
 
+def class_threshold_select(values: Tensor, classes: Tensor, counts: Tensor, class_thresh: Tensor) -> Tuple[Tensor, Tensor]:
+    """Per-row stable selection of ``values >= class_thresh[classes]`` among the first counts[s] entries.
+    values (S, stride) fp32, classes (S, stride) int64, class_thresh (K) fp32 -> (index (S, stride) int64, count (S) int32)."""
+    dev = _require_cuda(values, classes, counts, class_thresh)
+    v = _f32c(values)
+    cl = classes.detach().to(torch.int64).contiguous()
+    c = counts.to(torch.int32).contiguous()
+    th = _f32c(class_thresh)
+    if v.dim() != 2 or cl.shape != v.shape or c.shape != (v.shape[0],):
+        raise ValueError("values/classes must be (S, stride) and counts (S)")
+    S, stride = v.shape
+    idx = torch.empty((S, stride), dtype=torch.int64, device=dev)
+    cnt = torch.empty((S,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().sfod_class_threshold_select(v.data_ptr(), cl.data_ptr(), c.data_ptr(), S, stride, th.numel(), th.data_ptr(),
+                                                     idx.data_ptr(), cnt.data_ptr(), _stream(dev)), "sfod_class_threshold_select")
+    return idx, cnt
+
+
+def class_histogram(values: Tensor, classes: Tensor, counts: Tensor, num_classes: int, thres: float) -> Tensor:
+    """Per-class count of entries with ``values > thres`` over all rows (count_label_prediction for a batch) -> (K) int64."""
+    dev = _require_cuda(values, classes, counts)
+    v = _f32c(values)
+    cl = classes.detach().to(torch.int64).contiguous()
+    c = counts.to(torch.int32).contiguous()
+    S, stride = v.shape
+    hist = torch.empty((int(num_classes),), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().sfod_class_histogram(v.data_ptr(), cl.data_ptr(), c.data_ptr(), S, stride, int(num_classes), float(thres),
+                                              hist.data_ptr(), _stream(dev)), "sfod_class_histogram")
+    return hist
+
+
 # ----------------------------------------------------------------------------------------------- RPN selection
 def rpn_select(logits: Tensor, deltas: Tensor, image_sizes: Sequence[Tuple[int, int]], *, anchors: Optional[Tensor] = None,
                cell_anchors: Optional[Tensor] = None, feat_hw: Optional[Tuple[int, int]] = None, stride: int = 0,

@@ -304,3 +304,48 @@ def test_student_step_through_plugins_forward_backward(cfg, cuda_device):
         want = o.fast_rcnn_losses(sc, dl, osampled, 8)
     for k in want:
         assert torch.allclose(got[k].cpu(), want[k], rtol=1e-4, atol=1e-6), (k, got[k].item(), want[k].item())
+
+
+def test_adaptive_per_class_threshold_matches_oracle(cuda_device):
+    """adaptive_threshold_bbox / prediction_threshold_bbox / count_label_prediction /
+    update_adaptive_threshold on the class-threshold kernels vs the reference's numpy-round-trip arithmetic."""
+    from sfod_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    K = 8
+    insts, oinsts = [], []
+    for n in (100, 0, 37):
+        sc = torch.rand(n, generator=g).sort(descending=True).values
+        cl = torch.randint(0, K, (n,), generator=g)
+        bx = torch.rand(n, 4, generator=g) * 100
+        i = Instances((600, 1200)); i.pred_boxes = Boxes(bx.to(cuda_device)); i.scores = sc.to(cuda_device); i.pred_classes = cl.to(cuda_device)
+        insts.append(i); oinsts.append(dict(image_size=(600, 1200), pred_boxes=bx, scores=sc, pred_classes=cl))
+    crit = engine.AdaptiveConfidenceBasedSelfTrainingLoss(0.8, K, device=cuda_device)
+    reserve = torch.zeros(5, K, device=cuda_device)
+    row = engine.count_label_prediction(insts, K, 0.8)
+    want_row = o.count_label_prediction(oinsts, K, 0.8)
+    assert torch.equal(row.cpu(), want_row)
+    reserve[0] = row
+    reserve[1] = torch.tensor([9.0, 1, 4, 0, 2, 7, 3, 5], device=cuda_device)
+    engine.update_adaptive_threshold(crit, reserve)
+    acc = o.update_adaptive_threshold(reserve.cpu().clone())
+    assert torch.equal(crit.classwise_acc.cpu(), acc)
+    # a confidence sitting exactly on its class threshold is kept (>=)
+    thr = crit.class_thresholds().cpu()
+    insts[0].scores[3] = thr[insts[0].pred_classes[3].item()].item(); oinsts[0]["scores"][3] = insts[0].scores[3].item()
+    for method, as_gt in (("adaptive_thresholding", True), ("prediction_thresholding", False)):
+        got, avg = engine.process_pseudo_label(insts, 0.8, "roih", method, criterion=crit)
+        for gi, oi in zip(got, oinsts):
+            w = o.adaptive_threshold_bbox(oi, 0.8, acc, as_gt)
+            kb, kc = ("gt_boxes", "gt_classes") if as_gt else ("pred_boxes", "pred_classes")
+            assert torch.equal(gi.get(kb).tensor.cpu(), w[kb]) and torch.equal(gi.get(kc).cpu(), w[kc]) and torch.equal(gi.scores.cpu(), w["scores"])
+    mask = crit(insts[0].scores, insts[0].pred_classes)
+    assert torch.equal(mask.cpu(), o.adaptive_confidence_mask(oinsts[0]["scores"], oinsts[0]["pred_classes"], 0.8, acc))
+    with pytest.raises(ValueError):
+        engine.process_pseudo_label(insts, 0.8, "roih", "adaptive_thresholding")        # criterion missing
+    # raw operator on padded rows
+    v = torch.rand(4, 50, generator=g); c = torch.randint(0, K, (4, 50), generator=g)
+    counts = torch.tensor([50, 0, 13, 50], dtype=torch.int32)
+    idx, cnt = ops.class_threshold_select(v.to(cuda_device), c.to(cuda_device), counts.to(cuda_device), thr.to(cuda_device))
+    for s_ in range(4):
+        ref = (v[s_, :counts[s_]] >= thr[c[s_, :counts[s_]]]).nonzero().flatten()
+        assert cnt[s_].item() == ref.numel() and torch.equal(idx[s_, :ref.numel()].cpu(), ref)
