@@ -186,3 +186,23 @@ def test_world_size_2_gloo_sharding_and_bn_stat_reduction(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29517", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_pseudo_label_export_formats():
+    """COCO result json of detections, prediction_to_gt (score >= 0.7, ids from 1), detector_postprocess."""
+    inst = Instances((600, 1200))
+    inst.pred_boxes = Boxes(torch.tensor([[10.0, 20.0, 110.0, 220.0], [0.0, 0.0, 1200.0, 600.0], [5.0, 5.0, 6.0, 6.0]]))
+    inst.scores = torch.tensor([0.9, 0.75, 0.3])
+    inst.pred_classes = torch.tensor([2, 0, 7])
+    res = engine.instances_to_coco_json(inst, 42)
+    assert res[0] == {"image_id": 42, "category_id": 2, "bbox": [10.0, 20.0, 100.0, 200.0], "score": pytest.approx(0.9)}
+    assert [r["category_id"] for r in engine.instances_to_coco_json(inst, 1, id_map={0: 24, 2: 26, 7: 33})] == [26, 24, 33]
+    assert engine.instances_to_coco_json(inst[inst.scores > 2], 1) == []
+    ds = {"images": [{"id": 42}], "categories": [], "annotations": [{"id": 99}]}
+    out = engine.prediction_to_gt(res, ds, 0.7)
+    assert [a["id"] for a in out["annotations"]] == [1, 2] and out["annotations"][1]["bbox"] == [0.0, 0.0, 1200.0, 600.0]
+    assert "score" not in out["annotations"][0] and ds["annotations"] == [{"id": 99}]          # input untouched
+    assert len(engine.prediction_to_gt([{"image_id": 1, "bbox": [0, 0, 1, 1], "category_id": 1, "score": 0.7}], ds)["annotations"]) == 1   # >= keeps 0.7
+    pp = engine.detector_postprocess(inst, 1024, 2048)                                       # Cityscapes 1024x2048 <- 600x1200
+    assert pp.image_size == (1024, 2048) and torch.allclose(pp.pred_boxes.tensor[0], torch.tensor([10.0, 20, 110, 220]) * (2048 / 1200))
+    assert len(pp) == 3
