@@ -102,15 +102,5 @@ __device__ __forceinline__ float4 sfod_clip_box(float4 b, float h, float w) {
 }
 __device__ __forceinline__ bool sfod_finite4(float4 b) { return isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w); }
 
-// torchvision nms IoU test, fp32 ops in torchvision's order; returns true iff j is suppressed by i.
-__device__ __forceinline__ bool sfod_iou_gt(float4 a, float area_a, float4 b, float area_b, double thr) {
-  float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
-  float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
-  float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
-  float inter = __fmul_rn(w, h);
-  float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-  float ovr = __fdiv_rn(inter, uni);
-  return (double)ovr > thr;
-}
 __device__ __forceinline__ float sfod_box_area(float4 b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
 #endif

@@ -25,11 +25,10 @@ struct Seg { int start; int len; };  // range in the sorted box array
 
 template <bool kClassAware>
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float4 *__restrict__ boxes, const int *__restrict__ cls,
-                                                      const Seg *__restrict__ segs, const int *__restrict__ seg_of_block_z,
+                                                      const Seg *__restrict__ segs,
                                                       int rows_per_slab, int wstride, double thr,
                                                       unsigned long long *__restrict__ mask) {
   const int s = blockIdx.z;
-  (void)seg_of_block_z;
   const Seg seg = segs[s];
   const int rt = blockIdx.y, ct = blockIdx.x;
   if (ct < rt) return;
@@ -445,8 +444,8 @@ static inline int launch_mask(const float4 *boxes, const int *cls, const Seg *se
   if (S <= 0 || max_len <= 0) return SFOD_OK;
   const int tiles = (max_len + 63) / 64;
   dim3 grid(tiles, tiles, S);
-  if (cls) nms_mask_kernel<true><<<grid, 64, 0, stream>>>(boxes, cls, segs, nullptr, rows_per_slab, wstride, thr, mask);
-  else nms_mask_kernel<false><<<grid, 64, 0, stream>>>(boxes, nullptr, segs, nullptr, rows_per_slab, wstride, thr, mask);
+  if (cls) nms_mask_kernel<true><<<grid, 64, 0, stream>>>(boxes, cls, segs, rows_per_slab, wstride, thr, mask);
+  else nms_mask_kernel<false><<<grid, 64, 0, stream>>>(boxes, nullptr, segs, rows_per_slab, wstride, thr, mask);
   SFOD_LAUNCH_CHECK();
   return SFOD_OK;
 }

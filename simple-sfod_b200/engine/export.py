@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Sequence
 
 import torch
 
-from ..structures import Boxes, Instances
+from ..structures import Instances
 
 
 def detector_postprocess(results: Instances, output_height: int, output_width: int) -> Instances:

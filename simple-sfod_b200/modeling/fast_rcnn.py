@@ -10,7 +10,7 @@ pseudo-label threshold (``threshold_bbox``, reference daod/engine/trainers/sourc
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple, Union
+from typing import Dict, List, Optional, Tuple
 
 import torch
 from torch import Tensor, nn

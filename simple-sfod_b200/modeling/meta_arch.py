@@ -16,7 +16,7 @@ import torch
 from torch import Tensor, nn
 
 from ..registry import META_ARCH_REGISTRY, build_backbone, build_proposal_generator, build_roi_heads
-from ..structures import ImageList, Instances
+from ..structures import ImageList
 
 
 class _GradientScalar(torch.autograd.Function):

@@ -10,7 +10,7 @@ kernels.  The box-head FCs stay on cuBLAS (dense GEMMs are library work per BASE
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch

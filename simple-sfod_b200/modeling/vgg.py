@@ -9,7 +9,6 @@ from __future__ import annotations
 
 from typing import Dict, List, Union, cast
 
-import torch
 from torch import Tensor, nn
 
 from ..registry import BACKBONE_REGISTRY

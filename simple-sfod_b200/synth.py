@@ -3,7 +3,7 @@ Pure torch-CPU generation (no oracle dependency); callers move tensors to the GP
 from __future__ import annotations
 
 import math
-from typing import List, Tuple
+from typing import Tuple
 
 import torch
 

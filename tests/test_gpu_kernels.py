@@ -2,14 +2,11 @@
 on the same seeded inputs.  Integer results (keep indices, top-k indices, classes, rows, counts) must be
 bit-exact; floating-point results match within the tolerance stated in each test (BASELINE.json: 1e-5
 relative fp32; where the CUDA arithmetic is *defined* identically to the oracle's we assert equality)."""
-import math
-
 import numpy as np
 import pytest
 import torch
 import torchvision
 
-from oracle import c_oracle as co
 from oracle import d2_cpu as o
 import sfod_b200  # noqa: F401
 from sfod_b200 import synth
