@@ -1,0 +1,93 @@
+"""Drop-in check at the plugin boundary: the REFERENCE's own plugin sources -- PseudoLabRPN / DARPN,
+SourceFreeAdaptiveTeacherStandardROIHeads (+ Eval, AdaptiveTeacher variants), SourceFreeFastRCNNOutputLayers, vgg_backbone --
+import unchanged against ``sfod_b200.d2shim`` (a ``detectron2`` namespace backed by this package) and build from the
+reference's config keys on top of the B200 base classes.  Reads /root/reference, so it runs only where the reference is
+mounted (the build container); it is skipped on the GPU box.  No reference source is copied into the repository."""
+import importlib
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+REF = "/root/reference/daod/modeling"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import sfod_b200  # noqa: F401
+    from sfod_b200 import d2shim
+    had = {k: v for k, v in sys.modules.items() if k.split(".")[0] == "detectron2"}
+    assert d2shim.install(force=True)
+    pkgs = {}
+    for name, sub in (("refdaod_pg", "proposal_generator"), ("refdaod_rh", "roi_heads"), ("refdaod_ma", "meta_arch")):
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REF, sub)]          # the package's real __init__ (which pulls unrelated baselines) is not executed
+        sys.modules[name] = m
+        pkgs[sub] = name
+    mods = {
+        "rpn": importlib.import_module("refdaod_pg.rpn"),
+        "fast": importlib.import_module("refdaod_rh.source_free_fast_rcnn"),
+        "heads": importlib.import_module("refdaod_rh.source_free_adaptive_teacher_roi_heads"),
+        "heads_eval": importlib.import_module("refdaod_rh.source_free_adaptive_teacher_roi_heads_eval"),
+        "heads_at": importlib.import_module("refdaod_rh.adaptive_teacher_roi_heads"),
+        "vgg": importlib.import_module("refdaod_ma.vgg"),
+    }
+    yield mods, sys.modules["detectron2"].registries
+    d2shim.uninstall()
+    for k in [k for k in sys.modules if k.startswith("refdaod_")]:
+        del sys.modules[k]
+    sys.modules.update(had)
+
+
+def test_reference_plugin_sources_import_and_register(ref):
+    mods, regs = ref
+    from sfod_b200 import modeling
+    for name in ("PseudoLabRPN", "DARPN"):
+        assert name in regs["PROPOSAL_GENERATOR"]
+    for name in ("SourceFreeAdaptiveTeacherStandardROIHeads", "SourceFreeAdaptiveTeacherEvalStandardROIHeads", "AdaptiveTeacherStandardROIHeads"):
+        assert name in regs["ROI_HEADS"]
+    for name in ("build_vgg_backbone", "build_vgg_fpn_backbone"):
+        assert name in regs["BACKBONE"]
+    # the reference classes are the reference's code (defined under /root/reference) on top of THIS package's bases
+    assert mods["rpn"].PseudoLabRPN.__module__ == "refdaod_pg.rpn" and issubclass(mods["rpn"].PseudoLabRPN, modeling.RPN)
+    assert issubclass(mods["fast"].SourceFreeFastRCNNOutputLayers, modeling.FastRCNNOutputLayers)
+    assert mods["heads"].__file__.startswith("/root/reference/")
+
+
+def test_reference_plugins_build_from_cfg_and_reach_the_kernel_boundary(ref):
+    mods, regs = ref
+    import detectron2.modeling as d2m                      # the shim
+    from sfod_b200 import config, modeling
+    from sfod_b200.structures import Boxes, ImageList, Instances
+    cfg = config.vgg_source_free_cfg(); cfg.MODEL.DEVICE = "cpu"
+    torch.manual_seed(0)
+    backbone = d2m.build_backbone(cfg)                     # reference vgg_backbone (nn.BatchNorm2d layers)
+    ours = modeling.vgg_backbone(cfg)
+    assert type(backbone).__module__ == "refdaod_ma.vgg"
+    assert list(backbone.state_dict().keys()) == list(ours.state_dict().keys())          # identical checkpoint layout
+    assert backbone.output_shape()["vgg4"].stride == 32 and backbone.output_shape()["vgg4"].channels == 512
+    rpn = d2m.build_proposal_generator(cfg, backbone.output_shape())
+    heads = d2m.build_roi_heads(cfg, backbone.output_shape())
+    assert type(rpn).__module__ == "refdaod_pg.rpn" and type(heads).__module__ == "refdaod_rh.source_free_adaptive_teacher_roi_heads"
+    assert type(heads.box_predictor).__module__ == "refdaod_rh.source_free_fast_rcnn"
+    assert isinstance(heads.box_pooler, modeling.ROIPooler) and heads.box_pooler.pooler_type == "ROIAlignV2"
+    assert rpn.pre_nms_topk == {True: 12000, False: 6000} and rpn.post_nms_topk == {True: 2000, False: 1000}
+    # the reference's forward runs its own Python and lands in libsfod_b200 at the operator boundary: on CPU tensors the
+    # library refuses (no CPU fallback) -- exactly at predict_proposals / the box pooler
+    feats = {"vgg4": torch.randn(1, 512, 6, 8)}
+    images = ImageList(torch.zeros(1, 3, 192, 256), [(192, 256)])
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        rpn(images, feats, None, compute_loss=False)
+    prop = Instances((192, 256)); prop.proposal_boxes = Boxes(torch.tensor([[4.0, 4, 100, 90]])); prop.objectness_logits = torch.zeros(1)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        heads(images, feats, [prop], targets=None, compute_loss=False, branch="unsup_data_weak")
+    # the reference's label_and_sample_proposals (its own override) runs on the shimmed helpers
+    tgt = Instances((192, 256)); tgt.gt_boxes = Boxes(torch.tensor([[0.0, 0, 110, 100]])); tgt.gt_classes = torch.tensor([3])
+    from sfod_b200.utils.events import EventStorage
+    with EventStorage() as st:
+        out = heads.label_and_sample_proposals([prop], [tgt], branch="supervised_target")
+    assert len(out[0]) == 2 and sorted(out[0].gt_classes.tolist()) == [3, 3]            # proposal + appended GT, both foreground
+    assert "roi_head/num_target_fg_samples_supervised_target" in st.latest()
