@@ -157,7 +157,9 @@ int sfod_rpn_select(const sfod_rpn_params *p, const float *logits, const float *
  * threshold_bbox(proposal_type="roih") of
  * daod/engine/trainers/source_free_adaptive_teacher.py:167-181.
  * cls_logits (R,K+1), deltas (R,4K) (or (R,4) when class_agnostic), proposals (R,4);
- * rows of image i are [row_offsets_dev[i], row_offsets_dev[i+1]) (int32, N+1 entries).
+ * rows of image i are [row_offsets_dev[i], row_offsets_dev[i+1]) (int32, N+1 entries); or, with rows_stride > 0 (packed
+ * layout, R == N * rows_stride), rows [i * rows_stride, i * rows_stride + row_offsets_dev[i]) where row_offsets_dev holds
+ * the N DEVICE-side row counts (e.g. out_count_dev of sfod_rpn_select) -- no host knowledge of the counts is needed.
  * mode 0: inference (score > score_thresh, per-class NMS, top-k);
  * Outputs per image, padded to topk: det_boxes (N,topk,4), det_scores (N,topk),
  * det_classes (N,topk) int64, det_rows (N,topk) int64 (row within the image),
@@ -176,6 +178,7 @@ typedef struct sfod_frcnn_params {
   int topk;
   float pseudo_thresh;
   int64_t coord_trick_max_n; /* 1000 reproduces torchvision-CPU's strategy switch */
+  int rows_stride;           /* 0: row_offsets_dev are prefix offsets; > 0: packed layout with device row counts */
 } sfod_frcnn_params;
 
 size_t sfod_frcnn_postprocess_workspace_bytes(const sfod_frcnn_params *p);

@@ -33,7 +33,7 @@ class FrcnnParams(C.Structure):
     _fields_ = [("N", C.c_int), ("R", C.c_int), ("K", C.c_int), ("class_agnostic", C.c_int),
                 ("max_rows_per_image", C.c_int), ("weights", C.c_float * 4), ("scale_clamp", C.c_float),
                 ("score_thresh", C.c_float), ("nms_thresh", C.c_double), ("topk", C.c_int), ("pseudo_thresh", C.c_float),
-                ("coord_trick_max_n", C.c_int64)]
+                ("coord_trick_max_n", C.c_int64), ("rows_stride", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/sfod_b200.h declares

@@ -187,6 +187,8 @@ SFOD_API int sfod_frcnn_postprocess(const sfod_frcnn_params *p, const float *cls
       !det_classes || !det_rows || !det_count_dev || !pseudo_count_dev)
     return SFOD_ERR_INVALID_ARG;
   if (p->N <= 0 || p->R < 0 || p->K <= 0 || p->max_rows_per_image <= 0 || p->topk <= 0) return SFOD_ERR_INVALID_ARG;
+  if (p->rows_stride < 0 || (p->rows_stride > 0 && (p->rows_stride > p->max_rows_per_image || (long long)p->rows_stride * p->N != p->R)))
+    return SFOD_ERR_INVALID_ARG;
   if (p->K > frk::kMaxK) return SFOD_ERR_UNSUPPORTED;
   if ((long long)p->max_rows_per_image * p->K >= (1ll << 24)) return SFOD_ERR_UNSUPPORTED;
   if (!sfod_aligned16(deltas) || !sfod_aligned16(proposals) || !sfod_aligned16(det_boxes) ||
@@ -203,7 +205,7 @@ SFOD_API int sfod_frcnn_postprocess(const sfod_frcnn_params *p, const float *cls
   if (p->R > 0) {
     frk::frcnn_decode_keys_kernel<<<(p->R + 127) / 128, 128, 0, st>>>(
         cls_logits, deltas, reinterpret_cast<const float4 *>(proposals), row_offsets_dev, image_hw_dev, N, p->R, K,
-        p->class_agnostic, pl.Rmax, pl.P, p->weights[0], p->weights[1], p->weights[2], p->weights[3], p->scale_clamp,
+        p->class_agnostic, p->rows_stride, pl.Rmax, pl.P, p->weights[0], p->weights[1], p->weights[2], p->weights[3], p->scale_clamp,
         p->score_thresh, b.cand_boxes, b.keys, b.maxc, probs_out, boxes_out);
     SFOD_LAUNCH_CHECK();
   }

@@ -27,13 +27,19 @@ __device__ __forceinline__ int image_of_row(const int *__restrict__ row_offsets,
 __global__ void __launch_bounds__(128) frcnn_decode_keys_kernel(
     const float *__restrict__ cls_logits, const float *__restrict__ deltas, const float4 *__restrict__ proposals,
     const int *__restrict__ row_offsets, const int *__restrict__ image_hw, int N, int R, int K, int class_agnostic,
-    int Rmax, int P, float wx, float wy, float ww, float wh, float scale_clamp, float score_thresh,
+    int rows_stride, int Rmax, int P, float wx, float wy, float ww, float wh, float scale_clamp, float score_thresh,
     float4 *__restrict__ cand_boxes, unsigned long long *__restrict__ keys, int *__restrict__ maxc_bits,
     float *__restrict__ probs_out, float *__restrict__ boxes_out) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= R) return;
-  const int img = image_of_row(row_offsets, N, g);
-  const int rl = g - row_offsets[img];
+  int img, rl;
+  if (rows_stride > 0) {   // packed layout: image i owns rows [i * stride, i * stride + count[i]); the rest is padding
+    img = g / rows_stride; rl = g - img * rows_stride;
+    if (img >= N || rl >= row_offsets[img]) return;
+  } else {
+    img = image_of_row(row_offsets, N, g);
+    rl = g - row_offsets[img];
+  }
   if (rl >= Rmax) return;  // caller bug guard; rows beyond the declared maximum are ignored
   const float img_h = (float)image_hw[2 * img], img_w = (float)image_hw[2 * img + 1];
   const int K1 = K + 1;

@@ -22,20 +22,41 @@ from .box_regression import Box2BoxTransform
 from .matcher import cross_entropy, dense_box_regression_loss, nonzero_tuple
 
 
+def packed_proposal_batch(proposals: List[Instances]):
+    """The padded RPN batch behind ``proposals`` if they are the untouched, complete, in-order lazy views of ONE batch."""
+    if not proposals or not all(hasattr(p, "packed_source") for p in proposals):
+        return None
+    srcs = [p.packed_source() for p in proposals]
+    if any(s is None for s in srcs) or any(s[0] is not srcs[0][0] for s in srcs):
+        return None
+    pb = srcs[0][0]
+    if [s[1] for s in srcs] != list(range(len(pb.image_sizes))):
+        return None
+    return pb
+
+
 class DetectionBatch:
     """Device-side result of the fused post-processing of one batch (padded to ``topk`` per image)."""
 
-    def __init__(self, out: Dict[str, Tensor], image_sizes, pseudo_thresh: float):
+    def __init__(self, out: Dict[str, Tensor], image_sizes, pseudo_thresh: float, proposal_batch=None):
         self.boxes, self.scores, self.classes, self.rows = out["boxes"], out["scores"], out["classes"], out["rows"]
         self.count, self.pseudo_count = out["count"], out["pseudo_count"]
         self.image_sizes = list(image_sizes)
         self.pseudo_thresh = pseudo_thresh
+        self.proposal_batch = proposal_batch          # padded RPN result these detections came from (packed path)
         self._host: Optional[List[List[int]]] = None
 
     def host_counts(self) -> List[List[int]]:
-        """[[detections per image], [pseudo-labels per image]] -- the one device->host read of the batch."""
+        """[[detections per image], [pseudo-labels per image]] -- the ONE device->host read of the batch; on the packed
+        path the same read also brings the RPN's proposal counts / non-finite counts."""
         if self._host is None:
-            self._host = torch.stack([self.count, self.pseudo_count]).cpu().tolist()
+            pb = self.proposal_batch
+            if pb is not None and pb._host is None:
+                h = torch.stack([self.count, self.pseudo_count, pb.count, pb.invalid]).cpu().tolist()
+                self._host = h[:2]
+                pb.set_host_counts(h[2], h[3])
+            else:
+                self._host = torch.stack([self.count, self.pseudo_count]).cpu().tolist()
         return self._host
 
     def instances(self) -> Tuple[List[Instances], List[Tensor]]:
@@ -197,14 +218,19 @@ class FastRCNNOutputLayers(nn.Module):
                         pseudo_thresh: Optional[float] = None) -> DetectionBatch:
         """The fused call; nothing is read back to the host until the caller asks for Instances."""
         scores, proposal_deltas = predictions
-        rows = [len(p) for p in proposals]
         image_sizes = [p.image_size for p in proposals]
-        proposal_boxes = torch.cat([p.proposal_boxes.tensor for p in proposals], dim=0)
         thr = self.pseudo_label_thresh if pseudo_thresh is None else pseudo_thresh
-        out = ops.frcnn_postprocess(scores, proposal_deltas, proposal_boxes, rows, image_sizes,
-                                    weights=self.box2box_transform.weights, scale_clamp=self.box2box_transform.scale_clamp,
-                                    score_thresh=self.test_score_thresh, nms_thresh=self.test_nms_thresh,
-                                    topk=self.test_topk_per_image, pseudo_thresh=thr)
+        kw = dict(weights=self.box2box_transform.weights, scale_clamp=self.box2box_transform.scale_clamp,
+                  score_thresh=self.test_score_thresh, nms_thresh=self.test_nms_thresh, topk=self.test_topk_per_image, pseudo_thresh=thr)
+        pb = packed_proposal_batch(proposals)
+        if pb is not None and scores.shape[0] == pb.boxes.shape[0] * pb.boxes.shape[1]:
+            # packed path: predictions were computed on the padded (N * P) rows; valid rows come from the device-side counts
+            out = ops.frcnn_postprocess(scores, proposal_deltas, pb.boxes.reshape(-1, 4), pb.count, image_sizes,
+                                        rows_stride=pb.boxes.shape[1], **kw)
+            return DetectionBatch(out, image_sizes, thr, proposal_batch=pb)
+        rows = [len(p) for p in proposals]
+        proposal_boxes = torch.cat([p.proposal_boxes.tensor for p in proposals], dim=0)
+        out = ops.frcnn_postprocess(scores, proposal_deltas, proposal_boxes, rows, image_sizes, **kw)
         return DetectionBatch(out, image_sizes, thr)
 
     def inference(self, predictions: Tuple[Tensor, Tensor], proposals: List[Instances]):

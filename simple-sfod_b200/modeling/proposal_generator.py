@@ -15,7 +15,7 @@ from torch import Tensor, nn
 
 from .. import ops
 from ..registry import PROPOSAL_GENERATOR_REGISTRY, RPN_HEAD_REGISTRY
-from ..structures import Boxes, ImageList, Instances, ShapeSpec, pairwise_iou
+from ..structures import Boxes, ImageList, Instances, LazyInstances, ShapeSpec, pairwise_iou
 from ..utils.events import get_event_storage
 from .anchor_generator import DefaultAnchorGenerator
 from .box_regression import Box2BoxTransform
@@ -54,6 +54,43 @@ class StandardRPNHead(nn.Module):
             pred_objectness_logits.append(self.objectness_logits(t))
             pred_anchor_deltas.append(self.anchor_deltas(t))
         return pred_objectness_logits, pred_anchor_deltas
+
+
+class ProposalBatch:
+    """Padded device-side result of one ``rpn_select`` call: boxes (N, P, 4), logits (N, P), count / invalid (N) int32.
+    The host copy of the counts is fetched at most once, and only if somebody needs per-image lengths."""
+
+    def __init__(self, boxes: Tensor, logits: Tensor, count: Tensor, invalid: Tensor, image_sizes, training: bool):
+        self.boxes, self.logits, self.count, self.invalid = boxes, logits, count, invalid
+        self.image_sizes = list(image_sizes)
+        self.training = training
+        self._host = None
+
+    def set_host_counts(self, counts: List[int], invalid: List[int]) -> None:
+        """Lets a later read of the same batch (the detections' count read) deliver these values for free."""
+        if self._host is None:
+            self._host = (list(counts), list(invalid))
+            self._check()
+
+    def _check(self) -> None:
+        if self.training and any(v > 0 for v in self._host[1]):   # detectron2 raises here, in training, before NMS
+            raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+
+    def host_counts(self) -> List[int]:
+        if self._host is None:
+            h = torch.stack([self.count, self.invalid]).cpu().tolist()   # the one device->host read
+            self._host = (h[0], h[1])
+            self._check()
+        return self._host[0]
+
+    def instances(self) -> List[Instances]:
+        def make(i):
+            def materialize(inst):
+                k = self.host_counts()[i]
+                inst.proposal_boxes = Boxes(self.boxes[i, :k])
+                inst.objectness_logits = self.logits[i, :k]
+            return LazyInstances(self.image_sizes[i], materialize, source=self, index=i)
+        return [make(i) for i in range(len(self.image_sizes))]
 
 
 class RPN(nn.Module):
@@ -184,17 +221,9 @@ class RPN(nn.Module):
                           image_sizes: List[Tuple[int, int]], feat_hw: Optional[List[Tuple[int, int]]] = None) -> List[Instances]:
         """d2 RPN.predict_proposals: List[Instances{proposal_boxes, objectness_logits}], score-descending."""
         boxes, logits, _, count, invalid = self.select_proposals(pred_objectness_logits, pred_anchor_deltas, image_sizes, feat_hw, anchors)
-        host = torch.stack([count, invalid]).cpu().tolist()  # the one device->host read of the batch
-        if self.training and any(v > 0 for v in host[1]):
-            raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
-        results = []
-        for i, image_size in enumerate(image_sizes):
-            k = host[0][i]
-            res = Instances(image_size)
-            res.proposal_boxes = Boxes(boxes[i, :k])
-            res.objectness_logits = logits[i, :k]
-            results.append(res)
-        return results
+        # No host read here: the Instances are cut out of the padded batch lazily (ROI heads of this package consume the
+        # padded batch directly; the counts arrive with the detections' single device->host read).
+        return ProposalBatch(boxes, logits, count, invalid, image_sizes, self.training).instances()
 
     def forward(self, images: ImageList, features: Dict[str, Tensor], gt_instances: Optional[List[Instances]] = None):
         feats = [features[f] for f in self.in_features]

@@ -19,7 +19,7 @@ from torch import Tensor, nn
 from ..registry import ROI_BOX_HEAD_REGISTRY, ROI_HEADS_REGISTRY
 from ..structures import Boxes, ImageList, Instances, ShapeSpec, pairwise_iou
 from ..utils.events import get_event_storage
-from .fast_rcnn import FastRCNNOutputLayers, SourceFreeFastRCNNOutputLayers
+from .fast_rcnn import FastRCNNOutputLayers, SourceFreeFastRCNNOutputLayers, packed_proposal_batch
 from .matcher import Matcher, add_ground_truth_to_proposals, subsample_labels
 from .poolers import ROIPooler
 
@@ -187,6 +187,16 @@ class _StandardROIHeadsBase(nn.Module):
 
     def _box_predictions(self, features: Dict[str, Tensor], proposals: List[Instances]):
         feats = [features[f] for f in self.box_in_features]
+        pb = packed_proposal_batch(proposals) if (not torch.is_grad_enabled() and len(feats) == 1) else None
+        if pb is not None:
+            # Sync-free inference path: pool the padded (N, P) proposal batch as it left the RPN kernel (rows beyond an
+            # image's count are zero boxes whose outputs are ignored downstream through the device-side counts).
+            N, P = pb.boxes.shape[:2]
+            idx = torch.arange(N, device=pb.boxes.device, dtype=pb.boxes.dtype).repeat_interleave(P).unsqueeze(1)
+            rois = torch.cat([idx, pb.boxes.reshape(N * P, 4)], dim=1)
+            box_features = self.box_pooler._pool_level(feats[0], rois, self.box_pooler.scales[0])
+            box_features = self.box_head(box_features)
+            return box_features, self.box_predictor(box_features)
         box_features = self.box_pooler(feats, [x.proposal_boxes for x in proposals])  # reference ...roi_heads.py:117
         box_features = self.box_head(box_features)
         return box_features, self.box_predictor(box_features)

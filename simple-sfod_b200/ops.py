@@ -421,12 +421,14 @@ def rpn_select(logits: Tensor, deltas: Tensor, image_sizes: Sequence[Tuple[int, 
 
 
 # ----------------------------------------------------------------------------------------------- Fast R-CNN post-process
-def frcnn_postprocess(cls_logits: Tensor, deltas: Tensor, proposals: Tensor, rows_per_image: Sequence[int],
-                      image_sizes: Sequence[Tuple[int, int]], *, weights: Sequence[float] = (10.0, 10.0, 5.0, 5.0),
-                      scale_clamp: float = SCALE_CLAMP, score_thresh: float = 0.05, nms_thresh: float = 0.5, topk: int = 100,
-                      pseudo_thresh: float = 0.8, want_probs: bool = False, want_boxes: bool = False):
+def frcnn_postprocess(cls_logits: Tensor, deltas: Tensor, proposals: Tensor, rows_per_image, image_sizes: Sequence[Tuple[int, int]], *,
+                      weights: Sequence[float] = (10.0, 10.0, 5.0, 5.0), scale_clamp: float = SCALE_CLAMP, score_thresh: float = 0.05,
+                      nms_thresh: float = 0.5, topk: int = 100, pseudo_thresh: float = 0.8, want_probs: bool = False,
+                      want_boxes: bool = False, rows_stride: int = 0):
     """FastRCNNOutputLayers.inference + threshold_bbox("roih") for all images in one call.
-    cls_logits (R, K+1), deltas (R, 4K) or (R, 4), proposals (R, 4) concatenated over images."""
+    cls_logits (R, K+1), deltas (R, 4K) or (R, 4), proposals (R, 4) concatenated over images.
+    ``rows_per_image``: a list of ints (rows of image i follow those of image i-1), or -- packed layout, ``rows_stride > 0`` --
+    an int32 DEVICE tensor of N row counts, image i owning rows [i*rows_stride, i*rows_stride + count[i]) (no host sync)."""
     dev = _require_cuda(cls_logits, deltas, proposals)
     cl, dl, pr = _f32c(cls_logits), _f32c(deltas), _f32c(proposals)
     R, K1 = cl.shape
@@ -435,15 +437,22 @@ def frcnn_postprocess(cls_logits: Tensor, deltas: Tensor, proposals: Tensor, row
         raise ValueError("cls_logits must have K+1 >= 2 columns")
     if dl.shape[0] != R or dl.shape[1] not in (4, 4 * K) or pr.shape != (R, 4):
         raise ValueError("deltas / proposals shapes do not match cls_logits")
-    if sum(rows_per_image) != R or len(rows_per_image) != len(image_sizes):
+    packed = rows_stride > 0
+    if packed:
+        if not isinstance(rows_per_image, Tensor) or rows_per_image.dtype != torch.int32 or not rows_per_image.is_cuda:
+            raise ValueError("packed layout needs an int32 CUDA tensor of per-image row counts")
+        if rows_per_image.numel() != len(image_sizes) or rows_stride * len(image_sizes) != R:
+            raise ValueError("packed layout: R must equal N * rows_stride and counts must have N entries")
+    elif sum(rows_per_image) != R or len(rows_per_image) != len(image_sizes):
         raise ValueError("rows_per_image must sum to R and match image_sizes")
     if topk < 0:
         raise ValueError("topk_per_image < 0 (return all) is not supported by the fused path")
-    N = len(rows_per_image)
+    N = len(image_sizes)
     p = FrcnnParams()
     p.N, p.R, p.K = N, R, K
     p.class_agnostic = int(dl.shape[1] == 4 and K != 1)
-    p.max_rows_per_image = max(1, max(rows_per_image)) if N else 1
+    p.rows_stride = int(rows_stride) if packed else 0
+    p.max_rows_per_image = int(rows_stride) if packed else (max(1, max(rows_per_image)) if N else 1)
     for i in range(4):
         p.weights[i] = float(weights[i])
     p.scale_clamp, p.score_thresh, p.nms_thresh = float(scale_clamp), float(score_thresh), float(nms_thresh)
@@ -451,10 +460,13 @@ def frcnn_postprocess(cls_logits: Tensor, deltas: Tensor, proposals: Tensor, row
     T = int(topk)
     L = _lib.lib()
     with torch.cuda.device(dev):
-        offs = [0]
-        for r in rows_per_image:
-            offs.append(offs[-1] + int(r))
-        row_off = _small_i32(dev, offs)
+        if packed:
+            row_off = rows_per_image.contiguous()
+        else:
+            offs = [0]
+            for r in rows_per_image:
+                offs.append(offs[-1] + int(r))
+            row_off = _small_i32(dev, offs)
         hw = _small_i32(dev, [v for s in image_sizes for v in (int(s[0]), int(s[1]))])
         det_boxes = torch.empty((N, T, 4), dtype=torch.float32, device=dev)
         det_scores = torch.empty((N, T), dtype=torch.float32, device=dev)

@@ -205,6 +205,38 @@ class Instances:
     __repr__ = __str__
 
 
+class LazyInstances(Instances):
+    """An ``Instances`` whose fields are cut out of a padded device batch only when somebody looks at them.
+
+    The fused kernels return padded (N, P, ...) tensors plus device-side counts; slicing ``[:count]`` needs the count on the
+    host.  Producers hand out ``LazyInstances(image_size, materialize)``: any access to a field, ``len()`` or indexing
+    calls ``materialize(self)`` once (ONE device->host read shared by the whole batch), after which the object behaves
+    exactly like ``Instances``.  Consumers that understand the padded batch (``roi_heads`` of this package) use
+    ``packed_source()`` instead and never trigger the read."""
+
+    def __init__(self, image_size: Tuple[int, int], materialize, source=None, index: int = 0):
+        object.__setattr__(self, "_image_size", image_size)
+        object.__setattr__(self, "_fields_store", {})
+        object.__setattr__(self, "_materialize_fn", materialize)
+        object.__setattr__(self, "_source", source)
+        object.__setattr__(self, "_index", index)
+
+    @property
+    def _fields(self) -> Dict[str, Any]:
+        fn = object.__getattribute__(self, "_materialize_fn")
+        if fn is not None:
+            object.__setattr__(self, "_materialize_fn", None)
+            fn(self)
+        return object.__getattribute__(self, "_fields_store")
+
+    def is_materialized(self) -> bool:
+        return object.__getattribute__(self, "_materialize_fn") is None
+
+    def packed_source(self):
+        """(batch object, image index) while the fields have not been touched, else None."""
+        return None if self.is_materialized() else (object.__getattribute__(self, "_source"), object.__getattribute__(self, "_index"))
+
+
 class ImageList:
     """detectron2.structures.ImageList: a padded batch plus the true (h, w) of every image."""
 

@@ -349,3 +349,31 @@ def test_adaptive_per_class_threshold_matches_oracle(cuda_device):
     for s_ in range(4):
         ref = (v[s_, :counts[s_]] >= thr[c[s_, :counts[s_]]]).nonzero().flatten()
         assert cnt[s_].item() == ref.numel() and torch.equal(idx[s_, :ref.numel()].cpu(), ref)
+
+
+def test_teacher_step_has_one_host_sync_per_batch(teacher, cuda_device):
+    """SURVEY.md section 7 'hard parts': detectron2's List[Instances] API without per-image syncs.  The RPN hands its padded
+    batch to the ROI heads lazily (device-side counts), so a whole pseudo-labelling step performs ONE synchronising
+    device->host read: the detections' / proposals' counts."""
+    import warnings
+    img = torch.randint(0, 256, (2, 3, 320, 480), dtype=torch.uint8, generator=torch.Generator().manual_seed(8)).to(cuda_device)
+    def step():
+        with torch.no_grad():
+            _, p_rpn, p_roih = teacher(img, branch="unsup_data_weak")
+        pl, _ = engine.process_pseudo_label(p_roih, 0.8, "roih", "thresholding")
+        return p_rpn, p_roih, pl
+    step()                                            # warm-up: workspaces, small constant tensors, cuDNN algorithm choice
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("warn")
+    try:
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            p_rpn, p_roih, pl = step()
+        syncs = [x for x in w if "synchroniz" in str(x.message).lower()]
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert len(syncs) == 1, [str(x.message)[:120] for x in syncs]
+    assert not p_rpn[0].is_materialized()             # nobody looked at the proposals: they never left the device
+    n = [len(p) for p in p_rpn]                       # looking now costs no further read (counts came with the detections)
+    assert p_rpn[0].is_materialized() and all(0 < k <= 2000 for k in n)
+    assert [len(p) for p in p_roih] == p_roih[0]._sfod_batch.host_counts()[0]
