@@ -177,15 +177,19 @@ struct SepSmem {
   float *tile;   // kTileFloats
   float *Ad;     // H * 8: Ad[y*8 + ph] = sum of y-weights of bin ph on row y, divided by grid_h
   float *Bd;     // W * 8
-  int *lim;      // [0..3] ymin, ymax, xmin, xmax; [4..10] first row of bin ph; [11..17] last row of bin ph
+  int *lim;      // [0..3] ymin, ymax, xmin, xmax; [4..10] first row of bin ph; [11..17] last row of bin ph;
+                 // [18..24] first column of the compact window of bin pw; [25] widest bin window in columns (0 = none)
+  float *Bc;     // kPW * kNXMax: Bc[pw*kNXMax + j] = Bd[(lim[18+pw] + j)*8 + pw], the nonzero run of column weights of bin pw
 };
+constexpr int kNXMax = 4;                  // widest per-bin column window handled by the compact (sparse-in-x) forward
 __host__ __device__ inline size_t sep_smem_bytes(int H, int W) {
-  return (size_t)kTileFloats * 4 + (size_t)(H + W) * 8 * 4 + 32 * 4;
+  return (size_t)kTileFloats * 4 + (size_t)(H + W) * 8 * 4 + 32 * 4 + 32 * 4;
 }
 __device__ __forceinline__ SepSmem sep_carve(float *base, int H, int W) {
   SepSmem s;
   s.tile = base; s.Ad = base + kTileFloats; s.Bd = s.Ad + H * 8;
   s.lim = reinterpret_cast<int *>(s.Bd + W * 8);
+  s.Bc = reinterpret_cast<float *>(s.lim + 32);
   return s;
 }
 
@@ -193,7 +197,7 @@ __device__ __forceinline__ SepSmem sep_carve(float *base, int H, int W) {
 __device__ __forceinline__ void sep_build_tables(const SepSmem &s, const RoiGeom &g, int H, int W) {
   const int tid = threadIdx.x;
   for (int i = tid; i < (H + W) * 8; i += blockDim.x) s.Ad[i] = 0.f;  // Ad and Bd are contiguous
-  if (tid == 0) { s.lim[0] = H; s.lim[1] = -1; s.lim[2] = W; s.lim[3] = -1; }
+  if (tid == 0) { s.lim[0] = H; s.lim[1] = -1; s.lim[2] = W; s.lim[3] = -1; s.lim[25] = 0; }
   __syncthreads();
   if (tid < kPH) {
     const int ph = tid; int mn = H, mx = -1;
@@ -216,6 +220,13 @@ __device__ __forceinline__ void sep_build_tables(const SepSmem &s, const RoiGeom
       mn = min(mn, lo); mx = max(mx, hi);
     }
     if (mx >= 0) { atomicMin(&s.lim[2], mn); atomicMax(&s.lim[3], mx); }
+    // compact window of this bin: columns [x0, x0 + kNXMax) inside the row, covering [mn, mx] whenever it is narrow enough
+    // (only this thread touched column pw of Bd, so the dense entries can be read back without a barrier)
+    const int x0 = mx >= 0 ? max(0, min(mn, W - kNXMax)) : 0;
+    s.lim[18 + pw] = x0;
+#pragma unroll
+    for (int j = 0; j < kNXMax; ++j) s.Bc[pw * kNXMax + j] = (mx >= 0 && x0 + j < W) ? s.Bd[(x0 + j) * 8 + pw] : 0.f;
+    if (mx >= 0) atomicMax(&s.lim[25], W >= kNXMax ? mx - x0 + 1 : kNXMax + 1);
   }
   __syncthreads();
 }
@@ -290,6 +301,63 @@ __device__ __forceinline__ void sep_fwd_pass(const SepSmem &s, const float2 *__r
     }
 }
 
+// The same pass with the column weights in compact form.  With the adaptive sampling grid every bin touches at most
+// grid_w + 1 consecutive columns, so instead of 7 (mostly zero) weights per pixel of the ROI's bounding box a row costs
+// 7 * NX pixel loads with ONE register-resident weight each: no weight traffic on the shared-memory crossbar and
+// NX / (7 ns) of the FMAs.  Summation order per bin (ascending x) is that of the dense pass; the skipped terms are exact
+// zeros.  NX = widest bin window of this ROI rounded up to a template instance; narrower bins carry zero weights.
+template <int PH0, int NPH, int kC, int NX>
+__device__ __forceinline__ void sep_fwd_pass_compact(const SepSmem &s, const float2 *__restrict__ fbase2, int C, int W,
+                                                     float *__restrict__ t0, float *__restrict__ t1, int half) {
+  const int cs2 = (kC ? kC : C) >> 1;
+  int y0 = s.lim[4 + PH0], y1 = s.lim[11 + PH0];
+#pragma unroll
+  for (int a = 1; a < NPH; ++a) { y0 = min(y0, s.lim[4 + PH0 + a]); y1 = max(y1, s.lim[11 + PH0 + a]); }
+  float bw[kPW][NX];
+  int xo[kPW];
+#pragma unroll
+  for (int b = 0; b < kPW; ++b) {
+    xo[b] = s.lim[18 + b] * cs2;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) bw[b][j] = s.Bc[b * kNXMax + j];
+  }
+  float2 acc[NPH][kPW];
+#pragma unroll
+  for (int a = 0; a < NPH; ++a)
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) acc[a][b] = make_float2(0.f, 0.f);
+  for (int y = y0; y <= y1; ++y) {
+    const float2 *prow = fbase2 + (size_t)y * W * cs2;
+    float2 T[kPW];
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) {
+      float2 f[NX];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) f[j] = __ldg(prow + xo[b] + j * cs2);
+      T[b] = make_float2(bw[b][0] * f[0].x, bw[b][0] * f[0].y);
+#pragma unroll
+      for (int j = 1; j < NX; ++j) { T[b].x = fmaf(bw[b][j], f[j].x, T[b].x); T[b].y = fmaf(bw[b][j], f[j].y, T[b].y); }
+    }
+    const float4 av4 = *reinterpret_cast<const float4 *>(s.Ad + y * 8 + PH0);
+    const float av[4] = {av4.x, av4.y, av4.z, av4.w};
+#pragma unroll
+    for (int a = 0; a < NPH; ++a) {
+      if (av[a] != 0.f) {
+#pragma unroll
+        for (int b = 0; b < kPW; ++b) { acc[a][b].x = fmaf(av[a], T[b].x, acc[a][b].x); acc[a][b].y = fmaf(av[a], T[b].y, acc[a][b].y); }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NPH; ++a)
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) {
+      const float v0 = acc[a][b].x, v1 = acc[a][b].y;
+      t0[(PH0 + a) * kPW + b] = half ? v1 : v0;
+      t1[(PH0 + a) * kPW + b] = half ? v0 : v1;
+    }
+}
+
 template <int kC>
 __global__ void __launch_bounds__(kSepThreads, 4) roi_align_fwd_sep_kernel(const float *__restrict__ feat /* NHWC */,
                                                                            const float *__restrict__ rois, int N, int C, int H,
@@ -311,8 +379,20 @@ __global__ void __launch_bounds__(kSepThreads, 4) roi_align_fwd_sep_kernel(const
     float *t1 = s.tile + (size_t)(2 * tid + 1 - half) * kBins;
     if (ymax >= ymin && xmax >= xmin) {
       const float2 *fbase2 = reinterpret_cast<const float2 *>(feat + (size_t)g.n * H * W * C + c0);
-      sep_fwd_pass<0, 4, kC>(s, fbase2, C, W, xmin, xmax, t0, t1, half);
-      sep_fwd_pass<4, 3, kC>(s, fbase2, C, W, xmin, xmax, t0, t1, half);
+      const int nx = s.lim[25];   // CTA-uniform
+      if (nx <= 2) {
+        sep_fwd_pass_compact<0, 4, kC, 2>(s, fbase2, C, W, t0, t1, half);
+        sep_fwd_pass_compact<4, 3, kC, 2>(s, fbase2, C, W, t0, t1, half);
+      } else if (nx == 3) {
+        sep_fwd_pass_compact<0, 4, kC, 3>(s, fbase2, C, W, t0, t1, half);
+        sep_fwd_pass_compact<4, 3, kC, 3>(s, fbase2, C, W, t0, t1, half);
+      } else if (nx == 4) {
+        sep_fwd_pass_compact<0, 4, kC, 4>(s, fbase2, C, W, t0, t1, half);
+        sep_fwd_pass_compact<4, 3, kC, 4>(s, fbase2, C, W, t0, t1, half);
+      } else {   // wide bins (fixed sampling_ratio with bins wider than a pixel, or maps narrower than the window): dense tables
+        sep_fwd_pass<0, 4, kC>(s, fbase2, C, W, xmin, xmax, t0, t1, half);
+        sep_fwd_pass<4, 3, kC>(s, fbase2, C, W, xmin, xmax, t0, t1, half);
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < kBins; ++k) { t0[k] = 0.f; t1[k] = 0.f; }
