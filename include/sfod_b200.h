@@ -80,8 +80,9 @@ int sfod_ema_multi_tensor(const void *device_plan, int64_t n_chunks, double keep
  * input (N,C,H,W) fp32 in `layout`; rois (R,5) = [batch_index, x1, y1, x2, y2];
  * output (R,C,PH,PW) contiguous (torchvision layout).  `exact` != 0 selects the kernel that
  * reproduces torchvision's per-sample summation order bit for bit (NCHW gather); exact == 0
- * selects the separable channels-last kernel (<= 1e-5 relative). */
-size_t sfod_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int layout, int exact);
+ * selects the separable channels-last kernel (<= 1e-5 relative), whose
+ * workspace also holds one table record per ROI (hence R in the query). */
+size_t sfod_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int R, int layout, int exact);
 int sfod_roi_align_fwd(const float *input, int layout, const float *rois, int N, int C, int H, int W, int R, int PH,
                        int PW, float spatial_scale, int sampling_ratio, int aligned, int exact, float *output,
                        void *workspace, size_t workspace_bytes, sfod_stream_t stream);

@@ -45,7 +45,7 @@ SIGNATURES = {
     "sfod_ema_plan_bytes": (C.c_size_t, [C.c_int64]),
     "sfod_ema_plan_build": (C.c_int, [C.POINTER(EmaTensor), C.c_int, c_ptr, C.c_size_t]),
     "sfod_ema_multi_tensor": (C.c_int, [c_ptr, C.c_int64, C.c_double, c_ptr]),
-    "sfod_roi_align_fwd_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
+    "sfod_roi_align_fwd_workspace_bytes": (C.c_size_t, [C.c_int] * 7),
     "sfod_roi_align_fwd": (C.c_int, [c_ptr, C.c_int, c_ptr] + [C.c_int] * 7 + [C.c_float, C.c_int, C.c_int, C.c_int, c_ptr,
                                      c_ptr, C.c_size_t, c_ptr]),
     "sfod_roi_align_bwd_workspace_bytes": (C.c_size_t, [C.c_int] * 5),

@@ -156,40 +156,38 @@ __global__ void __launch_bounds__(256) roi_align_bwd_generic_kernel(const float 
 
 // --------------------------------------------------------------------------- separable fast path (7x7, NHWC)
 // Bilinear sampling + bin averaging is separable: out = A . F . B^T per channel, A (7 x H) and B (7 x W) built once per
-// ROI in shared memory.  The kernel is bound by instruction issue and L2 latency, not by DRAM (the feature map is
-// L2-resident and the 100 KB/ROI output is the only HBM traffic), so it is organised to minimise instructions per pixel:
-//   * one CTA = one ROI x 256 consecutive channels, 2 channels per thread (one LDG.64 per pixel, a warp reads 256
-//     contiguous bytes); the weight tables are warp-uniform shared-memory broadcasts (2 LDS.128 per pixel);
-//   * the channel stride is a template constant for the common C, so the <= 8 pixel loads of a batch are LDG.64 with
-//     immediate offsets from one base pointer (no per-load address arithmetic), issued before any FMA consumes them,
-//     and partial batches execute exactly their valid pixels (warp-uniform branches, no padded work);
+// ROI.  The kernels are bound by instruction issue and L2 latency, not by DRAM (the feature map is L2-resident and the
+// 100 KB/ROI output is the only HBM traffic), so they are organised to minimise instructions and exposed latency:
+//   * one work item = one ROI x 256 consecutive channels on a 128-thread CTA, 2 channels per thread (one LDG.64 per
+//     pixel, a warp reads 256 contiguous bytes);
+//   * forward: B is used in COMPACT form (each bin touches <= grid_w + 1 consecutive columns), its weights live in
+//     registers, and the channel stride is a template constant so the 7 * NX pixel loads of a row are LDG.64 with
+//     immediate offsets; backward and the wide-bin fallback use dense warp-uniform tables (2 LDS.128 per pixel);
 //   * the 7 bin rows are produced in two passes (bins 0-3, then 4-6), which halves the accumulator registers
 //     (28 pairs instead of 49) and lifts occupancy to 4 CTAs/SM; only rows shared by bins 3 and 4 are visited twice;
 //   * the (256 x 49) output tile is staged in shared memory with a conflict-free lane permutation and leaves the SM
-//     as ONE 50 176 B cp.async.bulk (TMA) store.
+//     as ONE 50 176 B cp.async.bulk (TMA) store that drains while the next item is computed (persistent CTAs).
 constexpr int kPH = 7, kPW = 7, kBins = kPH * kPW;
 constexpr int kSepThreads = 128;           // 2 channels per thread
 constexpr int kCT = 2 * kSepThreads;       // 256 channels per CTA
 constexpr int kTileFloats = kCT * kBins;   // 12 544 floats = 50 176 B
-constexpr int kXB = 8;                     // pixels per load batch
 
 struct SepSmem {
   float *tile;   // kTileFloats
   float *Ad;     // H * 8: Ad[y*8 + ph] = sum of y-weights of bin ph on row y, divided by grid_h
   float *Bd;     // W * 8
-  int *lim;      // [0..3] ymin, ymax, xmin, xmax; [4..10] first row of bin ph; [11..17] last row of bin ph;
-                 // [18..24] first column of the compact window of bin pw; [25] widest bin window in columns (0 = none)
-  float *Bc;     // kPW * kNXMax: Bc[pw*kNXMax + j] = Bd[(lim[18+pw] + j)*8 + pw], the nonzero run of column weights of bin pw
+  int *lim;      // [0..3] ymin, ymax, xmin, xmax; [4..10] first row of bin ph; [11..17] last row of bin ph
+                 // (the forward's table records add [18..26], see roi_sep_tables_kernel)
+  float *Bc;     // forward only: compact column weights (see roi_sep_tables_kernel)
 };
-constexpr int kNXMax = 4;                  // widest per-bin column window handled by the compact (sparse-in-x) forward
 __host__ __device__ inline size_t sep_smem_bytes(int H, int W) {
-  return (size_t)kTileFloats * 4 + (size_t)(H + W) * 8 * 4 + 32 * 4 + 32 * 4;
+  return (size_t)kTileFloats * 4 + (size_t)(H + W) * 8 * 4 + 32 * 4;
 }
 __device__ __forceinline__ SepSmem sep_carve(float *base, int H, int W) {
   SepSmem s;
   s.tile = base; s.Ad = base + kTileFloats; s.Bd = s.Ad + H * 8;
   s.lim = reinterpret_cast<int *>(s.Bd + W * 8);
-  s.Bc = reinterpret_cast<float *>(s.lim + 32);
+  s.Bc = nullptr;
   return s;
 }
 
@@ -197,7 +195,7 @@ __device__ __forceinline__ SepSmem sep_carve(float *base, int H, int W) {
 __device__ __forceinline__ void sep_build_tables(const SepSmem &s, const RoiGeom &g, int H, int W) {
   const int tid = threadIdx.x;
   for (int i = tid; i < (H + W) * 8; i += blockDim.x) s.Ad[i] = 0.f;  // Ad and Bd are contiguous
-  if (tid == 0) { s.lim[0] = H; s.lim[1] = -1; s.lim[2] = W; s.lim[3] = -1; s.lim[25] = 0; }
+  if (tid == 0) { s.lim[0] = H; s.lim[1] = -1; s.lim[2] = W; s.lim[3] = -1; }
   __syncthreads();
   if (tid < kPH) {
     const int ph = tid; int mn = H, mx = -1;
@@ -220,13 +218,6 @@ __device__ __forceinline__ void sep_build_tables(const SepSmem &s, const RoiGeom
       mn = min(mn, lo); mx = max(mx, hi);
     }
     if (mx >= 0) { atomicMin(&s.lim[2], mn); atomicMax(&s.lim[3], mx); }
-    // compact window of this bin: columns [x0, x0 + kNXMax) inside the row, covering [mn, mx] whenever it is narrow enough
-    // (only this thread touched column pw of Bd, so the dense entries can be read back without a barrier)
-    const int x0 = mx >= 0 ? max(0, min(mn, W - kNXMax)) : 0;
-    s.lim[18 + pw] = x0;
-#pragma unroll
-    for (int j = 0; j < kNXMax; ++j) s.Bc[pw * kNXMax + j] = (mx >= 0 && x0 + j < W) ? s.Bd[(x0 + j) * 8 + pw] : 0.f;
-    if (mx >= 0) atomicMax(&s.lim[25], W >= kNXMax ? mx - x0 + 1 : kNXMax + 1);
   }
   __syncthreads();
 }
@@ -243,11 +234,127 @@ __device__ __forceinline__ void sep_row_fma(float2 (&T)[kPW], const float *__res
   T[6].x = fmaf(w1.z, f.x, T[6].x); T[6].y = fmaf(w1.z, f.y, T[6].y);
 }
 
-// One pass over the rows feeding bins [PH0, PH0 + NPH): accumulates and writes those bin rows of the output tile.
-// fbase2: float2 pointer to (image, pixel 0, this thread's channel pair); cs2: channel stride in float2 units.
+// ---- per-ROI table records (forward).  A small pre-kernel builds, for every ROI, the record the forward kernel needs:
+//   ints  [0..31]  lim: [0..1] ymin, ymax; [2..3] xmin, xmax; [4..10] / [11..17] first / last row of bin ph;
+//                       [18..24] first column of the compact window of bin pw; [25] widest bin window in columns
+//                       (kNXMax + 1 = use the dense column tables); [26] image index (-1: invalid -> zero output)
+//   floats [32..59] Bc[pw*kNXMax + j]: weight of column lim[18+pw] + j for bin pw (the nonzero run of B's row pw)
+//   floats [64..64+8H) Ad[y*8 + ph], ph < 7; word y*8 + 7 holds (first bin fed by row y) | (number of such bins << 8)
+// so that the persistent forward CTAs prefetch it with cp.async while they work on the previous ROI instead of spending
+// ~20 % of their life in a latency-bound prologue (ROI load from DRAM, table build by 14 threads, two barriers).
+constexpr int kNXMax = 4;                  // widest per-bin column window handled by the compact (sparse-in-x) forward
+constexpr int kRecHead = 64;
+__host__ __device__ inline int sep_rec_floats(int H) { return kRecHead + 8 * H; }
+
+__global__ void __launch_bounds__(128) roi_sep_tables_kernel(const float *__restrict__ rois, int R, int N, int H, int W, float scale,
+                                                             int sampling_ratio, int aligned, float *__restrict__ recs,
+                                                             unsigned *__restrict__ counter) {
+  extern __shared__ __align__(16) float tb_smem[];
+  const int rec = sep_rec_floats(H);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + warp;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;   // work counter of the forward kernel that follows in stream order
+  if (r >= R) return;
+  float *my = tb_smem + (size_t)warp * rec;
+  int *lim = reinterpret_cast<int *>(my);
+  float *Bc = my + 32, *Ad = my + kRecHead;
+  for (int i = lane; i < rec; i += 32) my[i] = 0.f;
+  RoiGeom g = roi_geometry(rois + 5 * (size_t)r, scale, aligned, kPH, kPW, sampling_ratio);
+  const bool valid = g.n >= 0 && g.n < N;
+  if (!valid) { g.gh = 0; g.gw = 0; }
+  __syncwarp();
+  int ymn = H, ymx = -1, xmn = W, xmx = -1, nx = 0;
+  if (lane < kPH) {
+    const int ph = lane;
+    const float inv = g.gh > 0 ? __fdiv_rn(1.0f, (float)g.gh) : 0.f;
+    for (int iy = 0; iy < g.gh; ++iy) {
+      int lo, hi; float l, h;
+      if (!bilinear_1d(sample_coord(g.sh, ph, g.bh, iy, g.gh), H, lo, hi, l, h)) continue;
+      Ad[lo * 8 + ph] += h * inv; Ad[hi * 8 + ph] += l * inv;
+      ymn = min(ymn, lo); ymx = max(ymx, hi);
+    }
+    lim[4 + ph] = ymn; lim[11 + ph] = ymx;
+  } else if (lane >= 8 && lane < 8 + kPW) {
+    const int pw = lane - 8;
+    const float inv = g.gw > 0 ? __fdiv_rn(1.0f, (float)g.gw) : 0.f;
+    for (int ix = 0; ix < g.gw; ++ix) {
+      int lo, hi; float l, h;
+      if (!bilinear_1d(sample_coord(g.sw, pw, g.bw, ix, g.gw), W, lo, hi, l, h)) continue;
+      xmn = min(xmn, lo); xmx = max(xmx, hi);
+    }
+    // compact window [x0, x0 + kNXMax) kept inside the row; it covers [xmn, xmx] whenever the bin is narrow enough
+    const int x0 = xmx >= 0 ? max(0, min(xmn, W - kNXMax)) : 0;
+    lim[18 + pw] = x0;
+    if (xmx >= 0) nx = (W >= kNXMax && xmx - x0 + 1 <= kNXMax) ? xmx - x0 + 1 : kNXMax + 1;
+    if (nx >= 1 && nx <= kNXMax) {
+      for (int ix = 0; ix < g.gw; ++ix) {   // same sample order as the dense table => identical sums
+        int lo, hi; float l, h;
+        if (!bilinear_1d(sample_coord(g.sw, pw, g.bw, ix, g.gw), W, lo, hi, l, h)) continue;
+        Bc[pw * kNXMax + (lo - x0)] += h * inv; Bc[pw * kNXMax + (hi - x0)] += l * inv;
+      }
+    }
+  }
+  ymn = __reduce_min_sync(0xFFFFFFFFu, ymn); ymx = __reduce_max_sync(0xFFFFFFFFu, ymx);
+  xmn = __reduce_min_sync(0xFFFFFFFFu, xmn); xmx = __reduce_max_sync(0xFFFFFFFFu, xmx);
+  nx = __reduce_max_sync(0xFFFFFFFFu, nx);
+  if (lane == 0) { lim[0] = ymn; lim[1] = ymx; lim[2] = xmn; lim[3] = xmx; lim[25] = nx; lim[26] = valid ? g.n : -1; }
+  __syncwarp();
+  for (int y = lane; y < H; y += 32) {   // bins fed by row y form a run [first, first + count): packed into the row's padding word
+    int first = kPH, last = -1;
+#pragma unroll
+    for (int a = 0; a < kPH; ++a)
+      if (Ad[y * 8 + a] != 0.f) { first = min(first, a); last = a; }
+    Ad[y * 8 + 7] = __int_as_float(last >= 0 ? (first | ((last - first + 1) << 8)) : 0);
+  }
+  __syncwarp();
+  float4 *dst = reinterpret_cast<float4 *>(recs + (size_t)r * rec);
+  const float4 *src = reinterpret_cast<const float4 *>(my);
+  for (int i = lane; i < rec / 4; i += 32) dst[i] = src[i];
+}
+
+// Dense column tables of one ROI for the rare wide-bin case (called by all threads of the CTA; CTA-uniform).
+__device__ __forceinline__ void sep_build_x_dense(float *Bd, const RoiGeom &g, int W) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < W * 8; i += blockDim.x) Bd[i] = 0.f;
+  __syncthreads();
+  if (tid < kPW) {
+    const int pw = tid;
+    const float inv = g.gw > 0 ? __fdiv_rn(1.0f, (float)g.gw) : 0.f;
+    for (int ix = 0; ix < g.gw; ++ix) {
+      int lo, hi; float l, h;
+      if (!bilinear_1d(sample_coord(g.sw, pw, g.bw, ix, g.gw), W, lo, hi, l, h)) continue;
+      Bd[lo * 8 + pw] += h * inv; Bd[hi * 8 + pw] += l * inv;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void sep_tile_wait_free() {   // the previous ROI's bulk store has finished READING the tile
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncthreads();
+}
+
+// registers -> shared tile (flat [channel][49], the global layout).  Lanes 0-15 write their even channel while lanes
+// 16-31 write their odd channel (and vice versa): word index (2*tid + j)*49 + k hits 32 distinct banks per instruction.
+template <int PH0, int NPH, bool kFirst>
+__device__ __forceinline__ void sep_store_acc(const float2 (&acc)[NPH][kPW], float *__restrict__ t0, float *__restrict__ t1, int half,
+                                              bool active) {
+  if (kFirst) sep_tile_wait_free();
+  if (!active) return;
+#pragma unroll
+  for (int a = 0; a < NPH; ++a)
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) {
+      const float v0 = acc[a][b].x, v1 = acc[a][b].y;
+      t0[(PH0 + a) * kPW + b] = half ? v1 : v0;
+      t1[(PH0 + a) * kPW + b] = half ? v0 : v1;
+    }
+}
+
+// One pass over the rows feeding bins [PH0, PH0 + NPH), dense column tables (2 LDS.128 of weights per pixel).
 template <int PH0, int NPH, int kC>
-__device__ __forceinline__ void sep_fwd_pass(const SepSmem &s, const float2 *__restrict__ fbase2, int C, int W, int xmin, int xmax,
-                                             float *__restrict__ t0, float *__restrict__ t1, int half) {
+__device__ __forceinline__ void sep_fwd_pass_dense(const SepSmem &s, const float2 *__restrict__ fbase2, int C, int W, int xmin, int xmax,
+                                                   float *__restrict__ t0, float *__restrict__ t1, int half, bool active) {
   const int cs2 = (kC ? kC : C) >> 1;
   int y0 = s.lim[4 + PH0], y1 = s.lim[11 + PH0];
 #pragma unroll
@@ -262,23 +369,7 @@ __device__ __forceinline__ void sep_fwd_pass(const SepSmem &s, const float2 *__r
 #pragma unroll
     for (int b = 0; b < kPW; ++b) T[b] = make_float2(0.f, 0.f);
     const float2 *prow = fbase2 + (size_t)y * W * cs2;
-    for (int x0 = xmin; x0 <= xmax; x0 += kXB) {
-      const float2 *p = prow + (size_t)x0 * cs2;
-      const float *bw = s.Bd + x0 * 8;
-      const int nv = xmax - x0 + 1;   // warp-uniform
-      float2 f[kXB];
-      if (nv >= kXB) {
-#pragma unroll
-        for (int i = 0; i < kXB; ++i) f[i] = __ldg(p + (size_t)i * cs2);
-#pragma unroll
-        for (int i = 0; i < kXB; ++i) sep_row_fma(T, bw + 8 * i, f[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < kXB - 1; ++i) if (i < nv) f[i] = __ldg(p + (size_t)i * cs2);
-#pragma unroll
-        for (int i = 0; i < kXB - 1; ++i) if (i < nv) sep_row_fma(T, bw + 8 * i, f[i]);
-      }
-    }
+    for (int x = xmin; x <= xmax; ++x) sep_row_fma(T, s.Bd + x * 8, __ldg(prow + (size_t)x * cs2));
     const float4 av4 = *reinterpret_cast<const float4 *>(s.Ad + y * 8 + PH0);   // PH0 in {0, 4}: 16-byte aligned
     const float av[4] = {av4.x, av4.y, av4.z, av4.w};
 #pragma unroll
@@ -289,16 +380,7 @@ __device__ __forceinline__ void sep_fwd_pass(const SepSmem &s, const float2 *__r
       }
     }
   }
-  // registers -> shared tile (flat [channel][49], the global layout).  Lanes 0-15 write their even channel while lanes
-  // 16-31 write their odd channel (and vice versa): word index (2*tid + j)*49 + k hits 32 distinct banks per instruction.
-#pragma unroll
-  for (int a = 0; a < NPH; ++a)
-#pragma unroll
-    for (int b = 0; b < kPW; ++b) {
-      const float v0 = acc[a][b].x, v1 = acc[a][b].y;
-      t0[(PH0 + a) * kPW + b] = half ? v1 : v0;
-      t1[(PH0 + a) * kPW + b] = half ? v0 : v1;
-    }
+  sep_store_acc<PH0, NPH, PH0 == 0>(acc, t0, t1, half, active);
 }
 
 // The same pass with the column weights in compact form.  With the adaptive sampling grid every bin touches at most
@@ -308,7 +390,7 @@ __device__ __forceinline__ void sep_fwd_pass(const SepSmem &s, const float2 *__r
 // zeros.  NX = widest bin window of this ROI rounded up to a template instance; narrower bins carry zero weights.
 template <int PH0, int NPH, int kC, int NX>
 __device__ __forceinline__ void sep_fwd_pass_compact(const SepSmem &s, const float2 *__restrict__ fbase2, int C, int W,
-                                                     float *__restrict__ t0, float *__restrict__ t1, int half) {
+                                                     float *__restrict__ t0, float *__restrict__ t1, int half, bool active) {
   const int cs2 = (kC ? kC : C) >> 1;
   int y0 = s.lim[4 + PH0], y1 = s.lim[11 + PH0];
 #pragma unroll
@@ -326,17 +408,38 @@ __device__ __forceinline__ void sep_fwd_pass_compact(const SepSmem &s, const flo
   for (int a = 0; a < NPH; ++a)
 #pragma unroll
     for (int b = 0; b < kPW; ++b) acc[a][b] = make_float2(0.f, 0.f);
+  // NX == 2 (the common case) is software-pipelined: the pixel loads of row y + 1 are issued before the accumulation of
+  // row y, so each warp keeps a row of loads in flight while it (or its neighbours) issue FMAs; wider windows would spill
+  constexpr bool kPipe = NX <= 2;
+  float2 f[kPW][NX];
+  if (kPipe) {
+    const float2 *prow = fbase2 + (size_t)y0 * W * cs2;
+#pragma unroll
+    for (int b = 0; b < kPW; ++b)
+#pragma unroll
+      for (int j = 0; j < NX; ++j) f[b][j] = __ldg(prow + xo[b] + j * cs2);
+  }
   for (int y = y0; y <= y1; ++y) {
-    const float2 *prow = fbase2 + (size_t)y * W * cs2;
+    if (!kPipe) {
+      const float2 *prow = fbase2 + (size_t)y * W * cs2;
+#pragma unroll
+      for (int b = 0; b < kPW; ++b)
+#pragma unroll
+        for (int j = 0; j < NX; ++j) f[b][j] = __ldg(prow + xo[b] + j * cs2);
+    }
     float2 T[kPW];
 #pragma unroll
     for (int b = 0; b < kPW; ++b) {
-      float2 f[NX];
+      T[b] = make_float2(bw[b][0] * f[b][0].x, bw[b][0] * f[b][0].y);
 #pragma unroll
-      for (int j = 0; j < NX; ++j) f[j] = __ldg(prow + xo[b] + j * cs2);
-      T[b] = make_float2(bw[b][0] * f[0].x, bw[b][0] * f[0].y);
+      for (int j = 1; j < NX; ++j) { T[b].x = fmaf(bw[b][j], f[b][j].x, T[b].x); T[b].y = fmaf(bw[b][j], f[b][j].y, T[b].y); }
+    }
+    if (kPipe && y < y1) {
+      const float2 *prow = fbase2 + (size_t)(y + 1) * W * cs2;
 #pragma unroll
-      for (int j = 1; j < NX; ++j) { T[b].x = fmaf(bw[b][j], f[j].x, T[b].x); T[b].y = fmaf(bw[b][j], f[j].y, T[b].y); }
+      for (int b = 0; b < kPW; ++b)
+#pragma unroll
+        for (int j = 0; j < NX; ++j) f[b][j] = __ldg(prow + xo[b] + j * cs2);
     }
     const float4 av4 = *reinterpret_cast<const float4 *>(s.Ad + y * 8 + PH0);
     const float av[4] = {av4.x, av4.y, av4.z, av4.w};
@@ -348,67 +451,369 @@ __device__ __forceinline__ void sep_fwd_pass_compact(const SepSmem &s, const flo
       }
     }
   }
-#pragma unroll
-  for (int a = 0; a < NPH; ++a)
-#pragma unroll
-    for (int b = 0; b < kPW; ++b) {
-      const float v0 = acc[a][b].x, v1 = acc[a][b].y;
-      t0[(PH0 + a) * kPW + b] = half ? v1 : v0;
-      t1[(PH0 + a) * kPW + b] = half ? v0 : v1;
-    }
+  sep_store_acc<PH0, NPH, PH0 == 0>(acc, t0, t1, half, active);
 }
 
+__host__ __device__ inline size_t sep_fwd_smem_bytes(int H, int W) {
+  // output tile, two table records (current ROI / prefetched next ROI), dense column table of the fallback, work-item slots
+  return (size_t)kTileFloats * 4 + 2 * (size_t)sep_rec_floats(H) * 4 + (size_t)W * 8 * 4 + 16;
+}
+
+// Persistent forward: CTAs pull (ROI, 256-channel slab) items from a global counter.  Per item and CTA: two barriers, no
+// global-memory latency outside the row loops -- the table record of the NEXT item streams in through cp.async and the
+// bulk store of the PREVIOUS item drains while the rows of the current one are accumulated.
 template <int kC>
-__global__ void __launch_bounds__(kSepThreads, 4) roi_align_fwd_sep_kernel(const float *__restrict__ feat /* NHWC */,
-                                                                           const float *__restrict__ rois, int N, int C, int H,
-                                                                           int W, float scale, int sampling_ratio, int aligned,
-                                                                           float *__restrict__ output) {
+__global__ void __launch_bounds__(kSepThreads, 3) roi_align_fwd_sep_kernel(const float *__restrict__ feat /* NHWC */,
+                                                                           const float *__restrict__ rois,
+                                                                           const float *__restrict__ recs,
+                                                                           unsigned *__restrict__ counter, int N, int C, int H,
+                                                                           int W, int R, float scale, int sampling_ratio,
+                                                                           int aligned, float *__restrict__ output) {
   extern __shared__ __align__(128) float sep_smem[];
-  const SepSmem s = sep_carve(sep_smem, H, W);
-  const int r = blockIdx.x, cbase = blockIdx.y * kCT;
+  const int rec = sep_rec_floats(H);
+  float *tile = sep_smem, *tab = tile + kTileFloats, *Bd = tab + 2 * rec;
+  int *s_item = reinterpret_cast<int *>(Bd + W * 8);
   const int tid = threadIdx.x;
-  RoiGeom g = roi_geometry(rois + 5 * (size_t)r, scale, aligned, kPH, kPW, sampling_ratio);
-  if (g.n < 0 || g.n >= N) { g.gh = 0; g.gw = 0; g.n = 0; }  // invalid batch index -> zeros
-  sep_build_tables(s, g, H, W);
-  const int ymin = s.lim[0], ymax = s.lim[1], xmin = s.lim[2], xmax = s.lim[3];
-  const int c0 = cbase + 2 * tid;
-  const bool active = c0 < C;
-  if (active) {
-    const int half = (tid >> 4) & 1;
-    float *t0 = s.tile + (size_t)(2 * tid + half) * kBins;
-    float *t1 = s.tile + (size_t)(2 * tid + 1 - half) * kBins;
-    if (ymax >= ymin && xmax >= xmin) {
-      const float2 *fbase2 = reinterpret_cast<const float2 *>(feat + (size_t)g.n * H * W * C + c0);
+  const int nslab = (C + kCT - 1) / kCT;
+  const int nitems = R * nslab;
+  int cur = blockIdx.x;
+  if (cur >= nitems) return;
+  unsigned long long l2_stream;   // the output stream must not evict the feature map from L2
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_stream));
+  auto fetch = [&](int item, int b) {
+    const float4 *src = reinterpret_cast<const float4 *>(recs + (size_t)(item / nslab) * rec);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(tab + b * rec);
+    for (int i = tid; i < rec / 4; i += kSepThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(cur, 0);
+  if (tid == 0) s_item[1] = (int)(gridDim.x + atomicAdd(counter, 1u));
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int half = (tid >> 4) & 1;
+  float *t0 = tile + (size_t)(2 * tid + half) * kBins;
+  float *t1 = tile + (size_t)(2 * tid + 1 - half) * kBins;
+  int buf = 0;
+  for (;;) {
+    const int nxt = s_item[buf ^ 1];
+    if (nxt < nitems) fetch(nxt, buf ^ 1);
+    int after = 0;
+    if (tid == 0) after = (int)(gridDim.x + atomicAdd(counter, 1u));
+    const int r = cur / nslab, cbase = (cur - r * nslab) * kCT;
+    SepSmem s;
+    s.tile = tile; s.lim = reinterpret_cast<int *>(tab + buf * rec); s.Bc = tab + buf * rec + 32; s.Ad = tab + buf * rec + kRecHead;
+    s.Bd = Bd;
+    const int n = s.lim[26];
+    const bool empty = n < 0 || s.lim[1] < s.lim[0] || s.lim[3] < s.lim[2];
+    const bool active = cbase + 2 * tid < C;
+    const int c0 = active ? cbase + 2 * tid : cbase;   // idle lanes of a partial slab shadow a valid channel pair
+    if (!empty) {
+      const float2 *fbase2 = reinterpret_cast<const float2 *>(feat + (size_t)n * H * W * C + c0);
       const int nx = s.lim[25];   // CTA-uniform
       if (nx <= 2) {
-        sep_fwd_pass_compact<0, 4, kC, 2>(s, fbase2, C, W, t0, t1, half);
-        sep_fwd_pass_compact<4, 3, kC, 2>(s, fbase2, C, W, t0, t1, half);
+        sep_fwd_pass_compact<0, 4, kC, 2>(s, fbase2, C, W, t0, t1, half, active);
+        sep_fwd_pass_compact<4, 3, kC, 2>(s, fbase2, C, W, t0, t1, half, active);
       } else if (nx == 3) {
-        sep_fwd_pass_compact<0, 4, kC, 3>(s, fbase2, C, W, t0, t1, half);
-        sep_fwd_pass_compact<4, 3, kC, 3>(s, fbase2, C, W, t0, t1, half);
+        sep_fwd_pass_compact<0, 4, kC, 3>(s, fbase2, C, W, t0, t1, half, active);
+        sep_fwd_pass_compact<4, 3, kC, 3>(s, fbase2, C, W, t0, t1, half, active);
       } else if (nx == 4) {
-        sep_fwd_pass_compact<0, 4, kC, 4>(s, fbase2, C, W, t0, t1, half);
-        sep_fwd_pass_compact<4, 3, kC, 4>(s, fbase2, C, W, t0, t1, half);
-      } else {   // wide bins (fixed sampling_ratio with bins wider than a pixel, or maps narrower than the window): dense tables
-        sep_fwd_pass<0, 4, kC>(s, fbase2, C, W, xmin, xmax, t0, t1, half);
-        sep_fwd_pass<4, 3, kC>(s, fbase2, C, W, xmin, xmax, t0, t1, half);
+        sep_fwd_pass_compact<0, 4, kC, 4>(s, fbase2, C, W, t0, t1, half, active);
+        sep_fwd_pass_compact<4, 3, kC, 4>(s, fbase2, C, W, t0, t1, half, active);
+      } else {   // wide bins (fixed sampling_ratio with bins wider than a pixel, or maps narrower than the window)
+        const RoiGeom g = roi_geometry(rois + 5 * (size_t)r, scale, aligned, kPH, kPW, sampling_ratio);
+        sep_build_x_dense(Bd, g, W);
+        sep_fwd_pass_dense<0, 4, kC>(s, fbase2, C, W, s.lim[2], s.lim[3], t0, t1, half, active);
+        sep_fwd_pass_dense<4, 3, kC>(s, fbase2, C, W, s.lim[2], s.lim[3], t0, t1, half, active);
       }
     } else {
+      sep_tile_wait_free();
+      if (active) {
 #pragma unroll
-      for (int k = 0; k < kBins; ++k) { t0[k] = 0.f; t1[k] = 0.f; }
+        for (int k = 0; k < kBins; ++k) { t0[k] = 0.f; t1[k] = 0.f; }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (tid == 0) s_item[buf] = after;
+    __syncthreads();   // tile complete, next record landed, everybody is done with this record and this item slot
+    if (tid == 0) {
+      const int nch = min(kCT, C - cbase);
+      const unsigned bytes = (unsigned)nch * kBins * 4u;
+      float *dst = output + ((size_t)r * C + cbase) * kBins;
+      const unsigned src = (unsigned)__cvta_generic_to_shared(tile);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src), "r"(bytes), "l"(l2_stream) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    cur = nxt; buf ^= 1;
+    if (cur >= nitems) break;
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---- slab-resident forward (the default when the map is small enough, e.g. VGG 18 x 37).
+// The kernel above is bound by L2 latency: every pixel of every ROI is a ~500-cycle global load and the register file
+// limits how many of them a warp keeps in flight.  Here the feature map of one image and 32 channels (H*W*128 B; 85 KB
+// for 18 x 37) is made RESIDENT in shared memory and every ROI of that image is served from it: pixel reads become
+// conflict-free 128 B LDS (lane = channel), the L2 sees each slab once per CTA instead of once per ROI, and a warp
+// needs no memory-level parallelism at all.
+//   * work = (32-channel slab, ROI) pairs, numbered slab-major and cut into one contiguous range per CTA (1 CTA/SM, 16
+//     warps); a CTA loads the slab of each image that occurs in its range once, then its warps pull ROIs of that image
+//     from a shared-memory ticket counter (ROIs may arrive in any image order; sorted input costs 1-2 slab loads per CTA);
+//   * one warp = one ROI at a time, one channel per lane, all 49 accumulators in registers (single pass, no row is
+//     visited twice), column weights compact and register-resident exactly as in the kernel above;
+//   * the table record of the warp's NEXT ROI streams in through cp.async while the current one is accumulated, and
+//     the warp's (32 x 49) result leaves as one 6 272 B bulk store that drains during the next ROI.
+constexpr int kSlabCh = 32;
+constexpr int kSlabStage = kSlabCh * kBins;            // 1 568 floats staged per warp
+constexpr int kSlabMaxImages = 1024;                   // presence bitmap (32 words)
+
+__host__ __device__ inline size_t slab_warp_floats(int H) { return (size_t)kSlabStage + 2 * (size_t)sep_rec_floats(H); }
+__host__ __device__ inline size_t slab_smem_bytes(int H, int W, int warps) {
+  return ((size_t)H * W * kSlabCh + (size_t)warps * slab_warp_floats(H)) * 4 + 40 * 4;
+}
+
+__device__ __forceinline__ void slab_stage_wait_free() {   // this warp's previous bulk store has finished reading its stage
+  if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
+
+// acc[a][:] += av[a] * T[:] for the run of bins a in [first, first + count) that row y feeds (first | count << 8 = info).
+// A warp-uniform switch on the first bin and nested count tests: only the FMAs of bins that really use the row are
+// issued (1-2 of the 7 for all but tiny ROIs), instead of 49 predicated ones.
+template <int A0>
+__device__ __forceinline__ void slab_acc_from(float (&acc)[kPH][kPW], const float (&av)[kPH], const float (&T)[kPW], int count) {
+#pragma unroll
+  for (int b = 0; b < kPW; ++b) acc[A0][b] = fmaf(av[A0], T[b], acc[A0][b]);
+  if constexpr (A0 + 1 < kPH) {
+    if (count > 1) slab_acc_from<A0 + 1>(acc, av, T, count - 1);
+  }
+}
+__device__ __forceinline__ void slab_accumulate(float (&acc)[kPH][kPW], const float (&av)[kPH], const float (&T)[kPW], int info) {
+  const int count = info >> 8;
+  switch (info & 0xff) {
+    case 0: slab_acc_from<0>(acc, av, T, count); break;
+    case 1: slab_acc_from<1>(acc, av, T, count); break;
+    case 2: slab_acc_from<2>(acc, av, T, count); break;
+    case 3: slab_acc_from<3>(acc, av, T, count); break;
+    case 4: slab_acc_from<4>(acc, av, T, count); break;
+    case 5: slab_acc_from<5>(acc, av, T, count); break;
+    default: slab_acc_from<6>(acc, av, T, count); break;
+  }
+}
+
+// rows of one ROI from the resident slab; S = slab + lane, compact column windows of width NX
+template <int kImm>
+__device__ __forceinline__ float slab_lds(unsigned addr) {   // ld.shared with an immediate byte offset
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(kImm));
+  return v;
+}
+
+template <int NX>
+__device__ __forceinline__ void slab_rows_compact(const float *__restrict__ S, int W, const int *__restrict__ lim,
+                                                  const float *__restrict__ Bc, const float *__restrict__ Ad,
+                                                  float (&acc)[kPH][kPW]) {
+  float bw[kPW][NX];
+  unsigned pb[kPW];   // shared-window byte address of (row 0, first column of bin b, this lane's channel)
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(S);
+#pragma unroll
+  for (int b = 0; b < kPW; ++b) {
+    pb[b] = sbase + (unsigned)lim[18 + b] * (kSlabCh * 4);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) bw[b][j] = Bc[b * kNXMax + j];
+  }
+  const int y0 = lim[0], y1 = lim[1];
+  const unsigned rstride = (unsigned)W * (kSlabCh * 4);
+  for (int y = y0; y <= y1; ++y) {
+    const float4 a0 = *reinterpret_cast<const float4 *>(Ad + y * 8), a1 = *reinterpret_cast<const float4 *>(Ad + y * 8 + 4);
+    const float av[kPH] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z};
+    const int info = __float_as_int(a1.w);
+    if (info == 0) continue;   // no bin uses this row
+    const unsigned ro = (unsigned)y * rstride;
+    float T[kPW];
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) {
+      const unsigned p = pb[b] + ro;
+      T[b] = bw[b][0] * slab_lds<0>(p);
+      if (NX > 1) T[b] = fmaf(bw[b][1 % NX], slab_lds<kSlabCh * 4>(p), T[b]);
+      if (NX > 2) T[b] = fmaf(bw[b][2 % NX], slab_lds<2 * kSlabCh * 4>(p), T[b]);
+      if (NX > 3) T[b] = fmaf(bw[b][3 % NX], slab_lds<3 * kSlabCh * 4>(p), T[b]);
+    }
+    slab_accumulate(acc, av, T, info);
+  }
+}
+
+// wide-bin fallback: dense column table Bd (W x 8, built by the warp in its own stage buffer)
+__device__ __forceinline__ void slab_rows_dense(const float *__restrict__ S, int W, const int *__restrict__ lim,
+                                                const float *__restrict__ Bd, const float *__restrict__ Ad,
+                                                float (&acc)[kPH][kPW]) {
+  const int y0 = lim[0], y1 = lim[1], x0 = lim[2], x1 = lim[3];
+  for (int y = y0; y <= y1; ++y) {
+    const float *row = S + y * W * kSlabCh;
+    float T[kPW];
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) T[b] = 0.f;
+    for (int x = x0; x <= x1; ++x) {
+      const float f = row[x * kSlabCh];
+      const float4 w0 = *reinterpret_cast<const float4 *>(Bd + x * 8), w1 = *reinterpret_cast<const float4 *>(Bd + x * 8 + 4);
+      T[0] = fmaf(w0.x, f, T[0]); T[1] = fmaf(w0.y, f, T[1]); T[2] = fmaf(w0.z, f, T[2]); T[3] = fmaf(w0.w, f, T[3]);
+      T[4] = fmaf(w1.x, f, T[4]); T[5] = fmaf(w1.y, f, T[5]); T[6] = fmaf(w1.z, f, T[6]);
+    }
+    const float4 a0 = *reinterpret_cast<const float4 *>(Ad + y * 8), a1 = *reinterpret_cast<const float4 *>(Ad + y * 8 + 4);
+    const float av[kPH] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z};
+    if (__float_as_int(a1.w) != 0) slab_accumulate(acc, av, T, __float_as_int(a1.w));
+  }
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab_kernel(const float *__restrict__ feat /* NHWC */,
+                                                                            const float *__restrict__ rois,
+                                                                            const float *__restrict__ recs, int N, int C, int H,
+                                                                            int W, int R, float scale, int sampling_ratio,
+                                                                            int aligned, float *__restrict__ output) {
+  extern __shared__ __align__(128) float sep_smem[];
+  const int rec = sep_rec_floats(H);
+  const int HW = H * W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float *slab = sep_smem;
+  float *mine = slab + (size_t)HW * kSlabCh + (size_t)warp * slab_warp_floats(H);
+  float *stage = mine, *recbuf = mine + kSlabStage;
+  int *ctrl = reinterpret_cast<int *>(slab + (size_t)HW * kSlabCh + (size_t)kWarps * slab_warp_floats(H));
+  int *s_ticket = ctrl, *s_invalid = ctrl + 1, *s_span = ctrl + 2;
+  unsigned *s_present = reinterpret_cast<unsigned *>(ctrl + 8);   // kSlabMaxImages bits
+
+  unsigned long long l2_stream;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_stream));
+  const int nslab = (C + kSlabCh - 1) / kSlabCh;
+  const long long total = (long long)nslab * R;
+  long long lo = total * blockIdx.x / gridDim.x;
+  const long long hi = total * (blockIdx.x + 1) / gridDim.x;
+
+  auto fetch_rec = [&](int r, int b) {   // warp-wide cp.async of one table record
+    const float4 *src = reinterpret_cast<const float4 *>(recs + (size_t)r * rec);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(recbuf + b * rec);
+    for (int i = lane; i < rec / 4; i += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto ticket = [&]() -> int {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(s_ticket, 1);
+    return __shfl_sync(0xFFFFFFFFu, t, 0);
+  };
+
+  while (lo < hi) {
+    const int sl = (int)(lo / R), r_lo = (int)(lo - (long long)sl * R);
+    const int r_hi = (int)min((long long)R, r_lo + (hi - lo));
+    lo += r_hi - r_lo;
+    const int cbase = sl * kSlabCh, nch = min(kSlabCh, C - cbase);
+    // which images occur in [r_lo, r_hi)?
+    if (tid < kSlabMaxImages / 32) s_present[tid] = 0u;
+    if (tid == 0) *s_invalid = 0;
+    __syncthreads();
+    for (int r = r_lo + tid; r < r_hi; r += kWarps * 32) {
+      const int img = reinterpret_cast<const int *>(recs + (size_t)r * rec)[26];
+      if (img >= 0) atomicOr(&s_present[img >> 5], 1u << (img & 31)); else *s_invalid = 1;
+    }
+    __syncthreads();
+    for (int n = -1; n < N; ++n) {   // n == -1: ROIs with an invalid image index (zero output, no slab needed)
+      if (n < 0 ? (*s_invalid == 0) : !((s_present[n >> 5] >> (n & 31)) & 1u)) continue;   // CTA-uniform
+      if (n >= 0) {
+        const float *src = feat + (size_t)n * HW * C + cbase;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(slab);
+        const int q4 = nch >> 2;   // 16-byte chunks per pixel
+        for (int idx = tid; idx < HW * 8; idx += kWarps * 32) {
+          const int px = idx >> 3, q = idx & 7;
+          if (q < q4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * idx), "l"(src + (size_t)px * C + q * 4) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      // first / last ROI of this image inside the range (sorted input: the tickets then visit no foreign ROI)
+      if (tid == 0) { s_span[0] = r_hi; s_span[1] = r_lo - 1; }
+      __syncthreads();
+      {
+        int first = r_hi, last = r_lo - 1;
+        for (int r = r_lo + tid; r < r_hi; r += kWarps * 32) {
+          const int img = reinterpret_cast<const int *>(recs + (size_t)r * rec)[26];
+          if (img == n || (n < 0 && img < 0)) { first = min(first, r); last = max(last, r); }
+        }
+        first = __reduce_min_sync(0xFFFFFFFFu, first); last = __reduce_max_sync(0xFFFFFFFFu, last);
+        if (lane == 0 && last >= first) { atomicMin(&s_span[0], first); atomicMax(&s_span[1], last); }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      const int t_end = s_span[1] + 1;
+      if (tid == 0) *s_ticket = s_span[0];
+      __syncthreads();
+      const float *S = slab + lane;
+      int buf = 0;
+      int t = ticket();
+      if (t < t_end) fetch_rec(t, 0);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      while (t < t_end) {
+        const int tn = ticket();
+        if (tn < t_end) fetch_rec(tn, buf ^ 1);
+        const float *rb = recbuf + buf * rec;
+        const int *lim = reinterpret_cast<const int *>(rb);
+        if (lim[26] == n || (n < 0 && lim[26] < 0)) {
+          float acc[kPH][kPW];
+#pragma unroll
+          for (int a = 0; a < kPH; ++a)
+#pragma unroll
+            for (int b = 0; b < kPW; ++b) acc[a][b] = 0.f;
+          const bool empty = n < 0 || lim[1] < lim[0] || lim[3] < lim[2];
+          if (!empty) {
+            const int nx = lim[25];
+            if (nx <= 2) slab_rows_compact<2>(S, W, lim, rb + 32, rb + kRecHead, acc);
+            else if (nx == 3) slab_rows_compact<3>(S, W, lim, rb + 32, rb + kRecHead, acc);
+            else if (nx == 4) slab_rows_compact<4>(S, W, lim, rb + 32, rb + kRecHead, acc);
+            else {   // wide bins: dense column table, built by this warp in its (drained) stage buffer
+              slab_stage_wait_free();
+              const RoiGeom g = roi_geometry(rois + 5 * (size_t)t, scale, aligned, kPH, kPW, sampling_ratio);
+              for (int i = lane; i < W * 8; i += 32) stage[i] = 0.f;
+              __syncwarp();
+              if (lane < kPW) {
+                const float inv = g.gw > 0 ? __fdiv_rn(1.0f, (float)g.gw) : 0.f;
+                for (int ix = 0; ix < g.gw; ++ix) {
+                  int xl, xh; float l, h;
+                  if (!bilinear_1d(sample_coord(g.sw, lane, g.bw, ix, g.gw), W, xl, xh, l, h)) continue;
+                  stage[xl * 8 + lane] += h * inv; stage[xh * 8 + lane] += l * inv;
+                }
+              }
+              __syncwarp();
+              slab_rows_dense(S, W, lim, stage, rb + kRecHead, acc);
+              __syncwarp();
+            }
+          }
+          slab_stage_wait_free();
+          if (lane < nch) {
+#pragma unroll
+            for (int a = 0; a < kPH; ++a)
+#pragma unroll
+              for (int b = 0; b < kPW; ++b) stage[lane * kBins + a * kPW + b] = acc[a][b];   // stride 49: conflict-free
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            float *dst = output + ((size_t)t * C + cbase) * kBins;
+            const unsigned src = (unsigned)__cvta_generic_to_shared(stage);
+            const unsigned bytes = (unsigned)nch * kBins * 4u;
+            // the 1.6 GB output stream must not evict the feature map and the table records from L2
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src), "r"(bytes), "l"(l2_stream) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        t = tn; buf ^= 1;
+      }
+      __syncthreads();   // every warp is done with this slab (and with the ticket counter)
     }
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  if (tid == 0) {
-    const int nch = min(kCT, C - cbase);
-    const unsigned bytes = (unsigned)nch * kBins * 4u;
-    float *dst = output + ((size_t)r * C + cbase) * kBins;
-    const unsigned src = (unsigned)__cvta_generic_to_shared(s.tile);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Backward of the separable form: gF = A^T . gOut . B per channel pair, accumulated into an NHWC gradient with 8-byte
@@ -537,7 +942,9 @@ __global__ void __launch_bounds__(256) roi_pool_bwd_kernel(const float *__restri
 }
 
 bool sep_supported(int C, int H, int W, int PH, int PW) {
-  return PH == kPH && PW == kPW && (C % 4) == 0 && sep_smem_bytes(H, W) <= 100 * 1024;
+  // shared-memory budgets of the backward (dense tables), the persistent forward and the 4-ROI table pre-kernel
+  return PH == kPH && PW == kPW && (C % 4) == 0 && sep_smem_bytes(H, W) <= 100 * 1024 && sep_fwd_smem_bytes(H, W) <= 100 * 1024 &&
+         4 * (size_t)sep_rec_floats(H) * sizeof(float) <= 48 * 1024;
 }
 
 }  // namespace
@@ -552,10 +959,21 @@ SFOD_API int sfod_nhwc_to_nchw(const float *src, float *dst, int N, int C, int H
   return launch_transpose(src, dst, N, HW, C, sfod_cu(stream));
 }
 
-SFOD_API size_t sfod_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int layout, int exact) {
-  // exact kernel reads NCHW, separable kernel reads NHWC: a converted copy is needed when layouts differ
+SFOD_API size_t sfod_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int R, int layout, int exact) {
+  // exact kernel reads NCHW, separable kernel reads NHWC: a converted copy is needed when layouts differ; the separable
+  // kernel also needs one table record per ROI and its work counter
   const bool need = exact ? (layout == SFOD_NHWC) : (layout == SFOD_NCHW);
-  return need ? sfod_align_up((size_t)N * C * H * W * sizeof(float), 256) : 256;
+  size_t bytes = need ? sfod_align_up((size_t)N * C * H * W * sizeof(float), 256) : 0;
+  if (!exact) bytes += 256 + sfod_align_up((size_t)(R > 0 ? R : 0) * sep_rec_floats(H) * sizeof(float), 256);
+  return bytes ? bytes : 256;
+}
+
+static int sep_fwd_grid(const void *kern, size_t smem, int items) {   // resident CTAs of the persistent forward
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSepThreads, smem) != cudaSuccess || per_sm < 1) return -1;
+  const long long g = (long long)sms * per_sm;
+  return (int)(g < items ? g : items);
 }
 
 SFOD_API int sfod_roi_align_fwd(const float *input, int layout, const float *rois, int N, int C, int H, int W, int R, int PH,
@@ -570,19 +988,52 @@ SFOD_API int sfod_roi_align_fwd(const float *input, int layout, const float *roi
   const size_t fbytes = (size_t)N * C * H * W * sizeof(float);
   if (fast) {
     const float *feat = input;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    size_t used = 0;
     if (layout == SFOD_NCHW) {
       if (!workspace || workspace_bytes < fbytes) return SFOD_ERR_WORKSPACE_TOO_SMALL;
       int rc = launch_transpose(input, static_cast<float *>(workspace), N, C, H * W, st);
       if (rc) return rc;
       feat = static_cast<const float *>(workspace);
+      used = sfod_align_up(fbytes, 256);
     }
     if (!sfod_aligned16(feat)) return SFOD_ERR_ALIGNMENT;
-    const size_t smem = sep_smem_bytes(H, W);
-    dim3 grid(R, (C + kCT - 1) / kCT);
+    const size_t rec_bytes = (size_t)sep_rec_floats(H) * sizeof(float);
+    if (!workspace || workspace_bytes < used + 256 + (size_t)R * rec_bytes) return SFOD_ERR_WORKSPACE_TOO_SMALL;
+    if (!sfod_aligned16(ws + used)) return SFOD_ERR_ALIGNMENT;
+    unsigned *counter = reinterpret_cast<unsigned *>(ws + used);
+    float *recs = reinterpret_cast<float *>(ws + used + 256);
+    roi_sep_tables_kernel<<<(R + 3) / 4, 128, 4 * rec_bytes, st>>>(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, recs, counter);
+    SFOD_LAUNCH_CHECK();
+    // slab-resident kernel when one image x 32 channels of the map fits in shared memory next to the warps' buffers
+    int sms = 0, cur_dev = 0, max_optin = 0;
+    SFOD_CUDA_TRY(cudaGetDevice(&cur_dev));
+    SFOD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev));
+    SFOD_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cur_dev));
+    if (N <= kSlabMaxImages && (size_t)W * 8 <= (size_t)kSlabStage) {
+      const size_t s16 = slab_smem_bytes(H, W, 16), s8 = slab_smem_bytes(H, W, 8);
+      if (s16 <= (size_t)max_optin) {
+        SFOD_CUDA_TRY(cudaFuncSetAttribute(roi_align_fwd_slab_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s16));
+        roi_align_fwd_slab_kernel<16><<<sms, 16 * 32, s16, st>>>(feat, rois, recs, N, C, H, W, R, spatial_scale, sampling_ratio, aligned, output);
+        SFOD_LAUNCH_CHECK();
+        return SFOD_OK;
+      }
+      if (s8 <= (size_t)max_optin) {
+        SFOD_CUDA_TRY(cudaFuncSetAttribute(roi_align_fwd_slab_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8));
+        roi_align_fwd_slab_kernel<8><<<sms, 8 * 32, s8, st>>>(feat, rois, recs, N, C, H, W, R, spatial_scale, sampling_ratio, aligned, output);
+        SFOD_LAUNCH_CHECK();
+        return SFOD_OK;
+      }
+    }
+    const size_t smem = sep_fwd_smem_bytes(H, W);
+    const int items = R * ((C + kCT - 1) / kCT);
 #define SFOD_ROI_FWD(KC)                                                                                                     \
     do {                                                                                                                     \
       SFOD_CUDA_TRY(cudaFuncSetAttribute(roi_align_fwd_sep_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      roi_align_fwd_sep_kernel<KC><<<grid, kSepThreads, smem, st>>>(feat, rois, N, C, H, W, spatial_scale, sampling_ratio, aligned, output); \
+      const int grid = sep_fwd_grid(reinterpret_cast<const void *>(roi_align_fwd_sep_kernel<KC>), smem, items);             \
+      if (grid < 1) return SFOD_ERR_UNSUPPORTED;                                                                                   \
+      roi_align_fwd_sep_kernel<KC><<<grid, kSepThreads, smem, st>>>(feat, rois, recs, counter, N, C, H, W, R, spatial_scale, \
+                                                                    sampling_ratio, aligned, output);                        \
     } while (0)
     switch (C) {
       case 256: SFOD_ROI_FWD(256); break;

@@ -206,7 +206,7 @@ class _RoIAlignFn(torch.autograd.Function):
         L = _lib.lib()
         if R > 0:
             with torch.cuda.device(dev):
-                ws = _workspace(dev, "roi", L.sfod_roi_align_fwd_workspace_bytes(N, Cc, H, W, layout, int(exact)))
+                ws = _workspace(dev, "roi", L.sfod_roi_align_fwd_workspace_bytes(N, Cc, H, W, R, layout, int(exact)))
                 with _timed("roi_align_fwd"):
                     check(L.sfod_roi_align_fwd(xin.data_ptr(), layout, r.data_ptr(), N, Cc, H, W, R, ph, pw, float(scale), int(sr),
                                                int(aligned), int(exact), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),

@@ -155,6 +155,13 @@ def test_roi_align_kat_and_api(ops, cuda_device):
     got = ops.roi_align(xs.to(d), [b.to(d) for b in bl], 7, 1.0, 0, True).cpu()
     _close(got, ref)
     assert ops.roi_align(xs.to(d), torch.zeros(0, 5, device=d), 7).shape == (0, 8, 7, 7)
+    # maps narrower than the compact column window (dense-table fallback) and a partial 256-channel slab
+    for shape in ((1, 4, 6, 3), (2, 260, 9, 2), (1, 12, 3, 40)):
+        xn = torch.randn(*shape, generator=torch.Generator().manual_seed(sum(shape)))
+        rn = torch.tensor([[0, 0.2, 0.4, shape[3] - 0.5, shape[2] - 0.7], [shape[0] - 1, 0.0, 0.0, 1.0, 1.0],
+                           [0, -3.0, -2.0, shape[3] + 4.0, shape[2] + 1.0], [0, 1.2, 1.1, 1.3, 1.15]], dtype=torch.float32)
+        for sr in (0, 3):
+            _close(ops.roi_align(xn.to(d), rn.to(d), 7, 1.0, sr, True).cpu(), torchvision.ops.roi_align(xn, rn, 7, 1.0, sr, True))
     with pytest.raises(ValueError):
         ops.roi_align(xs.to(d), torch.zeros(3, 4, device=d), 7)
 
