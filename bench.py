@@ -366,7 +366,7 @@ def run_b200(args):
 
     # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture of this same command
     traffic_map = {"bn_finalize_apply": "bn_apply_nchw_kernel", "bn_finalize_apply_pool": "bn_apply_pool_nchw_kernel",
-                   "bn_partial_stats": "bn_stats_nchw_kernel", "roi_align_fwd": "roi_align_fwd_sep_kernel",
+                   "bn_partial_stats": "bn_stats_nchw_kernel", "roi_align_fwd": "roi_align_fwd_slab_kernel",
                    "ema_multi_tensor": "ema_multi_tensor_kernel"}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:

@@ -14,6 +14,6 @@ cap() {  # name, kernel regex, launch count
   sz=$(stat -c %s gpurun_out/prof_${TAG}_$1.ncu-rep)
   if [ "$sz" -gt 6000000 ]; then rm -f gpurun_out/prof_${TAG}_$1.ncu-rep; fi
 }
-cap det 'roi_align|ema_multi|nms_|bitonic|rpn_|frcnn_|transpose' 40
+cap det 'roi_align|roi_sep|ema_multi|nms_|bitonic|rpn_|frcnn_|transpose' 41
 cap bn 'bn_apply|bn_stats|bn_finalize' 39
 du -sh gpurun_out
