@@ -12,6 +12,8 @@
 //   j < 16        : in registers (static indices),
 //   16 <= j < 512 : warp shuffles (partner lane = lane ^ (j/16)),
 //   j >= 512      : one swizzled shared-memory exchange per stage (conflict-free 64-bit banks),
+//   j >= keys/CTA : distributed-shared-memory exchange between the CTAs of a thread-block cluster (a 16 384-key tile is
+//                   spread over 8 CTAs = 8 SMs x 4 warps instead of 32 warps queueing on one SM),
 //   j >= tile     : global-memory exchange kernel (only when P > 16384, e.g. 34 200 R101 anchors).
 #pragma once
 #include "common.cuh"
@@ -20,6 +22,7 @@ namespace bsort {
 
 constexpr int kE = 16;             // keys per thread
 constexpr int kMaxTile = 16384;    // keys per CTA (1024 threads), 128 KiB of shared memory
+constexpr int kClusterMinKeys = 2048; // a tile is spread over tile / 2048 (<= 8) CTAs of a cluster
 constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;
 
 __device__ __forceinline__ void cex(unsigned long long &a, unsigned long long &b, bool asc) {
@@ -59,12 +62,22 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return ((unsigned long long)hi << 32) | lo;
 }
 
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ const unsigned long long *cluster_peer(const unsigned long long *p, unsigned rank) {
+  unsigned long long out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(reinterpret_cast<unsigned long long>(p)), "r"(rank));
+  return reinterpret_cast<const unsigned long long *>(out);
+}
+
 // Runs the bitonic stages for merge sizes k = k_lo .. k_hi (powers of two, k_lo >= 2) restricted to
-// compare distances j < tile, on a tile of `tile` keys owned by this CTA (tile = 16 * blockDim.x).
-// `gbase` is the global index (within the segment) of the tile's first key: it defines directions.
-// smem: tile keys.
-__device__ __forceinline__ void block_bitonic(unsigned long long (&a)[kE], unsigned long long *smem, int tile,
-                                              long long gbase, int k_lo, int k_hi) {
+// compare distances j < tile, on a tile of `tile` keys owned by a cluster of `cl` CTAs (ctile = tile / cl = 16 * blockDim.x
+// keys per CTA, this CTA being number `rank`).  `gbase` is the global index (within the segment) of THIS CTA's first key:
+// it defines directions.  smem: ctile keys.
+__device__ __forceinline__ void block_bitonic(unsigned long long (&a)[kE], unsigned long long *smem, int tile, int ctile,
+                                              int rank, long long gbase, int k_lo, int k_hi) {
   const int t = threadIdx.x;
   const long long g0 = gbase + (long long)t * kE;  // global index of a[0]
   for (long long k = k_lo; k <= k_hi; k <<= 1) {
@@ -77,6 +90,23 @@ __device__ __forceinline__ void block_bitonic(unsigned long long (&a)[kE], unsig
     const bool asc = (g0 & k) == 0;
     long long j = k >> 1;
     if (j >= tile) j = tile >> 1;
+    // cluster stages: the partner key lives at the same position of CTA rank ^ (j / ctile)
+    for (; j >= ctile; j >>= 1) {
+      const int rj = (int)(j / ctile);
+      const int sw = t & 15;
+      __syncthreads();      // own threads are done with the shared-memory stage before
+#pragma unroll
+      for (int r = 0; r < kE; ++r) smem[t * kE + (r ^ sw)] = a[r];
+      cluster_sync_all();   // all tiles of the cluster are published
+      const unsigned long long *peer = cluster_peer(smem, (unsigned)(rank ^ rj));
+      const bool take_min = (((rank & rj) == 0) == asc);
+#pragma unroll
+      for (int r = 0; r < kE; ++r) {
+        const unsigned long long o = peer[t * kE + (r ^ sw)];
+        a[r] = take_min ? (a[r] < o ? a[r] : o) : (a[r] > o ? a[r] : o);
+      }
+      cluster_sync_all();   // every peer has read this CTA's tile before anything overwrites it
+    }
     // shared-memory stages
     for (; j >= 512; j >>= 1) {
       const int tj = (int)(j / kE);
@@ -110,17 +140,19 @@ __device__ __forceinline__ void block_bitonic(unsigned long long (&a)[kE], unsig
   }
 }
 
-// Tile kernel: grid (P / tile, S); block tile/16 threads; dynamic smem tile*8 bytes.
-__global__ void __launch_bounds__(1024) bitonic_tile_kernel(unsigned long long *keys, int P, int tile, int k_lo, int k_hi) {
+// Tile kernel: grid (cl * P / tile, S) launched as clusters of cl CTAs along x; block tile/cl/16 threads; dynamic smem
+// tile/cl*8 bytes.
+__global__ void __launch_bounds__(1024) bitonic_tile_kernel(unsigned long long *keys, int P, int tile, int cl, int k_lo, int k_hi) {
   extern __shared__ unsigned long long sort_smem[];
-  unsigned long long *seg = keys + (size_t)blockIdx.y * P + (size_t)blockIdx.x * tile;
+  const int ctile = tile / cl, rank = (int)(blockIdx.x % (unsigned)cl);
+  unsigned long long *seg = keys + (size_t)blockIdx.y * P + (size_t)blockIdx.x * ctile;
   unsigned long long a[kE];
   const int t = threadIdx.x;
   // 128-bit loads of the thread's 16 consecutive keys
   const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(seg + t * kE);
 #pragma unroll
   for (int r = 0; r < kE / 2; ++r) { ulonglong2 v = src[r]; a[2 * r] = v.x; a[2 * r + 1] = v.y; }
-  block_bitonic(a, sort_smem, tile, (long long)blockIdx.x * tile, k_lo, k_hi);
+  block_bitonic(a, sort_smem, tile, ctile, rank, (long long)blockIdx.x * ctile, k_lo, k_hi);
   ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(seg + t * kE);
 #pragma unroll
   for (int r = 0; r < kE / 2; ++r) dst[r] = make_ulonglong2(a[2 * r], a[2 * r + 1]);
@@ -149,20 +181,35 @@ static inline int segmented_sort(unsigned long long *keys, int S, int P, cudaStr
   if (S <= 0) return SFOD_OK;
   if (P < 512 || (P & (P - 1))) return SFOD_ERR_INVALID_ARG;
   const int tile = P < kMaxTile ? P : kMaxTile;
-  const size_t smem = (size_t)tile * sizeof(unsigned long long);
+  int cl = tile / kClusterMinKeys;   // keys per CTA >= 2048 (4 warps); portable cluster sizes only
+  if (cl > 8) cl = 8;
+  if (cl < 1) cl = 1;
+  const int ctile = tile / cl;
+  const size_t smem = (size_t)ctile * sizeof(unsigned long long);
   if (smem > 48 * 1024)
     SFOD_CUDA_TRY(cudaFuncSetAttribute(bitonic_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTile * 8));
-  dim3 grid(P / tile, S);
-  bitonic_tile_kernel<<<grid, tile / kE, smem, stream>>>(keys, P, tile, 2, tile);
-  SFOD_LAUNCH_CHECK();
+  dim3 grid(cl * (P / tile), S);
+  auto launch_tile = [&](int k_lo, int k_hi) -> int {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(ctile / kE, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SFOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bitonic_tile_kernel, keys, P, tile, cl, k_lo, k_hi));
+    sfod_count_launch();
+    return SFOD_OK;
+  };
+  int rc = launch_tile(2, tile);
+  if (rc) return rc;
   for (long long k = (long long)tile * 2; k <= P; k <<= 1) {
     for (long long j = k >> 1; j >= tile; j >>= 1) {
       dim3 g2((unsigned)((P / 2 + 255) / 256), S);
       bitonic_global_kernel<<<g2, 256, 0, stream>>>(keys, P, k, j);
       SFOD_LAUNCH_CHECK();
     }
-    bitonic_tile_kernel<<<grid, tile / kE, smem, stream>>>(keys, P, tile, (int)k, (int)k);
-    SFOD_LAUNCH_CHECK();
+    rc = launch_tile((int)k, (int)k);
+    if (rc) return rc;
   }
   return SFOD_OK;
 }
