@@ -370,6 +370,177 @@ __global__ void __launch_bounds__(kLazyThreads) nms_lazy_kernel(const float4 *__
   cluster_arrive(); cluster_wait();   // no CTA may exit while a peer can still push into its shared memory
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Deferred-apply cluster NMS (the default whenever the kept list fits in shared memory).
+// The lazy-row kernel above applies every kept list to ALL later boxes of the segment as soon as it is published.  When
+// the scan stops early -- RPN keeps post_nms_topk = 2000 of 9 990 candidates and reaches them after ~2 700 boxes -- three
+// quarters of those IoU tests are spent on boxes that are never visited (17 M of 20 M pairs per VGG image), and they sit
+// between consecutive cluster steps.  Here every CTA keeps the COMPLETE kept list of the segment (boxes, areas, classes;
+// owners push their tile's survivors into every CTA's copy) and a tile meets the kept boxes only when its turn comes
+// near: each CTA works ahead on its NEXT own tile only, a chunk of the backlog per cluster step sized so that it is done
+// exactly when the CTA becomes owner again.  The pair set evaluated for a visited box is the one of the lazy kernel
+// (first hit ends the box); unvisited boxes cost nothing; the step itself is the critical path (apply the newest list to
+// one tile, fixed-point resolve, push, split cluster barrier).  Same arithmetic, tie order and results.
+__host__ __device__ inline size_t deferred_smem_bytes(int own_cap_tiles, int cap) {
+  // own boxes (16 B) + kept boxes (16 B) | suppressor words, removed words (8 B) | own areas, classes, kept areas, classes, counts
+  return (size_t)own_cap_tiles * 64 * 16 + (size_t)cap * 16 + (size_t)own_cap_tiles * 64 * 8 + (((size_t)own_cap_tiles * 8 + 15) & ~(size_t)15) +
+         (size_t)own_cap_tiles * 64 * 8 + (size_t)cap * 8 + 16;
+}
+
+template <bool kClassAware>
+__global__ void __launch_bounds__(kLazyThreads) nms_deferred_kernel(const float4 *__restrict__ boxes, const int *__restrict__ cls,
+                                                                    const Seg *__restrict__ segs, float thr, int max_keep,
+                                                                    int keep_stride, int own_cap, int cap,
+                                                                    int *__restrict__ keep_rank, int *__restrict__ keep_count) {
+  extern __shared__ __align__(16) unsigned char lazy_raw[];
+  float4 *ob = reinterpret_cast<float4 *>(lazy_raw);
+  float4 *KB = ob + (size_t)own_cap * 64;
+  unsigned long long *col = reinterpret_cast<unsigned long long *>(KB + cap);
+  unsigned long long *removed = col + (size_t)own_cap * 64;
+  float *oa = reinterpret_cast<float *>(removed + ((own_cap + 1) & ~1));
+  int *oc = reinterpret_cast<int *>(oa + (size_t)own_cap * 64);
+  float *KA = reinterpret_cast<float *>(oc + (size_t)own_cap * 64);
+  int *KC = reinterpret_cast<int *>(KA + cap);
+  int *cnt = KC + cap;   // 3 slots
+
+  const int CL = (int)cluster_nctarank(), c = (int)cluster_ctarank();
+  const int s = blockIdx.y;
+  const Seg seg = segs[s];
+  const int n = seg.len;
+  const int W = (n + 63) >> 6;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool neg_thr = thr < 0.0f;
+  const int own_tiles = W > c ? (W - c + CL - 1) / CL : 0;
+  const int own_n = own_tiles * 64;
+  int *out = keep_rank + (size_t)s * keep_stride;
+
+  for (int idx = tid; idx < own_n; idx += kLazyThreads) {
+    const int q = idx >> 6, r = (q * CL + c) * 64 + (idx & 63);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cc = 0;
+    if (r < n) { b = boxes[seg.start + r]; if (kClassAware) cc = cls[seg.start + r]; }
+    ob[idx] = b; oa[idx] = sfod_box_area(b); oc[idx] = cc;
+  }
+  for (int q = tid; q < own_tiles; q += kLazyThreads) {
+    const int nvalid = min(64, n - (q * CL + c) * 64);
+    removed[q] = nvalid >= 64 ? 0ull : ~((1ull << nvalid) - 1ull);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < own_n * 8; idx += kLazyThreads) {   // intra-tile suppressor words (see the lazy kernel)
+    const int q = idx >> 9, j = (idx >> 3) & 63, ic = idx & 7;
+    const int nvalid = min(64, n - (q * CL + c) * 64);
+    unsigned bits = 0;
+    if (j < nvalid && ic * 8 < j) {
+      const float4 bj = ob[q * 64 + j]; const float aj = oa[q * 64 + j];
+      const int cj = oc[q * 64 + j];
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const int i = ic * 8 + ii;
+        if (i < j && (!kClassAware || oc[q * 64 + i] == cj) && lazy_iou_sup(ob[q * 64 + i], oa[q * 64 + i], bj, aj, thr, neg_thr))
+          bits |= 1u << ii;
+      }
+    }
+    reinterpret_cast<unsigned char *>(col)[(size_t)(q * 64 + j) * 8 + ic] = (unsigned char)bits;
+  }
+  __syncthreads();
+
+  // Resolve own tile q (global tile t) and append its survivors to the kept list of EVERY CTA at [base, base + nk).
+  auto resolve_publish = [&](int q, int t, int base) {
+    const int slot = t % 3;
+    if (warp == 0) {
+      const unsigned long long alive = ~removed[q];
+      const unsigned long long c0 = col[q * 64 + lane], c1 = col[q * 64 + 32 + lane];
+      const bool a0 = (alive >> lane) & 1ull, a1 = (alive >> (32 + lane)) & 1ull;
+      unsigned long long kept = alive;
+      for (;;) {
+        const unsigned lo = __ballot_sync(0xFFFFFFFFu, a0 && !(c0 & kept));
+        const unsigned hi = __ballot_sync(0xFFFFFFFFu, a1 && !(c1 & kept));
+        const unsigned long long nk = ((unsigned long long)hi << 32) | lo;
+        if (nk == kept) break;
+        kept = nk;
+      }
+      int nk = __popcll(kept);
+      if (base + nk > max_keep) {
+        const int allow = max_keep - base;
+        unsigned long long kk = kept, keep2 = 0;
+        for (int z = 0; z < allow; ++z) { const unsigned long long low = kk & (0ull - kk); keep2 |= low; kk ^= low; }
+        kept = keep2; nk = allow;
+      }
+      const unsigned klo = (unsigned)kept, khi = (unsigned)(kept >> 32);
+      if ((klo >> lane) & 1u) {
+        const int pos = base + __popc(klo & ((1u << lane) - 1u));
+        out[pos] = t * 64 + lane;
+        KB[pos] = ob[q * 64 + lane]; KA[pos] = oa[q * 64 + lane]; KC[pos] = oc[q * 64 + lane];
+      }
+      if ((khi >> lane) & 1u) {
+        const int pos = base + __popc(klo) + __popc(khi & ((1u << lane) - 1u));
+        out[pos] = t * 64 + 32 + lane;
+        KB[pos] = ob[q * 64 + 32 + lane]; KA[pos] = oa[q * 64 + 32 + lane]; KC[pos] = oc[q * 64 + 32 + lane];
+      }
+      if (lane == 0) cnt[slot] = nk;
+    }
+    __syncthreads();
+    const int kc = cnt[slot];
+    for (int p = warp; p < CL; p += kLazyThreads / 32) {   // one warp per peer: push through DSMEM
+      if (p == c) continue;
+      float4 *rKB = cluster_map(KB, (unsigned)p);
+      float *rKA = cluster_map(KA, (unsigned)p);
+      int *rKC = cluster_map(KC, (unsigned)p);
+      for (int k = lane; k < kc; k += 32) {
+        rKB[base + k] = KB[base + k]; rKA[base + k] = KA[base + k];
+        if (kClassAware) rKC[base + k] = KC[base + k];
+      }
+      if (lane == 0) cluster_map(cnt, (unsigned)p)[slot] = kc;
+    }
+  };
+
+  // own tile q against kept entries [k_lo, k_hi): 16 lanes share one box and stride through the list
+  auto apply = [&](int q, int k_lo, int k_hi) {
+    if (k_hi <= k_lo) return;
+    const int bi = tid >> 4, sub = tid & 15;
+    const unsigned long long bit = 1ull << bi;
+    if (removed[q] & bit) return;
+    const float4 bx = ob[q * 64 + bi]; const float ab = oa[q * 64 + bi];
+    const int cb = oc[q * 64 + bi];
+    for (int k = k_lo + sub, it = 0; k < k_hi; k += 16, ++it) {
+      if ((it & 3) == 3 && (removed[q] & bit)) break;   // another lane already removed this box
+      if (kClassAware && KC[k] != cb) continue;
+      if (lazy_iou_sup(KB[k], KA[k], bx, ab, thr, neg_thr)) { atomicOr(&removed[q], bit); break; }
+    }
+  };
+
+  int total = 0;
+  int next_q = 0;   // next own tile to resolve (global tile next_q * CL + c)
+  int done = 0;     // kept entries [0, done) have been applied to it
+  if (c == 0 && W > 0) { resolve_publish(0, 0, 0); next_q = 1; }
+  cluster_arrive(); cluster_wait();
+  for (int t = 0; t < W; ++t) {
+    const int new_total = total + cnt[t % 3];
+    const bool finished = (new_total >= max_keep) || (t + 1 >= W);
+    if (!finished && c == (t + 1) % CL) {   // owner of the next tile: finish its backlog + the newest list, resolve, publish
+      apply(next_q, done, new_total);
+      __syncthreads();
+      resolve_publish(next_q, t + 1, new_total);
+      ++next_q; done = 0;
+    }
+    cluster_arrive();
+    if (!finished && next_q < own_tiles) {   // work ahead on the next own tile: a share of the backlog per step
+      const int turn = next_q * CL + c - 1;  // loop iteration at which this CTA resolves it
+      const int steps_left = max(1, turn - t);
+      const int avail = new_total - done;    // the newest list is complete in this CTA's copy (barrier above)
+      int chunk = (avail + steps_left - 1) / steps_left;
+      chunk = min(avail, (chunk + 15) & ~15);
+      apply(next_q, done, done + chunk);
+      done += chunk;
+    }
+    cluster_wait();
+    total = new_total;
+    if (finished) break;
+  }
+  if (c == 0 && tid == 0) keep_count[s] = total < max_keep ? total : max_keep;
+  cluster_arrive(); cluster_wait();   // no CTA may exit while a peer can still push into its shared memory
+}
+
 // host helpers
 static inline int lazy_cluster_size(int S, int max_len, size_t *smem_out, int *own_cap_out) {
   int CL = 16;
@@ -439,6 +610,64 @@ static inline int launch_lazy_t(const float4 *boxes, const int *cls, const Seg *
   return SFOD_OK;
 }
 
+template <bool kCls>
+static inline int deferred_max_cluster() {   // see lazy_max_cluster
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  auto kern = nms_deferred_kernel<kCls>;
+  (void)cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  (void)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  int best = 0;
+  for (int CL = 16; CL >= 1; CL >>= 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL, 1, 1); cfg.blockDim = dim3(kLazyThreads, 1, 1); cfg.dynamicSmemBytes = 200 * 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0) { best = CL; break; }
+    (void)cudaGetLastError();
+  }
+  cached = best;
+  return best;
+}
+
+template <bool kCls>
+static inline int launch_deferred_t(const float4 *boxes, const int *cls, const Seg *segs, int S, int max_len, double thr, int max_keep,
+                                    int keep_stride, int *keep_rank, int *keep_count, cudaStream_t stream, bool *launched) {
+  *launched = false;
+  const int max_cl = deferred_max_cluster<kCls>();
+  if (max_cl <= 0) return SFOD_OK;
+  size_t unused; int own_cap;
+  int CL = lazy_cluster_size(S, max_len, &unused, &own_cap);
+  if (CL > max_cl) {
+    CL = max_cl;
+    const int W = (max_len + 63) / 64;
+    own_cap = (W + CL - 1) / CL; if (own_cap < 1) own_cap = 1;
+  }
+  int cap = max_keep < max_len ? max_keep : max_len;   // the kept list never grows beyond min(max_keep, segment length)
+  cap = (cap + 3) & ~3; if (cap < 4) cap = 4;
+  const size_t smem = deferred_smem_bytes(own_cap, cap);
+  if (smem > 200 * 1024) return SFOD_OK;   // kept list too long for shared memory: caller uses the lazy-row kernel
+  auto kern = nms_deferred_kernel<kCls>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL, S, 1); cfg.blockDim = dim3(kLazyThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  float thr_f = (float)thr;                                  // largest float <= thr (see lazy_iou_sup)
+  if ((double)thr_f > thr) thr_f = nextafterf(thr_f, -INFINITY);
+  if (cudaLaunchKernelEx(&cfg, kern, boxes, cls, segs, thr_f, max_keep, keep_stride, own_cap, cap, keep_rank, keep_count) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return SFOD_OK;
+  }
+  sfod_count_launch();
+  *launched = true;
+  return SFOD_OK;
+}
+
 static inline int launch_mask(const float4 *boxes, const int *cls, const Seg *segs, int S, int max_len, int rows_per_slab,
                               int wstride, double thr, unsigned long long *mask, cudaStream_t stream) {
   if (S <= 0 || max_len <= 0) return SFOD_OK;
@@ -460,14 +689,19 @@ static inline int launch_scan(const unsigned long long *mask, const Seg *segs, i
   return SFOD_OK;
 }
 
-// Segmented NMS entry used by every caller: lazy cluster kernel, or mask + scan when that cannot run.
+// Segmented NMS entry used by every caller: deferred-apply cluster kernel; lazy-row cluster kernel when the kept list does
+// not fit in shared memory; mask + scan when clusters cannot run.
 static inline int run_segmented(const float4 *boxes, const int *cls, const Seg *segs, int S, int max_len, int rows_per_slab,
                                 int wstride, double thr, int max_keep, int keep_stride, unsigned long long *mask,
                                 int *keep_rank, int *keep_count, cudaStream_t stream) {
   if (S <= 0) return SFOD_OK;
   if (max_len > 0) {
     bool launched = false;
-    int rc = cls ? launch_lazy_t<true>(boxes, cls, segs, S, max_len, thr, max_keep, keep_stride, keep_rank, keep_count, stream, &launched)
+    int rc = cls ? launch_deferred_t<true>(boxes, cls, segs, S, max_len, thr, max_keep, keep_stride, keep_rank, keep_count, stream, &launched)
+                 : launch_deferred_t<false>(boxes, cls, segs, S, max_len, thr, max_keep, keep_stride, keep_rank, keep_count, stream, &launched);
+    if (rc) return rc;
+    if (launched) return SFOD_OK;
+    rc = cls ? launch_lazy_t<true>(boxes, cls, segs, S, max_len, thr, max_keep, keep_stride, keep_rank, keep_count, stream, &launched)
                  : launch_lazy_t<false>(boxes, cls, segs, S, max_len, thr, max_keep, keep_stride, keep_rank, keep_count, stream, &launched);
     if (rc) return rc;
     if (launched) return SFOD_OK;
