@@ -203,6 +203,13 @@ __device__ __forceinline__ bool lazy_iou_sup(const float4 a, const float aa, con
   const float inter = __fmul_rn(w, h);
   if (inter > 0.0f || neg_thr) {  // inter == 0 => iou is 0, -0 or NaN: never > thr for thr >= 0
     const float uni = __fsub_rn(__fadd_rn(aa, ab), inter);
+    // fl(inter / uni) > thr is decided without the division unless inter is within 2^-19 of thr * uni: the quotient's
+    // rounding (2^-24) and that of the product cannot move a comparison that far.  Ordinary magnitudes only.
+    const float pr = __fmul_rn(thr, uni);
+    if (pr > 1e-30f && pr < 1e30f) {
+      if (inter > __fmul_rn(pr, 1.000002f)) return true;
+      if (inter < __fmul_rn(pr, 0.999998f)) return false;
+    }
     return __fdiv_rn(inter, uni) > thr;
   }
   return false;
@@ -381,27 +388,54 @@ __global__ void __launch_bounds__(kLazyThreads) nms_lazy_kernel(const float4 *__
 // exactly when the CTA becomes owner again.  The pair set evaluated for a visited box is the one of the lazy kernel
 // (first hit ends the box); unvisited boxes cost nothing; the step itself is the critical path (apply the newest list to
 // one tile, fixed-point resolve, push, split cluster barrier).  Same arithmetic, tie order and results.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+// one arrival on the barrier at the same shared-memory offset of CTA `rank`; release at cluster scope: the remote stores
+// this thread issued before it are visible to whoever observes the completed phase with acquire.cluster
+__device__ __forceinline__ void mbar_arrive_remote(unsigned long long *bar, unsigned rank) {
+  unsigned remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
 __host__ __device__ inline size_t deferred_smem_bytes(int own_cap_tiles, int cap) {
   // own boxes (16 B) + kept boxes (16 B) | suppressor words, removed words (8 B) | own areas, classes, kept areas, classes, counts
   return (size_t)own_cap_tiles * 64 * 16 + (size_t)cap * 16 + (size_t)own_cap_tiles * 64 * 8 + (((size_t)own_cap_tiles * 8 + 15) & ~(size_t)15) +
-         (size_t)own_cap_tiles * 64 * 8 + (size_t)cap * 8 + 16;
+         (size_t)own_cap_tiles * 64 * 8 + (size_t)cap * 8;
+}
+// + one arrival barrier and one count per tile of the segment
+__host__ __device__ inline size_t deferred_smem_bytes(int own_cap_tiles, int cap, int wcap) {
+  return deferred_smem_bytes(own_cap_tiles, cap) + (size_t)wcap * 12 + 16;
 }
 
 template <bool kClassAware>
 __global__ void __launch_bounds__(kLazyThreads) nms_deferred_kernel(const float4 *__restrict__ boxes, const int *__restrict__ cls,
                                                                     const Seg *__restrict__ segs, float thr, int max_keep,
-                                                                    int keep_stride, int own_cap, int cap,
+                                                                    int keep_stride, int own_cap, int cap, int wcap,
                                                                     int *__restrict__ keep_rank, int *__restrict__ keep_count) {
   extern __shared__ __align__(16) unsigned char lazy_raw[];
   float4 *ob = reinterpret_cast<float4 *>(lazy_raw);
   float4 *KB = ob + (size_t)own_cap * 64;
   unsigned long long *col = reinterpret_cast<unsigned long long *>(KB + cap);
   unsigned long long *removed = col + (size_t)own_cap * 64;
-  float *oa = reinterpret_cast<float *>(removed + ((own_cap + 1) & ~1));
+  unsigned long long *mbar = removed + ((own_cap + 1) & ~1);   // mbar[t]: "the kept list of tile t has landed in this CTA"
+  float *oa = reinterpret_cast<float *>(mbar + wcap);
   int *oc = reinterpret_cast<int *>(oa + (size_t)own_cap * 64);
   float *KA = reinterpret_cast<float *>(oc + (size_t)own_cap * 64);
   int *KC = reinterpret_cast<int *>(KA + cap);
-  int *cnt = KC + cap;   // 3 slots
+  int *cnt = KC + cap;   // cnt[t]: survivors of tile t
 
   const int CL = (int)cluster_nctarank(), c = (int)cluster_ctarank();
   const int s = blockIdx.y;
@@ -446,7 +480,6 @@ __global__ void __launch_bounds__(kLazyThreads) nms_deferred_kernel(const float4
 
   // Resolve own tile q (global tile t) and append its survivors to the kept list of EVERY CTA at [base, base + nk).
   auto resolve_publish = [&](int q, int t, int base) {
-    const int slot = t % 3;
     if (warp == 0) {
       const unsigned long long alive = ~removed[q];
       const unsigned long long c0 = col[q * 64 + lane], c1 = col[q * 64 + 32 + lane];
@@ -477,20 +510,22 @@ __global__ void __launch_bounds__(kLazyThreads) nms_deferred_kernel(const float4
         out[pos] = t * 64 + 32 + lane;
         KB[pos] = ob[q * 64 + 32 + lane]; KA[pos] = oa[q * 64 + 32 + lane]; KC[pos] = oc[q * 64 + 32 + lane];
       }
-      if (lane == 0) cnt[slot] = nk;
+      if (lane == 0) cnt[t] = nk;
     }
     __syncthreads();
-    const int kc = cnt[slot];
-    for (int p = warp; p < CL; p += kLazyThreads / 32) {   // one warp per peer: push through DSMEM
-      if (p == c) continue;
-      float4 *rKB = cluster_map(KB, (unsigned)p);
-      float *rKA = cluster_map(KA, (unsigned)p);
-      int *rKC = cluster_map(KC, (unsigned)p);
-      for (int k = lane; k < kc; k += 32) {
-        rKB[base + k] = KB[base + k]; rKA[base + k] = KA[base + k];
-        if (kClassAware) rKC[base + k] = KC[base + k];
+    const int kc = cnt[t];
+    for (int p = warp; p < CL; p += kLazyThreads / 32) {   // one warp per CTA of the cluster: push through DSMEM, then signal
+      if (p != c) {
+        float4 *rKB = cluster_map(KB, (unsigned)p);
+        float *rKA = cluster_map(KA, (unsigned)p);
+        int *rKC = cluster_map(KC, (unsigned)p);
+        for (int k = lane; k < kc; k += 32) {
+          rKB[base + k] = KB[base + k]; rKA[base + k] = KA[base + k];
+          if (kClassAware) rKC[base + k] = KC[base + k];
+        }
+        if (lane == 0) cluster_map(cnt, (unsigned)p)[t] = kc;
       }
-      if (lane == 0) cluster_map(cnt, (unsigned)p)[slot] = kc;
+      mbar_arrive_remote(&mbar[t], (unsigned)p);   // all 32 lanes: each releases its own stores (barrier count 32)
     }
   };
 
@@ -509,31 +544,37 @@ __global__ void __launch_bounds__(kLazyThreads) nms_deferred_kernel(const float4
     }
   };
 
+  for (int t = tid; t < W; t += kLazyThreads) mbar_init(&mbar[t], 32u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  cluster_arrive(); cluster_wait();   // every CTA's barriers exist before anybody signals them
+
+  // No cluster-wide barrier per step: the owner of tile t pushes its list and signals mbar[t] in every CTA (one-way
+  // DSMEM latency); nothing is ever reused (lists append, one barrier and one count per tile), so no flow control either.
   int total = 0;
   int next_q = 0;   // next own tile to resolve (global tile next_q * CL + c)
   int done = 0;     // kept entries [0, done) have been applied to it
   if (c == 0 && W > 0) { resolve_publish(0, 0, 0); next_q = 1; }
-  cluster_arrive(); cluster_wait();
+  const int cl_mask = CL - 1, cl_shift = __ffs(CL) - 1;   // CL is a power of two
   for (int t = 0; t < W; ++t) {
-    const int new_total = total + cnt[t % 3];
+    if (warp == 0) mbar_wait(&mbar[t], 0u);   // one warp polls, the others sleep at the barrier
+    __syncthreads();
+    const int new_total = total + cnt[t];
     const bool finished = (new_total >= max_keep) || (t + 1 >= W);
-    if (!finished && c == (t + 1) % CL) {   // owner of the next tile: finish its backlog + the newest list, resolve, publish
+    if (!finished && c == ((t + 1) & cl_mask)) {   // owner of the next tile: finish its backlog + the newest list, resolve, publish
       apply(next_q, done, new_total);
       __syncthreads();
       resolve_publish(next_q, t + 1, new_total);
       ++next_q; done = 0;
     }
-    cluster_arrive();
     if (!finished && next_q < own_tiles) {   // work ahead on the next own tile: a share of the backlog per step
-      const int turn = next_q * CL + c - 1;  // loop iteration at which this CTA resolves it
+      const int turn = (next_q << cl_shift) + c - 1;   // loop iteration at which this CTA resolves it
       const int steps_left = max(1, turn - t);
-      const int avail = new_total - done;    // the newest list is complete in this CTA's copy (barrier above)
-      int chunk = (avail + steps_left - 1) / steps_left;
+      const int avail = new_total - done;    // the newest list is complete in this CTA's copy (barrier wait above)
+      int chunk = (int)(__fdividef((float)avail, (float)steps_left)) + 1;   // ~ceil(avail / steps_left): a pacing heuristic only
       chunk = min(avail, (chunk + 15) & ~15);
       apply(next_q, done, done + chunk);
       done += chunk;
     }
-    cluster_wait();
     total = new_total;
     if (finished) break;
   }
@@ -648,7 +689,8 @@ static inline int launch_deferred_t(const float4 *boxes, const int *cls, const S
   }
   int cap = max_keep < max_len ? max_keep : max_len;   // the kept list never grows beyond min(max_keep, segment length)
   cap = (cap + 3) & ~3; if (cap < 4) cap = 4;
-  const size_t smem = deferred_smem_bytes(own_cap, cap);
+  const int wcap = (max_len + 63) / 64;
+  const size_t smem = deferred_smem_bytes(own_cap, cap, wcap);
   if (smem > 200 * 1024) return SFOD_OK;   // kept list too long for shared memory: caller uses the lazy-row kernel
   auto kern = nms_deferred_kernel<kCls>;
   cudaLaunchConfig_t cfg = {};
@@ -659,7 +701,7 @@ static inline int launch_deferred_t(const float4 *boxes, const int *cls, const S
   cfg.attrs = attr; cfg.numAttrs = 1;
   float thr_f = (float)thr;                                  // largest float <= thr (see lazy_iou_sup)
   if ((double)thr_f > thr) thr_f = nextafterf(thr_f, -INFINITY);
-  if (cudaLaunchKernelEx(&cfg, kern, boxes, cls, segs, thr_f, max_keep, keep_stride, own_cap, cap, keep_rank, keep_count) != cudaSuccess) {
+  if (cudaLaunchKernelEx(&cfg, kern, boxes, cls, segs, thr_f, max_keep, keep_stride, own_cap, cap, wcap, keep_rank, keep_count) != cudaSuccess) {
     (void)cudaGetLastError();
     return SFOD_OK;
   }
