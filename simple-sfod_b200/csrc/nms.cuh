@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(kLazyThreads) nms_deferred_kernel(const float4
     }
     if (!finished && next_q < own_tiles) {   // work ahead on the next own tile: a share of the backlog per step
       const int turn = (next_q << cl_shift) + c - 1;   // loop iteration at which this CTA resolves it
-      const int steps_left = max(1, turn - t);
+      const int steps_left = max(1, turn - t - 1);   // be done one step early: the step before the turn only sees the newest list
       const int avail = new_total - done;    // the newest list is complete in this CTA's copy (barrier wait above)
       int chunk = (int)(__fdividef((float)avail, (float)steps_left)) + 1;   // ~ceil(avail / steps_left): a pacing heuristic only
       chunk = min(avail, (chunk + 15) & ~15);
