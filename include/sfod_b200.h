@@ -226,7 +226,9 @@ int sfod_class_histogram(const float *values, const int64_t *classes, const int3
  *   caller all-reduces (together with the element count) before phase 2.
  * Phase 2 (sfod_bn_finalize_apply): mean, biased var (fp64), running stats
  *   r = (1-m) r + m stat with the unbiased variance n/(n-1), num_batches_tracked += 1,
- *   y = (x-mean)*invstd*weight+bias (optionally fused ReLU); y may alias x. */
+ *   y = (x-mean)*invstd*weight+bias (optionally fused ReLU); y may alias x.
+ * stats_dev must hold sfod_bn_stats_bytes(C) bytes: the (C,2) totals, then scratch of the
+ * library (scale/shift of phase 2, replicated partial totals of the channels-last pass). */
 size_t sfod_bn_stats_bytes(int C);
 /* pre_bias (C floats, may be NULL): a per-channel bias added to x before everything else -- the bias of the
  * convolution that feeds the BatchNorm (reference daod/modeling/meta_arch/vgg.py:17-19: Conv2d(bias=True) -> BatchNorm2d),

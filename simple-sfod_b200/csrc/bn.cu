@@ -13,6 +13,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kChunk = 16384;  // elements of one (n, c) plane per CTA: 64 per thread
+constexpr int kStatReplicas = 16;  // copies of the (sum, sum^2) totals the NHWC statistics kernel spreads its atomics over
 
 __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
@@ -68,15 +69,19 @@ __global__ void __launch_bounds__(kThreads) bn_stats_nchw_kernel(const float *__
 }
 
 // NHWC: x viewed as (M = N*HW rows, C columns).  A CTA covers `cols` float4 column groups x `rowlanes`
-// row lanes; each thread walks up to 64 rows with 128-bit loads (4 channels per load).
-__global__ void __launch_bounds__(kThreads) bn_stats_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
-                                                                 long long M, int C, int cols, int rowlanes,
-                                                                 double *__restrict__ stats) {
-  extern __shared__ double sred[];  // rowlanes * cols * 8 doubles
+// row lanes; each thread walks nrows (a multiple of 4, <= 64) rows with 128-bit loads (4 channels per load).
+__global__ void __launch_bounds__(kThreads, 5) bn_stats_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
+                                                                 long long M, int C, int cols, int rowlanes, int nrows,
+                                                                 double *__restrict__ stats_replicas) {
+  // fp64 atomics on one address are serialised by the L2 (~65 cycles each): with thousands of CTAs flushing 8 values per
+  // column group into the same 2C totals that alone would cost as much as reading x.  CTAs therefore flush into one of
+  // kStatReplicas copies (bn_fold_replicas_kernel adds them up afterwards).
+  double *stats = stats_replicas + (size_t)(blockIdx.x % kStatReplicas) * 2 * C;
+  extern __shared__ double sred[];  // rowlanes * cols * 9 doubles, then cols * 9 doubles, then cols * 4 floats
   const int G = C >> 2;
   const int col = threadIdx.x % cols, rl = threadIdx.x / cols;
   const int g = blockIdx.y * cols + col;
-  const long long row0 = (long long)blockIdx.x * rowlanes * 64;
+  const long long row0 = (long long)blockIdx.x * rowlanes * nrows;   // nrows <= 64 rows per thread
   const bool on = rl < rowlanes && g < G;
   float4 K = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 s = K, s2 = K, pb = K;
@@ -86,37 +91,58 @@ __global__ void __launch_bounds__(kThreads) bn_stats_nhwc_kernel(const float *__
     K = __ldg(reinterpret_cast<const float4 *>(x) + g);  // pivot: row 0
     K = make_float4(K.x + pb.x, K.y + pb.y, K.z + pb.z, K.w + pb.w);
     const float4 *p = reinterpret_cast<const float4 *>(x) + g;
-#pragma unroll 4
-    for (int i = 0; i < 64; ++i) {
-      const long long r = row0 + (long long)i * rowlanes + rl;
-      if (r < M) {
-        const float4 v = __ldg(p + (size_t)r * G);
-        const float d0 = (v.x + pb.x) - K.x, d1 = (v.y + pb.y) - K.y, d2 = (v.z + pb.z) - K.z, d3 = (v.w + pb.w) - K.w;
+    // batches of 4 rows: the four 128-bit loads are issued before any of them is consumed (bytes in flight, not
+    // occupancy, decide the bandwidth of this kernel); rows beyond M load row M-1 and are masked out
+    for (int i = 0; i < nrows; i += 4) {
+      float4 v[4];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long r = row0 + (long long)(i + j) * rowlanes + rl;
+        ok[j] = r < M;
+        v[j] = __ldg(p + (size_t)(ok[j] ? r : M - 1) * G);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float m = ok[j] ? 1.0f : 0.0f;
+        const float d0 = m * ((v[j].x + pb.x) - K.x), d1 = m * ((v[j].y + pb.y) - K.y);
+        const float d2 = m * ((v[j].z + pb.z) - K.z), d3 = m * ((v[j].w + pb.w) - K.w);
         s.x += d0; s.y += d1; s.z += d2; s.w += d3;
         s2.x = fmaf(d0, d0, s2.x); s2.y = fmaf(d1, d1, s2.y); s2.z = fmaf(d2, d2, s2.z); s2.w = fmaf(d3, d3, s2.w);
-        ++cnt;
+        cnt += ok[j] ? 1 : 0;
       }
     }
   }
   double *mine = sred + ((size_t)rl * cols + col) * 9;
+  double *tot = sred + (size_t)rowlanes * cols * 9;              // [cols][9]
+  float *piv = reinterpret_cast<float *>(tot + (size_t)cols * 9);   // [cols][4]
   if (rl < rowlanes) {
     mine[0] = s.x; mine[1] = s.y; mine[2] = s.z; mine[3] = s.w;
     mine[4] = s2.x; mine[5] = s2.y; mine[6] = s2.z; mine[7] = s2.w; mine[8] = (double)cnt;
+    if (rl == 0) { piv[4 * col] = K.x; piv[4 * col + 1] = K.y; piv[4 * col + 2] = K.z; piv[4 * col + 3] = K.w; }
   }
   __syncthreads();
-  if (rl == 0 && g < G) {
-    double a[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) a[k] = 0.0;
-    for (int q = 0; q < rowlanes; ++q) {
-      const double *o = sred + ((size_t)q * cols + col) * 9;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) a[k] += o[k];
-    }
-    const double Kd[4] = {(double)K.x, (double)K.y, (double)K.z, (double)K.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) flush_channel(stats, 4 * g + k, a[k], a[4 + k], a[8], Kd[k]);
+  for (int item = threadIdx.x; item < cols * 9; item += kThreads) {   // (column group, value) pairs in parallel
+    double t = 0.0;
+    for (int q = 0; q < rowlanes; ++q) t += sred[(size_t)q * cols * 9 + item];
+    tot[item] = t;
   }
+  __syncthreads();
+  if (threadIdx.x < cols * 4) {   // one thread per channel of the CTA
+    const int cl = threadIdx.x >> 2, kk = threadIdx.x & 3;
+    const int gg = blockIdx.y * cols + cl;
+    if (gg < G)
+      flush_channel(stats, 4 * gg + kk, tot[cl * 9 + kk], tot[cl * 9 + 4 + kk], tot[cl * 9 + 8], (double)piv[4 * cl + kk]);
+  }
+}
+
+__global__ void __launch_bounds__(128) bn_fold_replicas_kernel(const double *__restrict__ replicas, int C, double *__restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * C) return;
+  double t = 0.0;
+#pragma unroll
+  for (int r = 0; r < kStatReplicas; ++r) t += replicas[(size_t)r * 2 * C + i];
+  stats[i] = t;
 }
 
 // scalar fallback for NHWC with C % 4 != 0 (not used by any shipped config)
@@ -291,9 +317,11 @@ __global__ void __launch_bounds__(kThreads) bn_apply_nhwc_scalar_kernel(const fl
 
 }  // namespace
 
-SFOD_API size_t sfod_bn_stats_bytes(int C) { return C > 0 ? sfod_align_up((size_t)C * 4 * sizeof(double), 256) : 256; }
+SFOD_API size_t sfod_bn_stats_bytes(int C) {
+  return C > 0 ? sfod_align_up((size_t)C * (4 + 2 * kStatReplicas) * sizeof(double), 256) : 256;
+}
 // stats_dev layout: [0, 2C) doubles = (sum x, sum x^2) per channel (the all-reduce payload);
-// [2C, 4C) reused by phase 2 as float scale/shift scratch.
+// [2C, 4C) reused by phase 2 as float scale/shift scratch; [4C, 4C + 2C * kStatReplicas) replica totals of the NHWC pass.
 
 SFOD_API int sfod_bn_partial_stats(const float *x, const float *pre_bias, int layout, int N, int C, int64_t HW, double *stats_dev,
                                    sfod_stream_t stream) {
@@ -322,9 +350,16 @@ SFOD_API int sfod_bn_partial_stats(const float *x, const float *pre_bias, int la
   const int G = C >> 2;
   const int cols = G < 64 ? G : 64;
   const int rowlanes = kThreads / cols;
-  dim3 grid((unsigned)((M + (long long)rowlanes * 64 - 1) / ((long long)rowlanes * 64)), (unsigned)((G + cols - 1) / cols));
-  const size_t smem = (size_t)rowlanes * cols * 9 * sizeof(double);
-  bn_stats_nhwc_kernel<<<grid, kThreads, smem, st>>>(x, pre_bias, M, C, cols, rowlanes, stats_dev);
+  const long long gy = (G + cols - 1) / cols;
+  int nrows = 64;   // rows per thread: fewer for small maps so that the layer still fills the machine (>= 16 CTAs per SM)
+  while (nrows > 8 && ((M + (long long)rowlanes * nrows - 1) / ((long long)rowlanes * nrows)) * gy < (long long)SFOD_NUM_SMS * 16) nrows >>= 1;
+  dim3 grid((unsigned)((M + (long long)rowlanes * nrows - 1) / ((long long)rowlanes * nrows)), (unsigned)gy);
+  const size_t smem = ((size_t)rowlanes * cols * 9 + (size_t)cols * 9) * sizeof(double) + (size_t)cols * 4 * sizeof(float);
+  double *replicas = stats_dev + 4 * (size_t)C;
+  SFOD_CUDA_TRY(cudaMemsetAsync(replicas, 0, (size_t)C * 2 * kStatReplicas * sizeof(double), st));   // totals were zeroed above
+  bn_stats_nhwc_kernel<<<grid, kThreads, smem, st>>>(x, pre_bias, M, C, cols, rowlanes, nrows, replicas);
+  SFOD_LAUNCH_CHECK();
+  bn_fold_replicas_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(replicas, C, stats_dev);
   SFOD_LAUNCH_CHECK();
   return SFOD_OK;
 }
