@@ -876,14 +876,19 @@ __global__ void __launch_bounds__(kSepThreads, 4) roi_align_bwd_sep_kernel(const
   RoiGeom g = roi_geometry(rois + 5 * (size_t)r, scale, aligned, kPH, kPW, sampling_ratio);
   if (g.n < 0 || g.n >= N) return;
   const int nch = min(kCT, C - cbase);
-  // coalesced 128-bit staging of the contiguous (nch x 49) gradient tile
+  // asynchronous 128-bit staging of the contiguous (nch x 49) gradient tile: all ~25 copies of a thread are in flight at
+  // once and land while the tables are built
   {
     const float4 *src = reinterpret_cast<const float4 *>(grad_out + ((size_t)r * C + cbase) * kBins);
-    float4 *dst = reinterpret_cast<float4 *>(s.tile);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(s.tile);
     const int n4 = nch * kBins / 4;
-    for (int i = tid; i < n4; i += kSepThreads) dst[i] = __ldg(src + i);
+    for (int i = tid; i < n4; i += kSepThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  sep_build_tables(s, g, H, W);  // contains the barriers that also publish the tile
+  sep_build_tables(s, g, H, W);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();   // publishes the tile
   const int ymin = s.lim[0], ymax = s.lim[1], xmin = s.lim[2], xmax = s.lim[3];
   const int c0 = cbase + 2 * tid;
   if (c0 >= C || ymax < ymin || xmax < xmin) return;
