@@ -104,6 +104,40 @@ def test_nms_semantics_kats(ops, cuda_device):
         ops.nms(torch.zeros(3, 4), torch.zeros(3), 0.5)  # CPU tensors: no fallback
 
 
+@pytest.mark.parametrize("thr,num,den", [(0.5, 1.0, 3.0), (0.7, 3.0, 17.0)])
+def test_nms_decisions_at_the_threshold(ops, cuda_device, thr, num, den):
+    """Pairs of equal boxes shifted by w * num / den have IoU = (w - dx) / (w + dx) = thr in exact arithmetic; in fp32 they
+    land a few ulps on either side of it.  The kernels decide `fl(inter / union) > thr` without dividing when inter is
+    far from thr * union and with the exact division otherwise: the keep set must still be torchvision's, pair by pair."""
+    g = torch.Generator().manual_seed(77)
+    P = 3000
+    w = torch.rand(P, generator=g) * 200 + 10
+    h = torch.rand(P, generator=g) * 200 + 10
+    x0 = torch.rand(P, generator=g) * 50
+    y0 = torch.rand(P, generator=g) * 50
+    dx = w * num / den
+    # second half: just OUTSIDE the band in which the exact division runs (relative distance 2e-6 .. 3e-5, both sides)
+    eps = 10.0 ** (torch.rand(P, generator=g) * 1.2 - 5.7) * (torch.randint(0, 2, (P,), generator=g) * 2 - 1)
+    eps[: P // 2] = 0.0
+    dx = dx * (1.0 + eps)
+    a = torch.stack([x0, y0, x0 + w, y0 + h], 1)
+    b = torch.stack([x0 + dx, y0, x0 + dx + w, y0 + h], 1)
+    boxes = torch.cat([a, b]).contiguous()
+    scores = torch.cat([torch.full((P,), 0.9), torch.full((P,), 0.8)]) + torch.arange(2 * P) * 1e-6
+    idx = torch.cat([torch.arange(P), torch.arange(P)])
+    ref = o.batched_nms(boxes, scores, idx, thr)
+    suppressed = 2 * P - ref.numel()
+    assert 0.05 * P < suppressed < 0.95 * P, f"the construction must straddle the threshold ({suppressed} of {P} pairs suppressed)"
+    got = ops.batched_nms(boxes.to(cuda_device), scores.to(cuda_device), idx.to(cuda_device), thr).cpu()
+    assert torch.equal(got, ref)
+    # the same pairs as one segment each of the plain operator (class-unaware kernels): shift pairs apart instead
+    sub = slice(0, 400)
+    off = (torch.arange(400, dtype=torch.float32) * 512.0)[:, None] * torch.tensor([1.0, 0.0, 1.0, 0.0])
+    bb = torch.cat([a[sub] + off, b[sub] + off]).contiguous()
+    ss = torch.cat([scores[:P][sub], scores[P:][sub]])
+    assert torch.equal(ops.nms(bb.to(cuda_device), ss.to(cuda_device), thr).cpu(), torchvision.ops.nms(bb, ss, thr))
+
+
 @pytest.mark.parametrize("n", [900, 1000, 1001, 6000])
 def test_batched_nms_matches_torchvision_cpu_strategy(ops, cuda_device, n):
     """n <= 1000 -> coordinate trick arithmetic, above -> per-class."""
