@@ -217,6 +217,24 @@ int sfod_class_histogram(const float *values, const int64_t *classes, const int3
                          float thres, int64_t *hist_dev, sfod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Fused pairwise_iou + Matcher.  Replaces, per image,
+ * detectron2.structures.pairwise_iou followed by detectron2.modeling.matcher.Matcher.__call__ as
+ * reached from RPN.label_and_sample_anchors (called by daod/modeling/proposal_generator/rpn.py:45)
+ * and label_and_sample_proposals
+ * (daod/modeling/roi_heads/source_free_adaptive_teacher_roi_heads.py:165-215).
+ * gt_boxes (M,4), boxes (N,4) xyxy fp32 on the device; thresholds (num_thresholds ascending
+ * floats) and labels (num_thresholds + 1 ints in {-1,0,1}) on the HOST: label[k] is given to
+ * predictions whose best IoU v satisfies thresholds[k-1] <= v < thresholds[k].
+ * matches (N) int64 = index of the first gt with the maximal IoU (0 when M == 0); match_labels
+ * (N) int8; matched_vals (N) float or NULL.  allow_low_quality != 0 applies
+ * Matcher.set_low_quality_matches_ literally: every prediction whose IoU with some gt equals
+ * that gt's maximum over all predictions gets label 1.  The M x N matrix is never stored. */
+size_t sfod_iou_match_workspace_bytes(int M);
+int sfod_iou_match(const float *gt_boxes, const float *boxes, int M, int N, const float *thresholds, const int *labels,
+                   int num_thresholds, int allow_low_quality, int64_t *matches, int8_t *match_labels, float *matched_vals,
+                   void *workspace, size_t workspace_bytes, sfod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * BatchNorm train-mode forward / AdaBN statistic recomputation.  Replaces the
  * nn.BatchNorm2d train-mode forwards driven by test_refinement
  * (daod/engine/trainers/base.py:274-299, after reset_bn_stats :318-323) and by the teacher

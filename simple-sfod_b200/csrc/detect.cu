@@ -6,6 +6,7 @@
 #include "nms.cuh"
 #include "rpn.cuh"
 #include "frcnn.cuh"
+#include "match.cuh"
 
 // ===================================================================== generic torchvision-style NMS
 namespace {
@@ -419,4 +420,43 @@ SFOD_API const char *sfod_status_string(int status) {
     case SFOD_ERR_ALIGNMENT: return "pointer not 16-byte aligned";
     default: return status >= SFOD_ERR_CUDA_BASE ? cudaGetErrorString((cudaError_t)(status - SFOD_ERR_CUDA_BASE)) : "unknown";
   }
+}
+
+// ===================================================================== fused pairwise_iou + Matcher
+SFOD_API size_t sfod_iou_match_workspace_bytes(int M) { return sfod_align_up((size_t)(M > 0 ? M : 1) * sizeof(int), 256); }
+
+SFOD_API int sfod_iou_match(const float *gt_boxes, const float *boxes, int M, int N, const float *thresholds, const int *labels,
+                            int num_thresholds, int allow_low_quality, int64_t *matches, int8_t *match_labels, float *matched_vals,
+                            void *workspace, size_t workspace_bytes, sfod_stream_t stream) {
+  if (M < 0 || N < 0 || num_thresholds < 0 || num_thresholds > matchk::kMaxThresholds || !labels) return SFOD_ERR_INVALID_ARG;
+  if (num_thresholds > 0 && !thresholds) return SFOD_ERR_INVALID_ARG;
+  if (N == 0) return SFOD_OK;
+  if (!boxes || !matches || !match_labels || (M > 0 && !gt_boxes)) return SFOD_ERR_INVALID_ARG;
+  if (!sfod_aligned16(boxes) || (M > 0 && !sfod_aligned16(gt_boxes))) return SFOD_ERR_ALIGNMENT;
+  for (int q = 1; q < num_thresholds; ++q)
+    if (thresholds[q] < thresholds[q - 1]) return SFOD_ERR_INVALID_ARG;
+  cudaStream_t st = sfod_cu(stream);
+  matchk::Thresholds th;
+  th.count = num_thresholds;
+  for (int q = 0; q < matchk::kMaxThresholds; ++q) th.t[q] = q < num_thresholds ? thresholds[q] : 0.f;
+  for (int q = 0; q <= matchk::kMaxThresholds; ++q) th.label[q] = q <= num_thresholds ? labels[q] : 0;
+  const bool lowq = allow_low_quality && M > 0;
+  int *gt_max = nullptr;
+  if (lowq) {
+    if (!workspace || workspace_bytes < (size_t)M * sizeof(int)) return SFOD_ERR_WORKSPACE_TOO_SMALL;
+    gt_max = static_cast<int *>(workspace);
+    SFOD_CUDA_TRY(cudaMemsetAsync(gt_max, 0, (size_t)M * sizeof(int), st));
+  }
+  const unsigned grid = (unsigned)((N + matchk::kThreads - 1) / matchk::kThreads);
+  matchk::match_kernel<<<grid, matchk::kThreads, 0, st>>>(reinterpret_cast<const float4 *>(gt_boxes), reinterpret_cast<const float4 *>(boxes),
+                                                          M, N, th, reinterpret_cast<long long *>(matches),
+                                                          reinterpret_cast<signed char *>(match_labels), matched_vals, gt_max);
+  SFOD_LAUNCH_CHECK();
+  if (lowq) {
+    matchk::low_quality_kernel<<<grid, matchk::kThreads, 0, st>>>(reinterpret_cast<const float4 *>(gt_boxes),
+                                                                  reinterpret_cast<const float4 *>(boxes), M, N, gt_max,
+                                                                  reinterpret_cast<signed char *>(match_labels));
+    SFOD_LAUNCH_CHECK();
+  }
+  return SFOD_OK;
 }

@@ -45,6 +45,17 @@ class Matcher:
             self.set_low_quality_matches_(match_labels, match_quality_matrix)
         return matches, match_labels
 
+    def match_boxes(self, gt_boxes, boxes) -> Tuple[Tensor, Tensor]:
+        """``self(pairwise_iou(gt_boxes, boxes))`` for two ``Boxes``.  On CUDA tensors this is one fused native call
+        (``sfod_iou_match``: the M x N matrix is never stored and nothing synchronises); elsewhere the two torch steps."""
+        g, b = gt_boxes.tensor, boxes.tensor
+        if g.is_cuda and b.is_cuda:
+            from .. import ops
+            matches, match_labels, _ = ops.iou_match(g, b, self.thresholds[1:-1], self.labels, self.allow_low_quality_matches)
+            return matches, match_labels
+        from ..structures import pairwise_iou
+        return self(pairwise_iou(gt_boxes, boxes))
+
     def set_low_quality_matches_(self, match_labels: Tensor, match_quality_matrix: Tensor) -> None:
         highest_quality_foreach_gt, _ = match_quality_matrix.max(dim=1)
         _, pred_inds_with_highest_quality = nonzero_tuple(match_quality_matrix == highest_quality_foreach_gt[:, None])

@@ -152,8 +152,10 @@ class RPN(nn.Module):
         gt_boxes = [x.gt_boxes for x in gt_instances]
         gt_labels, matched_gt_boxes = [], []
         for gt_boxes_i in gt_boxes:
-            match_quality_matrix = pairwise_iou(gt_boxes_i, anchors)
-            matched_idxs, gt_labels_i = self.anchor_matcher(match_quality_matrix)
+            if hasattr(self.anchor_matcher, "match_boxes"):   # fused pairwise_iou + Matcher on the device
+                matched_idxs, gt_labels_i = self.anchor_matcher.match_boxes(gt_boxes_i, anchors)
+            else:
+                matched_idxs, gt_labels_i = self.anchor_matcher(pairwise_iou(gt_boxes_i, anchors))
             gt_labels_i = gt_labels_i.to(device=gt_boxes_i.device)
             if self.anchor_boundary_thresh >= 0:
                 raise NotImplementedError("RPN.BOUNDARY_THRESH >= 0 is not used by any shipped config")

@@ -142,8 +142,11 @@ class _StandardROIHeadsBase(nn.Module):
         proposals_with_gt, num_fg_samples, num_bg_samples = [], [], []
         for proposals_per_image, targets_per_image in zip(proposals, targets):
             has_gt = len(targets_per_image) > 0
-            match_quality_matrix = pairwise_iou(targets_per_image.gt_boxes, proposals_per_image.proposal_boxes)
-            matched_idxs, matched_labels = self.proposal_matcher(match_quality_matrix)
+            if hasattr(self.proposal_matcher, "match_boxes"):   # fused pairwise_iou + Matcher on the device
+                matched_idxs, matched_labels = self.proposal_matcher.match_boxes(targets_per_image.gt_boxes, proposals_per_image.proposal_boxes)
+            else:
+                matched_idxs, matched_labels = self.proposal_matcher(
+                    pairwise_iou(targets_per_image.gt_boxes, proposals_per_image.proposal_boxes))
             sampled_idxs, gt_classes = self._sample_proposals(matched_idxs, matched_labels, targets_per_image.gt_classes)
             proposals_per_image = proposals_per_image[sampled_idxs]
             proposals_per_image.gt_classes = gt_classes

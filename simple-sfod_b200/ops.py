@@ -364,6 +364,35 @@ def class_histogram(values: Tensor, classes: Tensor, counts: Tensor, num_classes
     return hist
 
 
+# ----------------------------------------------------------------------------------------------- box matching
+def iou_match(gt_boxes: Tensor, boxes: Tensor, thresholds: Sequence[float], labels: Sequence[int],
+              allow_low_quality_matches: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+    """Fused ``pairwise_iou(gt_boxes, boxes)`` + detectron2 ``Matcher(thresholds, labels, allow_low_quality_matches)``:
+    gt_boxes (M, 4), boxes (N, 4) -> (matches (N) int64, match_labels (N) int8, matched_vals (N) float32).
+    ``thresholds`` are the Matcher's inner thresholds (ascending), ``labels`` has one more entry."""
+    dev = _require_cuda(gt_boxes, boxes)
+    g, b = _f32c(gt_boxes).reshape(-1, 4), _f32c(boxes).reshape(-1, 4)
+    th = [float(t) for t in thresholds]
+    lb = [int(v) for v in labels]
+    if len(lb) != len(th) + 1 or any(v not in (-1, 0, 1) for v in lb):
+        raise ValueError("labels must hold len(thresholds) + 1 values from {-1, 0, 1}")
+    M, N = g.shape[0], b.shape[0]
+    matches = torch.empty((N,), dtype=torch.int64, device=dev)
+    mlabels = torch.empty((N,), dtype=torch.int8, device=dev)
+    vals = torch.empty((N,), dtype=torch.float32, device=dev)
+    if N == 0:
+        return matches, mlabels, vals
+    L = _lib.lib()
+    cth = (C.c_float * max(len(th), 1))(*th)
+    clb = (C.c_int * len(lb))(*lb)
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, "match", L.sfod_iou_match_workspace_bytes(M))
+        check(L.sfod_iou_match(g.data_ptr() if M else None, b.data_ptr(), M, N, cth, clb, len(th), int(bool(allow_low_quality_matches)),
+                               matches.data_ptr(), mlabels.data_ptr(), vals.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
+              "sfod_iou_match")
+    return matches, mlabels, vals
+
+
 # ----------------------------------------------------------------------------------------------- RPN selection
 def rpn_select(logits: Tensor, deltas: Tensor, image_sizes: Sequence[Tuple[int, int]], *, anchors: Optional[Tensor] = None,
                cell_anchors: Optional[Tensor] = None, feat_hw: Optional[Tuple[int, int]] = None, stride: int = 0,

@@ -510,3 +510,37 @@ def test_vgg_stage_fusion_matches_unfused_modules(cuda_device):
             _close(a, b, rtol=1e-4, atol_scale=1e-5)
         if k.endswith("num_batches_tracked"):
             assert a.item() == b.item() == 1
+
+
+# ------------------------------------------------------------------------------------------------ fused pairwise_iou + Matcher
+@pytest.mark.parametrize("M,N", [(0, 100), (1, 1), (5, 1000), (37, 9990), (600, 2000)])
+@pytest.mark.parametrize("cfg", [([0.3, 0.7], [0, -1, 1], True), ([0.5], [0, 1], False), ([0.5, 0.5], [0, -1, 1], True)],
+                         ids=["rpn", "roi_heads", "degenerate_interval"])
+def test_iou_match_equals_pairwise_iou_plus_matcher(ops, cuda_device, M, N, cfg):
+    """labels / matches are integers and must be bit-exact, the matched IoU value as well (same
+    separately rounded arithmetic as detectron2's pairwise_iou)."""
+    from sfod_b200.modeling.matcher import Matcher
+    from sfod_b200.structures import Boxes, pairwise_iou
+    thresholds, labels, lowq = cfg
+    g = torch.Generator().manual_seed(1000 + M + N)
+    def rand_boxes(n):
+        ctr = torch.rand(n, 2, generator=g) * torch.tensor([1200.0, 600.0])
+        wh = torch.rand(n, 2, generator=g) ** 2 * 400 + 2
+        return torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    gt, bx = rand_boxes(M), rand_boxes(N)
+    if M >= 5:
+        bx[: min(N, 50)] = gt[torch.randint(0, M, (min(N, 50),), generator=g)]          # exact copies: IoU 1 and ties between gts
+        gt[1] = gt[0]                                                                   # duplicate gt: first maximal index wins
+        gt[2] = torch.tensor([5000.0, 5000.0, 5010.0, 5010.0])                          # overlaps nothing: its maximum is 0
+        bx[-1] = torch.tensor([10.0, 10.0, 10.0, 30.0])                                 # degenerate prediction
+    m = Matcher(thresholds, labels, allow_low_quality_matches=lowq)
+    mqm = pairwise_iou(Boxes(gt), Boxes(bx))
+    ref_matches, ref_labels = m(mqm)
+    got_matches, got_labels, got_vals = ops.iou_match(gt.to(cuda_device), bx.to(cuda_device), thresholds, labels, lowq)
+    assert torch.equal(got_matches.cpu(), ref_matches)
+    assert torch.equal(got_labels.cpu(), ref_labels)
+    if M > 0:
+        assert torch.equal(got_vals.cpu(), mqm.max(dim=0).values)
+    # the Matcher method used by the plugins dispatches to the same call
+    mm, ml = m.match_boxes(Boxes(gt.to(cuda_device)), Boxes(bx.to(cuda_device)))
+    assert torch.equal(mm.cpu(), ref_matches) and torch.equal(ml.cpu(), ref_labels)
