@@ -534,8 +534,10 @@ def test_iou_match_equals_pairwise_iou_plus_matcher(ops, cuda_device, M, N, cfg)
         gt[2] = torch.tensor([5000.0, 5000.0, 5010.0, 5010.0])                          # overlaps nothing: its maximum is 0
         bx[-1] = torch.tensor([10.0, 10.0, 10.0, 30.0])                                 # degenerate prediction
     m = Matcher(thresholds, labels, allow_low_quality_matches=lowq)
-    mqm = pairwise_iou(Boxes(gt), Boxes(bx))
-    ref_matches, ref_labels = m(mqm)
+    mqm = o.pairwise_iou(gt, bx)                                   # the oracle's restatement (pinned against torchvision's Matcher)
+    ref_matches, ref_labels = o.matcher(mqm, thresholds, labels, lowq)
+    pm, pl = m(pairwise_iou(Boxes(gt), Boxes(bx)))                 # and the package's torch pair agree with it
+    assert torch.equal(pm, ref_matches) and torch.equal(pl, ref_labels)
     got_matches, got_labels, got_vals = ops.iou_match(gt.to(cuda_device), bx.to(cuda_device), thresholds, labels, lowq)
     assert torch.equal(got_matches.cpu(), ref_matches)
     assert torch.equal(got_labels.cpu(), ref_labels)
