@@ -139,13 +139,16 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float, seed: int = 1234
     step()
     first = time.perf_counter() - t0
     w_done = 1
+    per = first   # the first step pays for thread pools and primitive caches: size the sample by a warm step when one fits
     # bounded sample: shrink the number of executed steps if K+W steps would blow the wall-clock budget
-    w_run = max(0, min(warmup, int((budget_s * 0.25) // max(first, 1e-3))) - 1)
+    w_run = min(warmup - 1, max(1, int((budget_s * 0.25) // max(first, 1e-3)))) if (warmup > 1 and first < 0.4 * budget_s) else 0
     for _ in range(w_run):
+        tw = time.perf_counter()
         step()
+        per = time.perf_counter() - tw
         w_done += 1
     left = budget_s - (time.perf_counter() - t0)
-    k_run = max(1, min(steps, int(left // max(first, 1e-3))))
+    k_run = max(1, min(steps, int(left // max(per, 1e-3))))
     t1 = time.perf_counter()
     for _ in range(k_run):
         step()
@@ -414,7 +417,7 @@ def run_b200(args):
             "pseudo_labels_last_step": [len(p) for p in out[2]]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            _, info, _, _, _ = cpu_reference_run(1, 1, 40.0)
+            _, info, _, _, _ = cpu_reference_run(10, 2, 30.0)   # ~10-15 s of CPU work: a bounded sample of the same workload
             line["cpu_baseline"] = info
         except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
