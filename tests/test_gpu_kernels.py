@@ -245,6 +245,27 @@ def test_roi_align_backward(ops, cuda_device, layout):
     _close(xd2.grad, xr2.grad)
 
 
+@pytest.mark.parametrize("sr", [0, 2])
+def test_roi_align_backward_many_images(ops, cuda_device, sr):
+    """ROIs in any image order, an image without ROIs (its gradient must be all zeros), wide bins with a fixed sampling
+    ratio; NCHW and channels-last gradients agree."""
+    cfg = synth.V
+    N, R = 6, 600
+    x = synth.features(cfg, N, 61)
+    rois = synth.random_rois(N, R, 62)
+    rois[rois[:, 0] == 4, 0] = 2.0
+    g = torch.randn(R, cfg["C"], 7, 7, generator=torch.Generator().manual_seed(63))
+    xr = x.clone().requires_grad_(True)
+    torchvision.ops.roi_align(xr, rois, (7, 7), 1 / 32, sr, True).backward(g)
+    xd = x.to(cuda_device).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    ops.roi_align(xd, rois.to(cuda_device), (7, 7), 1 / 32, sr, True).backward(g.to(cuda_device))
+    _close(xd.grad.cpu(), xr.grad, rtol=1e-5, atol_scale=1e-5)
+    assert torch.count_nonzero(xd.grad[4]) == 0
+    xn = x.to(cuda_device).requires_grad_(True)                      # NCHW gradient: accumulated channels-last, transposed
+    ops.roi_align(xn, rois.to(cuda_device), (7, 7), 1 / 32, sr, True).backward(g.to(cuda_device))
+    _close(xn.grad.cpu(), xr.grad, rtol=1e-5, atol_scale=1e-5)
+
+
 def test_roi_pool_forward_backward(ops, cuda_device):
     cfg = synth.V
     N, R = 2, 256
