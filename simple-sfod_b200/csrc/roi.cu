@@ -236,14 +236,14 @@ __device__ __forceinline__ void sep_row_fma(float2 (&T)[kPW], const float *__res
 
 // ---- per-ROI table records (forward).  A small pre-kernel builds, for every ROI, the record the forward kernel needs:
 //   ints  [0..31]  lim: [0..1] ymin, ymax; [2..3] xmin, xmax; [4..10] / [11..17] first / last row of bin ph;
-//                       [18..24] first column of the compact window of bin pw; [25] widest bin window in columns
+//                       [18..24] first column of the compact window of bin pw; [25] window width of the ROI: 2, 3, 4, 6, 8
 //                       (kNXMax + 1 = use the dense column tables); [26] image index (-1: invalid -> zero output)
-//   floats [32..59] Bc[pw*kNXMax + j]: weight of column lim[18+pw] + j for bin pw (the nonzero run of B's row pw)
-//   floats [64..64+8H) Ad[y*8 + ph], ph < 7; word y*8 + 7 holds (first bin fed by row y) | (number of such bins << 8)
+//   floats [32..87] Bc[pw*kNXMax + j]: weight of column lim[18+pw] + j for bin pw (the nonzero run of B's row pw)
+//   floats [96..96+8H) Ad[y*8 + ph], ph < 7; word y*8 + 7 holds (first bin fed by row y) | (number of such bins << 8)
 // so that the persistent forward CTAs prefetch it with cp.async while they work on the previous ROI instead of spending
 // ~20 % of their life in a latency-bound prologue (ROI load from DRAM, table build by 14 threads, two barriers).
-constexpr int kNXMax = 4;                  // widest per-bin column window handled by the compact (sparse-in-x) forward
-constexpr int kRecHead = 64;
+constexpr int kNXMax = 8;                  // widest per-bin column window handled by the compact (sparse-in-x) forward
+constexpr int kRecHead = 96;               // 32 ints + 7 x 8 compact weights, padded
 __host__ __device__ inline int sep_rec_floats(int H) { return kRecHead + 8 * H; }
 
 __global__ void __launch_bounds__(128) roi_sep_tables_kernel(const float *__restrict__ rois, int R, int N, int H, int W, float scale,
@@ -276,17 +276,24 @@ __global__ void __launch_bounds__(128) roi_sep_tables_kernel(const float *__rest
     lim[4 + ph] = ymn; lim[11 + ph] = ymx;
   } else if (lane >= 8 && lane < 8 + kPW) {
     const int pw = lane - 8;
-    const float inv = g.gw > 0 ? __fdiv_rn(1.0f, (float)g.gw) : 0.f;
     for (int ix = 0; ix < g.gw; ++ix) {
       int lo, hi; float l, h;
       if (!bilinear_1d(sample_coord(g.sw, pw, g.bw, ix, g.gw), W, lo, hi, l, h)) continue;
       xmn = min(xmn, lo); xmx = max(xmx, hi);
     }
-    // compact window [x0, x0 + kNXMax) kept inside the row; it covers [xmn, xmx] whenever the bin is narrow enough
-    const int x0 = xmx >= 0 ? max(0, min(xmn, W - kNXMax)) : 0;
+  }
+  // window width of the ROI = widest bin, rounded up to a width the forward kernels are instantiated for
+  const int bin_w = (lane >= 8 && lane < 8 + kPW && xmx >= 0) ? xmx - xmn + 1 : 0;
+  const int wmax = __reduce_max_sync(0xFFFFFFFFu, bin_w);
+  nx = wmax <= 2 ? 2 : wmax <= 3 ? 3 : wmax <= 4 ? 4 : wmax <= 6 ? 6 : wmax <= kNXMax ? kNXMax : kNXMax + 1;
+  if (nx > W) nx = kNXMax + 1;   // map narrower than the window: dense tables
+  if (lane >= 8 && lane < 8 + kPW) {
+    const int pw = lane - 8;
+    const float inv = g.gw > 0 ? __fdiv_rn(1.0f, (float)g.gw) : 0.f;
+    // compact window [x0, x0 + nx) kept inside the row; it covers [xmn, xmx] because the bin is at most nx wide
+    const int x0 = (xmx >= 0 && nx <= kNXMax) ? max(0, min(xmn, W - nx)) : 0;
     lim[18 + pw] = x0;
-    if (xmx >= 0) nx = (W >= kNXMax && xmx - x0 + 1 <= kNXMax) ? xmx - x0 + 1 : kNXMax + 1;
-    if (nx >= 1 && nx <= kNXMax) {
+    if (nx <= kNXMax) {
       for (int ix = 0; ix < g.gw; ++ix) {   // same sample order as the dense table => identical sums
         int lo, hi; float l, h;
         if (!bilinear_1d(sample_coord(g.sw, pw, g.bw, ix, g.gw), W, lo, hi, l, h)) continue;
@@ -296,7 +303,6 @@ __global__ void __launch_bounds__(128) roi_sep_tables_kernel(const float *__rest
   }
   ymn = __reduce_min_sync(0xFFFFFFFFu, ymn); ymx = __reduce_max_sync(0xFFFFFFFFu, ymx);
   xmn = __reduce_min_sync(0xFFFFFFFFu, xmn); xmx = __reduce_max_sync(0xFFFFFFFFu, xmx);
-  nx = __reduce_max_sync(0xFFFFFFFFu, nx);
   if (lane == 0) { lim[0] = ymn; lim[1] = ymx; lim[2] = xmn; lim[3] = xmx; lim[25] = nx; lim[26] = valid ? g.n : -1; }
   __syncwarp();
   for (int y = lane; y < H; y += 32) {   // bins fed by row y form a run [first, first + count): packed into the row's padding word
@@ -454,6 +460,50 @@ __device__ __forceinline__ void sep_fwd_pass_compact(const SepSmem &s, const flo
   sep_store_acc<PH0, NPH, PH0 == 0>(acc, t0, t1, half, active);
 }
 
+// Compact pass for wider windows (NX = 6 or 8, ROIs with a 5..7 sample grid per bin -- common on stride-16 maps): the
+// weights are shared-memory broadcasts and a bin's NX pixels are loaded and folded one bin at a time; still NX / (7 ns)
+// of the dense pass's FMAs and one LDS.32 instead of two LDS.128 per pixel load.
+template <int PH0, int NPH, int kC, int NX>
+__device__ __forceinline__ void sep_fwd_pass_compact_wide(const SepSmem &s, const float2 *__restrict__ fbase2, int C, int W,
+                                                          float *__restrict__ t0, float *__restrict__ t1, int half, bool active) {
+  const int cs2 = (kC ? kC : C) >> 1;
+  int y0 = s.lim[4 + PH0], y1 = s.lim[11 + PH0];
+#pragma unroll
+  for (int a = 1; a < NPH; ++a) { y0 = min(y0, s.lim[4 + PH0 + a]); y1 = max(y1, s.lim[11 + PH0 + a]); }
+  int xo[kPW];
+#pragma unroll
+  for (int b = 0; b < kPW; ++b) xo[b] = s.lim[18 + b] * cs2;
+  float2 acc[NPH][kPW];
+#pragma unroll
+  for (int a = 0; a < NPH; ++a)
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) acc[a][b] = make_float2(0.f, 0.f);
+  for (int y = y0; y <= y1; ++y) {
+    const float2 *prow = fbase2 + (size_t)y * W * cs2;
+    float2 T[kPW];
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) {
+      float2 f[NX];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) f[j] = __ldg(prow + xo[b] + j * cs2);
+      const float *wb = s.Bc + b * kNXMax;
+      T[b] = make_float2(wb[0] * f[0].x, wb[0] * f[0].y);
+#pragma unroll
+      for (int j = 1; j < NX; ++j) { T[b].x = fmaf(wb[j], f[j].x, T[b].x); T[b].y = fmaf(wb[j], f[j].y, T[b].y); }
+    }
+    const float4 av4 = *reinterpret_cast<const float4 *>(s.Ad + y * 8 + PH0);
+    const float av[4] = {av4.x, av4.y, av4.z, av4.w};
+#pragma unroll
+    for (int a = 0; a < NPH; ++a) {
+      if (av[a] != 0.f) {
+#pragma unroll
+        for (int b = 0; b < kPW; ++b) { acc[a][b].x = fmaf(av[a], T[b].x, acc[a][b].x); acc[a][b].y = fmaf(av[a], T[b].y, acc[a][b].y); }
+      }
+    }
+  }
+  sep_store_acc<PH0, NPH, PH0 == 0>(acc, t0, t1, half, active);
+}
+
 __host__ __device__ inline size_t sep_fwd_smem_bytes(int H, int W) {
   // output tile, two table records (current ROI / prefetched next ROI), dense column table of the fallback, work-item slots
   return (size_t)kTileFloats * 4 + 2 * (size_t)sep_rec_floats(H) * 4 + (size_t)W * 8 * 4 + 16;
@@ -520,6 +570,12 @@ __global__ void __launch_bounds__(kSepThreads, 3) roi_align_fwd_sep_kernel(const
       } else if (nx == 4) {
         sep_fwd_pass_compact<0, 4, kC, 4>(s, fbase2, C, W, t0, t1, half, active);
         sep_fwd_pass_compact<4, 3, kC, 4>(s, fbase2, C, W, t0, t1, half, active);
+      } else if (nx == 6) {
+        sep_fwd_pass_compact_wide<0, 4, kC, 6>(s, fbase2, C, W, t0, t1, half, active);
+        sep_fwd_pass_compact_wide<4, 3, kC, 6>(s, fbase2, C, W, t0, t1, half, active);
+      } else if (nx == 8) {
+        sep_fwd_pass_compact_wide<0, 4, kC, 8>(s, fbase2, C, W, t0, t1, half, active);
+        sep_fwd_pass_compact_wide<4, 3, kC, 8>(s, fbase2, C, W, t0, t1, half, active);
       } else {   // wide bins (fixed sampling_ratio with bins wider than a pixel, or maps narrower than the window)
         const RoiGeom g = roi_geometry(rois + 5 * (size_t)r, scale, aligned, kPH, kPW, sampling_ratio);
         sep_build_x_dense(Bd, g, W);

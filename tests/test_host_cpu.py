@@ -44,7 +44,7 @@ def test_host_only_entry_points():
     assert L.sfod_abi_version() == 1
     assert L.sfod_status_string(0) == b"ok" and L.sfod_status_string(2) == b"workspace too small"
     assert L.sfod_nms_workspace_bytes(0) == 256 and L.sfod_nms_workspace_bytes(9990) > 9990 * 157 * 8
-    rec = (64 + 8 * 18) * 4                                                                            # per-ROI table record
+    rec = (96 + 8 * 18) * 4                                                                            # per-ROI table record
     assert L.sfod_roi_align_fwd_workspace_bytes(8, 512, 18, 37, 16000, 0, 0) >= 8 * 512 * 18 * 37 * 4 + 16000 * rec   # NCHW in -> NHWC copy + records
     assert 16000 * rec <= L.sfod_roi_align_fwd_workspace_bytes(8, 512, 18, 37, 16000, 1, 0) <= 16000 * rec + 1024
     assert L.sfod_roi_align_fwd_workspace_bytes(8, 512, 18, 37, 16000, 0, 1) == 256                 # exact kernel reads NCHW directly
