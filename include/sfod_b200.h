@@ -41,7 +41,7 @@ enum sfod_status {
 };
 
 enum sfod_layout { SFOD_NCHW = 0, SFOD_NHWC = 1 };
-enum sfod_dtype { SFOD_F32 = 0, SFOD_I64 = 1 };
+enum sfod_dtype { SFOD_F32 = 0, SFOD_I64 = 1, SFOD_U8 = 2 };
 
 int sfod_abi_version(void);
 const char *sfod_status_string(int status);
@@ -215,6 +215,17 @@ int sfod_class_threshold_select(const float *values, const int64_t *classes, con
  * receives, per class, the number of entries with value > thres over all S segments (zeroed by the call). */
 int sfod_class_histogram(const float *values, const int64_t *classes, const int32_t *counts_dev, int S, int stride, int K,
                          float thres, int64_t *hist_dev, sfod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Image preprocessing (normalise / pad / batch part).  Replaces
+ * GeneralizedRCNN.preprocess_image = `(x - pixel_mean) / pixel_std` + ImageList.from_tensors
+ * (daod/modeling/meta_arch/rcnn.py:92-104) for N equally sized CHW images that are
+ * `image_stride` elements apart (N = 1 for a list of differently sized images: one call per
+ * image into its slot of the padded batch).  images: uint8 (SFOD_U8) or float32 (SFOD_F32) on
+ * the device; mean/std: C floats on the HOST (C <= 8); out: (N,C,Hp,Wp) fp32 in `layout`,
+ * fl(fl(x - mean[c]) / std[c]) inside (H,W) and 0.0 in the padding. */
+int sfod_normalize_pad(const void *images, int dtype, int64_t image_stride, int N, int C, int H, int W, const float *mean,
+                       const float *stdv, int Hp, int Wp, int layout, float *out, sfod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Fused pairwise_iou + Matcher.  Replaces, per image,

@@ -66,6 +66,8 @@ SIGNATURES = {
     "sfod_threshold_select": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr]),
     "sfod_class_threshold_select": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "sfod_class_histogram": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr]),
+    "sfod_normalize_pad": (C.c_int, [c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                     C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "sfod_iou_match_workspace_bytes": (C.c_size_t, [C.c_int]),
     "sfod_iou_match": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int, C.c_int,
                                  c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),

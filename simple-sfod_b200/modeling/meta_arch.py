@@ -16,6 +16,7 @@ import torch
 from torch import Tensor, nn
 
 from ..registry import META_ARCH_REGISTRY, build_backbone, build_proposal_generator, build_roi_heads
+from .. import ops
 from ..structures import ImageList
 
 
@@ -78,6 +79,7 @@ class SourceFreeAdaptiveTeacherGeneralizedRCNN(nn.Module):
         self.register_buffer("pixel_mean", torch.tensor(pixel_mean).view(-1, 1, 1), False)
         self.register_buffer("pixel_std", torch.tensor(pixel_std).view(-1, 1, 1), False)
         assert self.pixel_mean.shape == self.pixel_std.shape
+        self._mean_std = (tuple(float(v) for v in pixel_mean), tuple(float(v) for v in pixel_std))
         self.dis_type, self.ins_dc = dis_type, ins_dc
         if dis_type is not None and dis_type in getattr(backbone, "_out_feature_channels", {}):
             self.DC_img = _ImageDomainClassifier(backbone._out_feature_channels[dis_type])  # reference ...rcnn.py:68
@@ -91,12 +93,21 @@ class SourceFreeAdaptiveTeacherGeneralizedRCNN(nn.Module):
     def preprocess_image(self, batched_inputs: List[Dict[str, Tensor]]) -> ImageList:
         """d2 GeneralizedRCNN.preprocess_image (reference ...rcnn.py:92-104): normalise, pad, batch."""
         images = [x["image"].to(self.device, non_blocking=True) for x in batched_inputs]
+        if images[0].is_cuda and all(im.dtype in (torch.uint8, torch.float32) for im in images):
+            # one native pass per image: normalise + zero-pad straight into the batch slot (sfod_normalize_pad)
+            batch, sizes = ops.normalize_pad(images, self._mean_std[0], self._mean_std[1], self.backbone.size_divisibility)
+            return ImageList(batch, sizes)
         images = [(x - self.pixel_mean) / self.pixel_std for x in images]
         return ImageList.from_tensors(images, self.backbone.size_divisibility)
 
     def preprocess_batch(self, images: Tensor) -> ImageList:
         """Same arithmetic for an already batched (N, 3, H, W) tensor of equally sized images (one launch)."""
-        x = (images.to(self.device, non_blocking=True) - self.pixel_mean) / self.pixel_std
+        images = images.to(self.device, non_blocking=True)
+        if images.is_cuda and images.dtype in (torch.uint8, torch.float32):
+            nhwc = images.is_contiguous(memory_format=torch.channels_last) and not images.is_contiguous()
+            x, sizes = ops.normalize_pad(images, self._mean_std[0], self._mean_std[1], 0, channels_last=nhwc)
+            return ImageList(x, sizes)
+        x = (images - self.pixel_mean) / self.pixel_std
         return ImageList(x, [tuple(images.shape[-2:])] * images.shape[0])
 
     def forward(self, batched_inputs, branch: str = "supervised", given_proposals=None, val_mode: bool = False):

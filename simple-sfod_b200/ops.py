@@ -20,6 +20,7 @@ from . import _lib
 from ._lib import EmaTensor, FrcnnParams, RpnParams, check
 
 NCHW, NHWC = 0, 1
+DT_F32, DT_I64, DT_U8 = 0, 1, 2   # enum sfod_dtype
 SCALE_CLAMP = math.log(1000.0 / 16)
 COORD_TRICK_MAX_N = 1000  # torchvision CPU switches batched_nms strategy at boxes.numel() > 4000
 
@@ -362,6 +363,54 @@ def class_histogram(values: Tensor, classes: Tensor, counts: Tensor, num_classes
         check(_lib.lib().sfod_class_histogram(v.data_ptr(), cl.data_ptr(), c.data_ptr(), S, stride, int(num_classes), float(thres),
                                               hist.data_ptr(), _stream(dev)), "sfod_class_histogram")
     return hist
+
+
+# ----------------------------------------------------------------------------------------------- image preprocessing
+def normalize_pad(images: Union[Tensor, Sequence[Tensor]], pixel_mean: Sequence[float], pixel_std: Sequence[float],
+                  size_divisibility: int = 0, channels_last: bool = False) -> Tuple[Tensor, List[Tuple[int, int]]]:
+    """``ImageList.from_tensors([(x - mean) / std for x in images], size_divisibility)`` in one pass per image size:
+    images is a (N, C, H, W) uint8/float32 tensor or a list of (C, H, W) tensors of any sizes; returns the padded fp32
+    batch (zeros in the padding; channels-last storage on request) and the true (h, w) of every image."""
+    if isinstance(images, Tensor):
+        if images.dim() != 4:
+            raise ValueError("a batched input must be (N, C, H, W)")
+        groups = [(images, list(range(images.shape[0])))]
+        sizes = [(int(images.shape[2]), int(images.shape[3]))] * images.shape[0]
+        C_ = int(images.shape[1])
+        dev = _require_cuda(images)
+    else:
+        if len(images) == 0:
+            raise ValueError("empty image list")
+        dev = _require_cuda(*images)
+        C_ = int(images[0].shape[0])
+        sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in images]
+        groups = [(im.unsqueeze(0), [i]) for i, im in enumerate(images)]
+    mean = [float(v) for v in pixel_mean]
+    std = [float(v) for v in pixel_std]
+    if len(mean) != C_ or len(std) != C_:
+        raise ValueError("pixel_mean / pixel_std must have one value per channel")
+    Hp, Wp = max(s[0] for s in sizes), max(s[1] for s in sizes)
+    if size_divisibility > 1:
+        Hp = (Hp + size_divisibility - 1) // size_divisibility * size_divisibility
+        Wp = (Wp + size_divisibility - 1) // size_divisibility * size_divisibility
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    out = torch.empty((len(sizes), C_, Hp, Wp), dtype=torch.float32, device=dev, memory_format=fmt)
+    cm, cs = (C.c_float * C_)(*mean), (C.c_float * C_)(*std)
+    L = _lib.lib()
+    slot = C_ * Hp * Wp
+    with torch.cuda.device(dev):
+        for t, idxs in groups:
+            if t.dtype == torch.uint8:
+                dt = DT_U8
+            elif t.dtype == torch.float32:
+                dt = DT_F32
+            else:
+                raise TypeError("images must be uint8 or float32")
+            t = t.contiguous()
+            n, _, H, W = t.shape
+            check(L.sfod_normalize_pad(t.data_ptr(), dt, C_ * H * W, n, C_, H, W, cm, cs, Hp, Wp, NHWC if channels_last else NCHW,
+                                       out.data_ptr() + idxs[0] * slot * 4, _stream(dev)), "sfod_normalize_pad")
+    return out, sizes
 
 
 # ----------------------------------------------------------------------------------------------- box matching

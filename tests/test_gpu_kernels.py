@@ -567,3 +567,30 @@ def test_iou_match_equals_pairwise_iou_plus_matcher(ops, cuda_device, M, N, cfg)
     # the Matcher method used by the plugins dispatches to the same call
     mm, ml = m.match_boxes(Boxes(gt.to(cuda_device)), Boxes(bx.to(cuda_device)))
     assert torch.equal(mm.cpu(), ref_matches) and torch.equal(ml.cpu(), ref_labels)
+
+
+# ------------------------------------------------------------------------------------------------ image preprocessing
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_normalize_pad_equals_preprocess_image(ops, cuda_device, dtype):
+    """SURVEY.md 8f rank 3 (normalise / pad / batch): bit-exact against `(x - mean) / std` + ImageList.from_tensors."""
+    from sfod_b200.structures import ImageList
+    g = torch.Generator().manual_seed(5)
+    mean, std = (103.530, 116.280, 123.675), (57.375, 57.120, 58.395)
+    tm, ts = torch.tensor(mean).view(-1, 1, 1), torch.tensor(std).view(-1, 1, 1)
+    def img(h, w):
+        t = torch.randint(0, 256, (3, h, w), generator=g, dtype=torch.uint8)
+        return t if dtype == torch.uint8 else t.float() + torch.rand(3, h, w, generator=g)
+    # a list of differently sized images, padded to a multiple of 32 (odd widths: scalar path)
+    ims = [img(37, 53), img(64, 40), img(50, 61)]
+    ref = ImageList.from_tensors([(x - tm) / ts for x in ims], 32)
+    got, sizes = ops.normalize_pad([x.to(cuda_device) for x in ims], mean, std, 32)
+    assert sizes == ref.image_sizes and got.shape == ref.tensor.shape
+    assert _bits_equal(got.cpu(), ref.tensor)
+    # an equally sized batch (vector path), NCHW and channels-last storage
+    b = torch.stack([img(48, 64) for _ in range(4)])
+    refb = (b - tm) / ts
+    for cl in (False, True):
+        gotb, sizesb = ops.normalize_pad(b.to(cuda_device), mean, std, 0, channels_last=cl)
+        assert sizesb == [(48, 64)] * 4
+        assert gotb.is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
+        assert _bits_equal(gotb.cpu().contiguous(), refb)
