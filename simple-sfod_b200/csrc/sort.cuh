@@ -8,10 +8,10 @@
 // order of a stable sort.
 //
 // Layout: S segments of P keys each (P a power of two >= 512), contiguous: keys[s*P + i].
-// A thread owns 16 consecutive keys in registers; compare-exchange distance j is served
-//   j < 16        : in registers (static indices),
-//   16 <= j < 512 : warp shuffles (partner lane = lane ^ (j/16)),
-//   j >= 512      : one swizzled shared-memory exchange per stage (conflict-free 64-bit banks),
+// A thread owns kE = 8 consecutive keys in registers; compare-exchange distance j is served
+//   j < 8         : in registers (static indices),
+//   8 <= j < 256  : warp shuffles (partner lane = lane ^ (j/8)),
+//   j >= 256      : one swizzled shared-memory exchange per stage (conflict-free 64-bit banks),
 //   j >= keys/CTA : distributed-shared-memory exchange between the CTAs of a thread-block cluster (a 16 384-key tile is
 //                   spread over 8 CTAs = 8 SMs x 4 warps instead of 32 warps queueing on one SM),
 //   j >= tile     : global-memory exchange kernel (only when P > 16384, e.g. 34 200 R101 anchors).
@@ -20,8 +20,8 @@
 
 namespace bsort {
 
-constexpr int kE = 16;             // keys per thread
-constexpr int kMaxTile = 16384;    // keys per CTA (1024 threads), 128 KiB of shared memory
+constexpr int kE = 8;              // keys per thread (8: half the serial work per thread of 16, one more shuffle stage)
+constexpr int kMaxTile = 16384;    // keys per cluster tile (8 CTAs x 256 threads x 8 keys)
 constexpr int kClusterMinKeys = 2048; // a tile is spread over tile / 2048 (<= 8) CTAs of a cluster
 constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;
 
@@ -44,9 +44,9 @@ __device__ __forceinline__ void reg_stages_small_k(unsigned long long (&a)[kE]) 
   }
 }
 __device__ __forceinline__ void reg_stages(unsigned long long (&a)[kE], int jstart, bool asc) {
-  // jstart in {8,4,2,1}: run j = jstart..1
+  // jstart in {kE/2, ..., 1}: run j = jstart..1
 #pragma unroll
-  for (int j = 8; j >= 1; j >>= 1) {
+  for (int j = kE / 2; j >= 1; j >>= 1) {
     if (j <= jstart) {
 #pragma unroll
       for (int r = 0; r < kE; ++r)
@@ -84,7 +84,7 @@ __device__ __forceinline__ void block_bitonic(unsigned long long (&a)[kE], unsig
     if (k < kE) {
       if (k == 2) reg_stages_small_k<2>(a);
       else if (k == 4) reg_stages_small_k<4>(a);
-      else reg_stages_small_k<8>(a);
+      else reg_stages_small_k<(kE > 8 ? 8 : 4)>(a);   // only reached when kE == 16
       continue;
     }
     const bool asc = (g0 & k) == 0;
@@ -93,7 +93,7 @@ __device__ __forceinline__ void block_bitonic(unsigned long long (&a)[kE], unsig
     // cluster stages: the partner key lives at the same position of CTA rank ^ (j / ctile)
     for (; j >= ctile; j >>= 1) {
       const int rj = (int)(j / ctile);
-      const int sw = t & 15;
+      const int sw = t & (kE - 1);
       __syncthreads();      // own threads are done with the shared-memory stage before
 #pragma unroll
       for (int r = 0; r < kE; ++r) smem[t * kE + (r ^ sw)] = a[r];
@@ -108,9 +108,9 @@ __device__ __forceinline__ void block_bitonic(unsigned long long (&a)[kE], unsig
       cluster_sync_all();   // every peer has read this CTA's tile before anything overwrites it
     }
     // shared-memory stages
-    for (; j >= 512; j >>= 1) {
+    for (; j >= 32 * kE; j >>= 1) {
       const int tj = (int)(j / kE);
-      const int sw = t & 15;
+      const int sw = t & (kE - 1);
       __syncthreads();
 #pragma unroll
       for (int r = 0; r < kE; ++r) smem[t * kE + (r ^ sw)] = a[r];
@@ -135,14 +135,14 @@ __device__ __forceinline__ void block_bitonic(unsigned long long (&a)[kE], unsig
         a[r] = take_min ? (a[r] < o ? a[r] : o) : (a[r] > o ? a[r] : o);
       }
     }
-    // in-register stages j = 8..1
-    reg_stages(a, 8, asc);
+    // in-register stages j = kE/2..1
+    reg_stages(a, kE / 2, asc);
   }
 }
 
 // Tile kernel: grid (cl * P / tile, S) launched as clusters of cl CTAs along x; block tile/cl/16 threads; dynamic smem
 // tile/cl*8 bytes.
-__global__ void __launch_bounds__(1024) bitonic_tile_kernel(unsigned long long *keys, int P, int tile, int cl, int k_lo, int k_hi) {
+__global__ void __launch_bounds__(kClusterMinKeys / kE) bitonic_tile_kernel(unsigned long long *keys, int P, int tile, int cl, int k_lo, int k_hi) {
   extern __shared__ unsigned long long sort_smem[];
   const int ctile = tile / cl, rank = (int)(blockIdx.x % (unsigned)cl);
   unsigned long long *seg = keys + (size_t)blockIdx.y * P + (size_t)blockIdx.x * ctile;
