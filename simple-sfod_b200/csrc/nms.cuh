@@ -4,15 +4,17 @@
 // fast_rcnn_inference_single_image -> batched_nms (reference roi_heads/fast_rcnn.py:133; one segment per
 // (image, class)), plus the torchvision-compatible nms/batched_nms operators.
 //
-// Two kernels:
-//  1. nms_mask_kernel: 64x64 tiles of the upper triangle; each thread owns one row box and ballots a
-//     64-bit suppression word against 64 column boxes staged in shared memory (float4 + area).
-//     IoU in torchvision's fp32 operation order, division skipped when the intersection is empty.
-//  2. nms_scan_kernel: one CTA per segment walks the tiles in order.  Warp 0 resolves the 64x64 diagonal
-//     block with a fully unrolled register chain (alive &= ~row_i if alive_i), the other warps then OR
-//     the kept rows into the shared `removed` bitmap (coalesced 8-byte loads).  The scan stops as soon
-//     as `max_keep` boxes are kept (post_nms_topk / detections-per-image), which is what bounds its
-//     latency in the low-suppression case.
+// Three implementations, chosen by run_segmented():
+//  A. nms_deferred_kernel (default): one thread-block cluster per segment; every CTA keeps the complete kept list in
+//     shared memory, tiles meet it only near their turn, owners publish through DSMEM + one mbarrier per tile.
+//  B. nms_lazy_kernel: the same cluster organisation with every kept list applied to all later boxes at once; used when
+//     the kept list cannot fit in shared memory (plain nms of many boxes with max_keep = n).
+//  C. nms_mask_kernel + nms_scan_kernel (fallback when clusters cannot launch):
+//     mask: 64x64 tiles of the upper triangle; each thread owns one row box and ballots a 64-bit suppression word
+//     against 64 column boxes staged in shared memory; scan: one CTA per segment walks the tiles in order, warp 0 resolves
+//     the diagonal block, the other warps OR the kept rows into the shared `removed` bitmap.
+// All of them use torchvision's fp32 IoU operation order, skip the division when the intersection is empty, give the same
+// keep set and order, and stop as soon as `max_keep` boxes are kept (post_nms_topk / detections-per-image).
 #pragma once
 #include "common.cuh"
 
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const unsigned l
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Lazy-row cluster NMS (the default path).  Greedy NMS only ever needs the IoU rows of boxes that end up KEPT, and a
+// Lazy-row cluster NMS (implementation B).  Greedy NMS only ever needs the IoU rows of boxes that end up KEPT, and a
 // box stops being tested the moment something suppresses it; the mask kernel above computes all n^2/2 pairs (50 M for
 // the 9 990 RPN candidates of one VGG image) although at most max_keep * n of them matter.  Here one thread-block
 // CLUSTER owns one segment (image, or image x class) and evaluates pairs on the fly from shared memory:
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(kLazyThreads) nms_lazy_kernel(const float4 *__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Deferred-apply cluster NMS (the default whenever the kept list fits in shared memory).
+// Deferred-apply cluster NMS (implementation A: the default whenever the kept list fits in shared memory).
 // The lazy-row kernel above applies every kept list to ALL later boxes of the segment as soon as it is published.  When
 // the scan stops early -- RPN keeps post_nms_topk = 2000 of 9 990 candidates and reaches them after ~2 700 boxes -- three
 // quarters of those IoU tests are spent on boxes that are never visited (17 M of 20 M pairs per VGG image), and they sit

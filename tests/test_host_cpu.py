@@ -208,3 +208,41 @@ def test_pseudo_label_export_formats():
     pp = engine.detector_postprocess(inst, 1024, 2048)                                       # Cityscapes 1024x2048 <- 600x1200
     assert pp.image_size == (1024, 2048) and torch.allclose(pp.pred_boxes.tensor[0], torch.tensor([10.0, 20, 110, 220]) * (2048 / 1200))
     assert len(pp) == 3
+
+
+def test_matcher_and_preprocessing_host_paths():
+    """Host side of the two 8f widenings: `Matcher.match_boxes` keeps detectron2's two-step result on CPU tensors (the
+    fused kernel is the CUDA path), argument errors are raised before any launch, and the native operators refuse CPU
+    tensors instead of falling back."""
+    from oracle import d2_cpu as oracle
+    from sfod_b200.modeling.matcher import Matcher
+    g = torch.Generator().manual_seed(11)
+    gt = torch.rand(7, 4, generator=g) * 200; gt[:, 2:] += gt[:, :2]
+    bx = torch.rand(300, 4, generator=g) * 200; bx[:, 2:] += bx[:, :2]
+    for th, lb, lq in (([0.3, 0.7], [0, -1, 1], True), ([0.5], [0, 1], False)):
+        m = Matcher(th, lb, allow_low_quality_matches=lq)
+        a = m.match_boxes(Boxes(gt), Boxes(bx))
+        b = m(pairwise_iou(Boxes(gt), Boxes(bx)))
+        r = oracle.matcher(oracle.pairwise_iou(gt, bx), th, lb, lq)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[0], r[0]) and torch.equal(a[1], r[1])
+    assert L_ws(0) == 256 and L_ws(1000) >= 4000
+    with pytest.raises(RuntimeError):
+        ops.iou_match(gt, bx, [0.5], [0, 1])                     # CPU tensors: no fallback
+    with pytest.raises(RuntimeError):
+        ops.normalize_pad(torch.zeros(2, 3, 8, 8, dtype=torch.uint8), (1.0, 2.0, 3.0), (1.0, 1.0, 1.0))
+    # host-side validation of the C entry points (no device work is reached)
+    L = _lib.lib()
+    th = (C.c_float * 2)(0.7, 0.3)                               # thresholds must ascend
+    lb = (C.c_int * 3)(0, -1, 1)
+    assert L.sfod_iou_match(None, None, 0, 0, th, lb, 2, 0, None, None, None, None, 0, None) == 0      # N == 0: nothing to do
+    assert L.sfod_iou_match(None, 16, 0, 4, th, lb, 2, 0, 16, 16, None, None, 0, None) == 1            # descending thresholds
+    assert L.sfod_iou_match(None, 16, 0, 4, th, lb, 9, 0, 16, 16, None, None, 0, None) == 1            # too many thresholds
+    mean = (C.c_float * 3)(1, 2, 3)
+    assert L.sfod_normalize_pad(None, 2, 0, 0, 3, 8, 8, mean, mean, 8, 8, 0, None, None) == 0          # N == 0
+    assert L.sfod_normalize_pad(16, 2, 192, 1, 3, 8, 8, mean, mean, 4, 8, 0, 16, None) == 1            # padded size < image size
+    assert L.sfod_normalize_pad(16, 1, 192, 1, 3, 8, 8, mean, mean, 8, 8, 0, 16, None) == 1            # int64 images are not accepted
+    assert L.sfod_normalize_pad(16, 2, 192, 1, 9, 8, 8, mean, mean, 8, 8, 0, 16, None) == 1            # more channels than supported
+
+
+def L_ws(m):
+    return _lib.lib().sfod_iou_match_workspace_bytes(m)
