@@ -12,6 +12,7 @@ When the real detectron2 is importable ``install()`` does nothing unless ``force
 """
 from __future__ import annotations
 
+import functools
 import importlib
 import sys
 import types
@@ -22,6 +23,7 @@ from torch import nn
 
 from . import config as _config
 from . import ops, structures
+from .engine import export as _export
 from .modeling import box_regression, fast_rcnn, matcher, poolers, proposal_generator, roi_heads
 from .registry import Registry
 from .structures import ShapeSpec
@@ -35,12 +37,109 @@ def _mod(name: str, **attrs) -> types.ModuleType:
     return m
 
 
+def _called_with_cfg(*args, **kwargs) -> bool:
+    if len(args) and isinstance(args[0], _config.CfgNode):
+        return True
+    return isinstance(kwargs.get("cfg", None), _config.CfgNode)
+
+
 def configurable(init_func=None, *, from_config=None):
-    """detectron2.config.configurable, reduced to what the hot-path classes need: this package's classes already accept
-    ``(cfg, input_shape)`` directly, so the decorator is the identity (on ``__init__`` and on functions)."""
+    """detectron2.config.configurable: an ``__init__`` decorated with it accepts either explicit arguments or a ``cfg`` first
+    argument, in which case ``cls.from_config(cfg, ...)`` supplies the explicit arguments (the reference's meta-architectures,
+    daod/modeling/meta_arch/source_free_adaptive_teacher_rcnn.py:27-92, are written that way).  The classes of this package
+    take ``(cfg, input_shape)`` directly and do not use the decorator."""
     if init_func is not None:
-        return init_func
-    return lambda f: f
+        assert from_config is None, "from_config is only for the function form of @configurable"
+
+        @functools.wraps(init_func)
+        def wrapped(self, *args, **kwargs):
+            if _called_with_cfg(*args, **kwargs):
+                try:
+                    from_config_func = type(self).from_config
+                except AttributeError as e:
+                    raise AttributeError("Class with @configurable must have a 'from_config' classmethod.") from e
+                explicit_args = from_config_func(*args, **kwargs)
+                init_func(self, **explicit_args)
+            else:
+                init_func(self, *args, **kwargs)
+        return wrapped
+
+    def wrapper(orig_func):
+        @functools.wraps(orig_func)
+        def wrapped(*args, **kwargs):
+            if _called_with_cfg(*args, **kwargs):
+                return orig_func(**from_config(*args, **kwargs))
+            return orig_func(*args, **kwargs)
+        wrapped.from_config = from_config
+        return wrapped
+    return wrapper
+
+
+class GeneralizedRCNN(nn.Module):
+    """detectron2.modeling.meta_arch.rcnn.GeneralizedRCNN reduced to what the reference's subclasses inherit
+    (daod/modeling/meta_arch/source_free_adaptive_teacher_rcnn.py:24 calls ``super(GeneralizedRCNN, self).__init__()`` and sets
+    every attribute itself; it uses ``device``, ``preprocess_image`` and ``inference`` of the base)."""
+
+    @property
+    def device(self) -> torch.device:
+        return self.pixel_mean.device
+
+    def preprocess_image(self, batched_inputs):
+        images = [x["image"].to(self.device) for x in batched_inputs]
+        if images[0].is_cuda and all(im.dtype in (torch.uint8, torch.float32) for im in images):
+            ms = self.__dict__.get("_sfod_mean_std")
+            if ms is None:   # one device read for the lifetime of the module
+                ms = (tuple(self.pixel_mean.flatten().tolist()), tuple(self.pixel_std.flatten().tolist()))
+                self.__dict__["_sfod_mean_std"] = ms
+            batch, sizes = ops.normalize_pad(images, ms[0], ms[1], self.backbone.size_divisibility)
+            return structures.ImageList(batch, sizes)
+        images = [(x - self.pixel_mean) / self.pixel_std for x in images]
+        return structures.ImageList.from_tensors(images, self.backbone.size_divisibility)
+
+    def inference(self, batched_inputs, detected_instances=None, do_postprocess: bool = True):
+        assert not self.training
+        images = self.preprocess_image(batched_inputs)
+        features = self.backbone(images.tensor)
+        if detected_instances is not None:
+            raise NotImplementedError("inference with given boxes is not used on the hot path")
+        if self.proposal_generator is not None:
+            proposals, _ = self.proposal_generator(images, features, None)
+        else:
+            proposals = [x["proposals"].to(self.device) for x in batched_inputs]
+        results, _ = self.roi_heads(images, features, proposals, None)
+        if do_postprocess:
+            return GeneralizedRCNN._postprocess(results, batched_inputs, images.image_sizes)
+        return results
+
+    @staticmethod
+    def _postprocess(instances, batched_inputs, image_sizes):
+        from .engine.export import detector_postprocess
+        out = []
+        for results_per_image, input_per_image, image_size in zip(instances, batched_inputs, image_sizes):
+            height = input_per_image.get("height", image_size[0])
+            width = input_per_image.get("width", image_size[1])
+            out.append({"instances": detector_postprocess(results_per_image, height, width)})
+        return out
+
+    def visualize_training(self, *a, **k):
+        raise NotImplementedError("visualisation (VIS_PERIOD > 0) is outside the hot path")
+
+
+class DatasetEvaluator:
+    """detectron2.evaluation.DatasetEvaluator interface (imported by daod/loss/bpc_loss.py:3)."""
+
+    def reset(self):
+        pass
+
+    def process(self, inputs, outputs):
+        pass
+
+    def evaluate(self):
+        pass
+
+
+def _convert_image_to_rgb(*a, **k):
+    raise NotImplementedError("convert_image_to_rgb is only used by visualisation, outside the hot path")
 
 
 class Backbone(nn.Module):
@@ -125,12 +224,20 @@ def install(force: bool = False) -> bool:
         "detectron2.utils.events": _mod("detectron2.utils.events", EventStorage=events.EventStorage, get_event_storage=events.get_event_storage),
         "detectron2.utils.comm": _mod("detectron2.utils.comm", get_world_size=get_world_size, is_main_process=lambda: True),
         "detectron2.data": _mod("detectron2.data", __path__=[]),
-        "detectron2.data.detection_utils": _mod("detectron2.data.detection_utils", get_fed_loss_cls_weights=_get_fed_loss_cls_weights),
+        "detectron2.data.detection_utils": _mod("detectron2.data.detection_utils", get_fed_loss_cls_weights=_get_fed_loss_cls_weights,
+                                                convert_image_to_rgb=_convert_image_to_rgb),
+        "detectron2.evaluation": _mod("detectron2.evaluation", DatasetEvaluator=DatasetEvaluator),
+        "detectron2.modeling.postprocessing": _mod("detectron2.modeling.postprocessing", detector_postprocess=_export.detector_postprocess),
+        "detectron2.modeling.meta_arch": _mod("detectron2.modeling.meta_arch", __path__=[], GeneralizedRCNN=GeneralizedRCNN,
+                                              META_ARCH_REGISTRY=regs["META_ARCH"]),
+        "detectron2.modeling.meta_arch.build": _mod("detectron2.modeling.meta_arch.build", META_ARCH_REGISTRY=regs["META_ARCH"]),
+        "detectron2.modeling.meta_arch.rcnn": _mod("detectron2.modeling.meta_arch.rcnn", GeneralizedRCNN=GeneralizedRCNN),
         "detectron2.modeling": _mod("detectron2.modeling", __path__=[], build_backbone=build_backbone, build_proposal_generator=build_proposal_generator,
                                     build_roi_heads=build_roi_heads, META_ARCH_REGISTRY=regs["META_ARCH"], BACKBONE_REGISTRY=regs["BACKBONE"],
                                     ROI_HEADS_REGISTRY=regs["ROI_HEADS"], ROI_BOX_HEAD_REGISTRY=regs["ROI_BOX_HEAD"], Backbone=Backbone,
-                                    StandardROIHeads=roi_heads._StandardROIHeadsBase),
-        "detectron2.modeling.backbone": _mod("detectron2.modeling.backbone", __path__=[], Backbone=Backbone, BACKBONE_REGISTRY=regs["BACKBONE"]),
+                                    StandardROIHeads=roi_heads._StandardROIHeadsBase, GeneralizedRCNN=GeneralizedRCNN),
+        "detectron2.modeling.backbone": _mod("detectron2.modeling.backbone", __path__=[], Backbone=Backbone, BACKBONE_REGISTRY=regs["BACKBONE"],
+                                             build_backbone=build_backbone),
         "detectron2.modeling.backbone.fpn": _mod("detectron2.modeling.backbone.fpn", FPN=FPN, LastLevelMaxPool=LastLevelMaxPool, LastLevelP6P7=LastLevelP6P7),
         "detectron2.modeling.box_regression": _mod("detectron2.modeling.box_regression", Box2BoxTransform=box_regression.Box2BoxTransform,
                                                    _dense_box_regression_loss=matcher.dense_box_regression_loss),
@@ -138,7 +245,8 @@ def install(force: bool = False) -> bool:
         "detectron2.modeling.matcher": _mod("detectron2.modeling.matcher", Matcher=matcher.Matcher),
         "detectron2.modeling.sampling": _mod("detectron2.modeling.sampling", subsample_labels=matcher.subsample_labels),
         "detectron2.modeling.proposal_generator": _mod("detectron2.modeling.proposal_generator", __path__=[], RPN=proposal_generator.RPN,
-                                                       PROPOSAL_GENERATOR_REGISTRY=regs["PROPOSAL_GENERATOR"]),
+                                                       PROPOSAL_GENERATOR_REGISTRY=regs["PROPOSAL_GENERATOR"],
+                                                       build_proposal_generator=build_proposal_generator),
         "detectron2.modeling.proposal_generator.build": _mod("detectron2.modeling.proposal_generator.build", PROPOSAL_GENERATOR_REGISTRY=regs["PROPOSAL_GENERATOR"],
                                                              build_proposal_generator=build_proposal_generator),
         "detectron2.modeling.proposal_generator.proposal_utils": _mod("detectron2.modeling.proposal_generator.proposal_utils",

@@ -91,3 +91,46 @@ def test_reference_plugins_build_from_cfg_and_reach_the_kernel_boundary(ref):
         out = heads.label_and_sample_proposals([prop], [tgt], branch="supervised_target")
     assert len(out[0]) == 2 and sorted(out[0].gt_classes.tolist()) == [3, 3]            # proposal + appended GT, both foreground
     assert "roi_head/num_target_fg_samples_supervised_target" in st.latest()
+
+
+def test_reference_meta_arch_source_builds_on_the_shim(ref):
+    """One level up: the reference's own META-ARCHITECTURE source (daod/modeling/meta_arch/source_free_adaptive_teacher_rcnn.py,
+    `@configurable` + `from_config`, its `dann` and `bpc_loss` imports) loads unchanged, builds from the config through the
+    shim's registries -- i.e. out of the reference's own backbone / RPN / ROI-head plugin classes on the B200 bases -- has the
+    checkpoint layout of this package's mirror, and its forward reaches the kernel boundary."""
+    mods, regs = ref
+    import types as _types
+    from sfod_b200 import config, modeling
+    ref_root = os.path.dirname(REF)                                  # /root/reference/daod
+    stubs = {"daod": [ref_root], "daod.modeling": [REF], "daod.loss": [os.path.join(ref_root, "loss")]}
+    saved = {k: sys.modules.get(k) for k in list(stubs) + ["daod.modeling.dann", "daod.loss.bpc_loss"]}
+    try:
+        for name, path in stubs.items():                              # namespace stubs: the packages' real __init__ files are not run
+            m = _types.ModuleType(name); m.__path__ = path; sys.modules[name] = m
+        ma = importlib.import_module("refdaod_ma.source_free_adaptive_teacher_rcnn")
+        assert ma.__file__.startswith("/root/reference/")
+        cls = regs["META_ARCH"].get("SourceFreeAdaptiveTeacherGeneralizedRCNN")
+        assert cls is ma.SourceFreeAdaptiveTeacherGeneralizedRCNN and cls.__module__ == "refdaod_ma.source_free_adaptive_teacher_rcnn"
+        cfg = config.vgg_source_free_cfg(); cfg.MODEL.DEVICE = "cpu"
+        torch.manual_seed(0)
+        model = cls(cfg)                                              # detectron2's `configurable` protocol: cfg -> from_config -> __init__
+        assert type(model.backbone).__module__ == "refdaod_ma.vgg"
+        assert type(model.proposal_generator).__module__ == "refdaod_pg.rpn"
+        assert type(model.roi_heads).__module__ == "refdaod_rh.source_free_adaptive_teacher_roi_heads"
+        mirror = modeling.SourceFreeAdaptiveTeacherGeneralizedRCNN(cfg)
+        ref_sd, our_sd = model.state_dict(), mirror.state_dict()
+        assert list(ref_sd.keys()) == list(our_sd.keys())             # same checkpoint: names, order
+        assert all(ref_sd[k].shape == our_sd[k].shape and ref_sd[k].dtype == our_sd[k].dtype for k in ref_sd)
+        mirror.load_state_dict(ref_sd)                                # and loadable both ways
+        model.load_state_dict(mirror.state_dict())
+        # the reference's forward (its own Python) on a CPU batch runs its torch backbone and stops at the first native operator
+        model.train()
+        batch = [{"image": torch.randint(0, 256, (3, 96, 128), dtype=torch.uint8).float()}]
+        with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA tensors only"):
+            model(batch, branch="unsup_data_weak")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
