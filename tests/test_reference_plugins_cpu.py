@@ -109,6 +109,11 @@ def test_reference_meta_arch_source_builds_on_the_shim(ref):
             m = _types.ModuleType(name); m.__path__ = path; sys.modules[name] = m
         ma = importlib.import_module("refdaod_ma.source_free_adaptive_teacher_rcnn")
         assert ma.__file__.startswith("/root/reference/")
+        # the other meta-architectures the reference registers (daod/modeling/meta_arch/__init__.py:1-5) stay importable too
+        for other in ("adaptive_teacher_rcnn", "da_faster_rcnn", "cda_faster_rcnn", "ts_ensemble"):
+            importlib.import_module("refdaod_ma." + other)
+        for name in ("AdaptiveTeacherGeneralizedRCNN", "MeanTeacherGeneralizedRCNN", "DAFasterRCNN", "CDAFasterRCNN"):
+            assert name in regs["META_ARCH"], name
         cls = regs["META_ARCH"].get("SourceFreeAdaptiveTeacherGeneralizedRCNN")
         assert cls is ma.SourceFreeAdaptiveTeacherGeneralizedRCNN and cls.__module__ == "refdaod_ma.source_free_adaptive_teacher_rcnn"
         cfg = config.vgg_source_free_cfg(); cfg.MODEL.DEVICE = "cpu"
