@@ -24,6 +24,7 @@ from torch import nn
 from . import config as _config
 from . import ops, structures
 from .engine import export as _export
+from .engine import hooks as _hooks
 from .modeling import box_regression, fast_rcnn, matcher, poolers, proposal_generator, roi_heads
 from .registry import Registry
 from .structures import ShapeSpec
@@ -227,6 +228,9 @@ def install(force: bool = False) -> bool:
         "detectron2.data.detection_utils": _mod("detectron2.data.detection_utils", get_fed_loss_cls_weights=_get_fed_loss_cls_weights,
                                                 convert_image_to_rgb=_convert_image_to_rgb),
         "detectron2.evaluation": _mod("detectron2.evaluation", DatasetEvaluator=DatasetEvaluator),
+        "detectron2.engine": _mod("detectron2.engine", __path__=[], HookBase=_hooks.HookBase, TrainerBase=_hooks.TrainerBase),
+        "detectron2.engine.hooks": _mod("detectron2.engine.hooks", HookBase=_hooks.HookBase),
+        "detectron2.engine.train_loop": _mod("detectron2.engine.train_loop", HookBase=_hooks.HookBase, TrainerBase=_hooks.TrainerBase),
         "detectron2.modeling.postprocessing": _mod("detectron2.modeling.postprocessing", detector_postprocess=_export.detector_postprocess),
         "detectron2.modeling.meta_arch": _mod("detectron2.modeling.meta_arch", __path__=[], GeneralizedRCNN=GeneralizedRCNN,
                                               META_ARCH_REGISTRY=regs["META_ARCH"]),

@@ -6,3 +6,4 @@ from .sharding import images_per_rank, shard_range  # noqa: F401
 from .adaptive_threshold import (AdaptiveConfidenceBasedSelfTrainingLoss, adaptive_threshold_bbox, count_label_prediction,  # noqa: F401
                                  prediction_threshold_bbox, update_adaptive_threshold)
 from .export import batch_to_coco_json, detector_postprocess, instances_to_coco_json, prediction_to_gt  # noqa: F401
+from .hooks import HookBase, TeacherEMAHook, TrainerBase  # noqa: F401

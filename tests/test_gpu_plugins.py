@@ -377,3 +377,42 @@ def test_teacher_step_has_one_host_sync_per_batch(teacher, cuda_device):
     n = [len(p) for p in p_rpn]                       # looking now costs no further read (counts came with the detections)
     assert p_rpn[0].is_materialized() and all(0 < k <= 2000 for k in n)
     assert [len(p) for p in p_roih] == p_roih[0]._sfod_batch.host_counts()[0]
+
+
+@pytest.mark.gpu
+def test_teacher_ema_hook_on_the_trainer_protocol(cuda_device):
+    """The mean-teacher update driven through detectron2's hook protocol (engine.TrainerBase / HookBase): burn-in copy at
+    iteration `burn_up_step` (keep rate 0 through the same formula), then keep_rate every iteration."""
+    import torch
+    from torch import nn
+    from sfod_b200.engine import TeacherEMAHook, TrainerBase
+    torch.manual_seed(3)
+    student = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.Linear(4, 5)).to(cuda_device)
+    teacher = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.Linear(4, 5)).to(cuda_device)
+    ref_t = {k: v.clone() for k, v in teacher.state_dict().items()}
+
+    class Loop(TrainerBase):
+        def run_step(self):
+            with torch.no_grad():
+                for p in student.parameters():
+                    p.add_(0.01)            # the student moves every iteration
+
+    loop = Loop()
+    loop.register_hooks([TeacherEMAHook(student, teacher, keep_rate=0.75, period=1, burn_up_step=2)])
+    expect = {k: v.clone() for k, v in ref_t.items()}
+    s_sd = {k: v.clone() for k, v in student.state_dict().items()}
+    for it in range(5):                      # the same schedule in plain torch
+        for k, v in s_sd.items():
+            if v.is_floating_point() and k in dict(student.named_parameters()):
+                s_sd[k] = v + 0.01
+        keep = None if it < 2 else (0.0 if it == 2 else 0.75)
+        if keep is not None:
+            for k in expect:
+                if expect[k].is_floating_point():
+                    expect[k] = s_sd[k] * (1 - keep) + expect[k] * keep
+                else:
+                    expect[k] = (s_sd[k].float() * (1 - keep) + expect[k].float() * keep).to(expect[k].dtype)
+    loop.train(0, 5)
+    got = teacher.state_dict()
+    for k in expect:
+        assert torch.allclose(got[k].float(), expect[k].float(), rtol=1e-6, atol=1e-7), k

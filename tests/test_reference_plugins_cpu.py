@@ -139,3 +139,43 @@ def test_reference_meta_arch_source_builds_on_the_shim(ref):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_reference_hook_runs_on_the_trainer_protocol(ref):
+    """The reference's own ValLossHook (daod/engine/hooks/val_loss.py) subclasses detectron2's HookBase; on the shim it runs
+    unchanged on this package's TrainerBase: same callbacks, `trainer.iter` / `max_iter` / `storage`."""
+    import types as _types
+    from sfod_b200.engine import HookBase, TrainerBase
+    m = _types.ModuleType("refdaod_hooks"); m.__path__ = ["/root/reference/daod/engine/hooks"]; sys.modules["refdaod_hooks"] = m
+    try:
+        vl = importlib.import_module("refdaod_hooks.val_loss")
+        assert vl.__file__.startswith("/root/reference/") and issubclass(vl.ValLossHook, HookBase)
+
+        class Model:
+            def __call__(self, data):
+                return {"loss_cls": torch.tensor(0.5) * data, "loss_box_reg": 0.25 * data, "num_fg": 3.0}, [], []
+
+        class Loop(TrainerBase):
+            steps = 0
+            def run_step(self):
+                self.steps += 1
+
+        order = []
+        class Probe(HookBase):
+            def before_train(self): order.append("before_train")
+            def before_step(self): order.append(f"before_step{self.trainer.iter}")
+            def after_step(self): order.append(f"after_step{self.trainer.iter}")
+            def after_train(self): order.append("after_train")
+
+        loop = Loop()
+        loop.register_hooks([Probe(), None, vl.ValLossHook(2, Model(), [1.0, 3.0], model_name="_student")])
+        loop.train(0, 5)
+        assert loop.steps == 5 and loop.iter == 5
+        assert order[0] == "before_train" and order[-1] == "after_train" and order[1:3] == ["before_step0", "after_step0"]
+        # evaluated after iterations 1, 3 (period 2) and 4 (final): mean over the loader of each loss_* entry
+        hist = loop.storage.history("total_loss_student_val")
+        assert len(hist) == 3 and abs(hist[-1] - (0.5 * 2.0 + 0.25 * 2.0)) < 1e-6
+        assert abs(loop.storage.latest()["loss_cls_student_val"] - 1.0) < 1e-6 and "num_fg_student_val" not in loop.storage.latest()
+    finally:
+        for k in [k for k in sys.modules if k.startswith("refdaod_hooks")]:
+            del sys.modules[k]
