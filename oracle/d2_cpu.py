@@ -25,13 +25,25 @@ anchored on the reference's own call sites:
 
 Pinning status
 --------------
-The reference ships no tests and no golden vectors, so the pins are:
-the known-answer vectors of SURVEY.md Appendix B (``tests/golden/kat.json``,
-re-derived by ``tests/golden/make_golden.py`` from torchvision/ATen CPU in this
-container) and seeded fixtures generated from the installed torchvision 0.26 CPU
-kernels (``tests/golden/*.npz``).  The detectron2 glue itself is **parity unpinned**
-against a running detectron2 (none is available); the native ops are pinned against
-the real torchvision CPU kernels.
+The reference ships no tests and no golden vectors.  Pins:
+
+1. **The reference's own on-disk functions, executed on the CPU** (tests/ref_exec.py imports / compiles them from
+   /root/reference on the detectron2 shim, copying nothing): ``fast_rcnn_inference_single_image_with_mcd`` (fast_rcnn.py:88-142),
+   ``convert_bbox_scores`` / ``fast_rcnn_inference_single_image_new`` (source_free_fast_rcnn.py:15-36,82-147), ``threshold_bbox``,
+   ``adaptive_threshold_bbox``, ``prediction_threshold_bbox``, ``process_pseudo_label``, ``count_label_prediction``,
+   ``update_adaptive_threshold`` (source_free_adaptive_teacher.py:150-310), ``_update_teacher_model`` (:583-603 and
+   adaptive_teacher.py:339-358), ``reset_bn_stats`` / ``recursive_traversal`` (base.py:318-328),
+   ``AdaptiveConfidenceBasedSelfTrainingLoss`` (adaptive_confidence.py:6-33) and the flatten of ``PseudoLabRPN.forward``
+   (rpn.py:25-58).  tests/test_oracle_vs_reference_cpu.py demands bit-equality with this module (live, in the build
+   container) and tests/golden/ref_exec.npz -- written FROM those functions by tests/golden/make_golden_ref.py -- carries the
+   same pin to the GPU box.
+2. The native CPU kernels the reference binds to (torchvision 0.26 ``nms`` / ``batched_nms`` / ``roi_align`` / ``roi_pool``,
+   ATen): called live by this module and frozen in tests/golden/{nms,roi,dense}.npz; known answers of SURVEY.md App. B in
+   tests/golden/kat.json.
+3. Still **unpinned against a running detectron2** (none is installable): the pieces of detectron2 0.6 that are NOT on disk in
+   the reference -- ``Box2BoxTransform.apply_deltas`` (pinned instead on torchvision's ``BoxCoder.decode_single``, its
+   importable twin), ``find_top_rpn_proposals``, ``DefaultAnchorGenerator``, ``ROIPooler`` glue, ``Matcher`` /
+   ``subsample_labels`` (pinned on torchvision's detection ``Matcher``).  They follow SURVEY.md Appendix A.
 
 Tie rule: ``torch.sort``/``topk`` on CPU are unspecified on exact ties
 (SURVEY.md B-4); the oracle canonicalises to value-descending / index-ascending

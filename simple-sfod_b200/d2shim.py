@@ -210,9 +210,37 @@ def install(force: bool = False) -> bool:
         assert isinstance(tensors, (list, tuple))
         return tensors[0] if len(tensors) == 1 else torch.cat(tensors, dim)
 
-    def get_world_size() -> int:
+    def _dist_on() -> bool:
         d = torch.distributed
-        return d.get_world_size() if d.is_available() and d.is_initialized() else 1
+        return d.is_available() and d.is_initialized()
+
+    def get_world_size() -> int:
+        return torch.distributed.get_world_size() if _dist_on() else 1
+
+    def get_rank() -> int:
+        return torch.distributed.get_rank() if _dist_on() else 0
+
+    def is_main_process() -> bool:
+        return get_rank() == 0
+
+    def synchronize() -> None:
+        if _dist_on() and get_world_size() > 1:
+            torch.distributed.barrier()
+
+    def gather(data, dst: int = 0, group=None):
+        """detectron2.utils.comm.gather: list of every rank's picklable ``data`` on ``dst``, [] elsewhere (reference base.py:198)."""
+        if get_world_size() == 1:
+            return [data]
+        out = [None] * get_world_size() if get_rank() == dst else None
+        torch.distributed.gather_object(data, out, dst=dst, group=group)
+        return out if get_rank() == dst else []
+
+    def all_gather(data, group=None):
+        if get_world_size() == 1:
+            return [data]
+        out = [None] * get_world_size()
+        torch.distributed.all_gather_object(out, data, group=group)
+        return out
 
     mods = {
         "detectron2": _mod("detectron2", __path__=[]),
@@ -223,7 +251,8 @@ def install(force: bool = False) -> bool:
                                   cross_entropy=matcher.cross_entropy, nonzero_tuple=matcher.nonzero_tuple),
         "detectron2.utils": _mod("detectron2.utils", __path__=[]),
         "detectron2.utils.events": _mod("detectron2.utils.events", EventStorage=events.EventStorage, get_event_storage=events.get_event_storage),
-        "detectron2.utils.comm": _mod("detectron2.utils.comm", get_world_size=get_world_size, is_main_process=lambda: True),
+        "detectron2.utils.comm": _mod("detectron2.utils.comm", get_world_size=get_world_size, get_rank=get_rank, is_main_process=is_main_process,
+                                    synchronize=synchronize, gather=gather, all_gather=all_gather),
         "detectron2.data": _mod("detectron2.data", __path__=[]),
         "detectron2.data.detection_utils": _mod("detectron2.data.detection_utils", get_fed_loss_cls_weights=_get_fed_loss_cls_weights,
                                                 convert_image_to_rgb=_convert_image_to_rgb),
@@ -256,7 +285,8 @@ def install(force: bool = False) -> bool:
         "detectron2.modeling.proposal_generator.proposal_utils": _mod("detectron2.modeling.proposal_generator.proposal_utils",
                                                                       add_ground_truth_to_proposals=matcher.add_ground_truth_to_proposals),
         "detectron2.modeling.roi_heads": _mod("detectron2.modeling.roi_heads", __path__=[], ROI_HEADS_REGISTRY=regs["ROI_HEADS"],
-                                              StandardROIHeads=roi_heads._StandardROIHeadsBase, build_roi_heads=build_roi_heads),
+                                              StandardROIHeads=roi_heads._StandardROIHeadsBase, build_roi_heads=build_roi_heads,
+                                              FastRCNNOutputLayers=fast_rcnn.FastRCNNOutputLayers),
         "detectron2.modeling.roi_heads.fast_rcnn": _mod("detectron2.modeling.roi_heads.fast_rcnn", FastRCNNOutputLayers=fast_rcnn.FastRCNNOutputLayers),
         "detectron2.modeling.roi_heads.box_head": _mod("detectron2.modeling.roi_heads.box_head", build_box_head=build_box_head,
                                                        ROI_BOX_HEAD_REGISTRY=regs["ROI_BOX_HEAD"]),

@@ -96,19 +96,37 @@ class TrainerBase:
 
 
 class TeacherEMAHook(HookBase):
-    """Mean-teacher update as a hook: every ``period`` iterations after ``burn_up_step`` the teacher becomes
-    ``keep_rate * teacher + (1 - keep_rate) * student`` in one native launch (the reference does this inline in ``run_step``:
-    daod/engine/trainers/source_free_adaptive_teacher.py:583-603; at the burn-in boundary adaptive_teacher.py:215-217 uses
-    keep_rate 0, i.e. a copy evaluated through the same formula)."""
+    """Mean-teacher update as a hook, in one native launch per update (``keep_rate * teacher + (1 - keep_rate) * student``).
 
-    def __init__(self, student, teacher, keep_rate: float = 0.9996, period: int = 1, burn_up_step: int = 0, world_size: int = 1):
+    The reference performs the update inline in ``run_step`` at one of two places, selected here with ``when``:
+
+    * ``"before_step"`` (default) -- daod/engine/trainers/adaptive_teacher.py:215-223: at the START of iteration ``it``, before the
+      teacher pseudo-labels that iteration's batch: ``it == BURN_UP_STEP`` copies the student (keep_rate 0 through the same
+      formula, also when BURN_UP_STEP is 0), later iterations with ``(it - BURN_UP_STEP) % TEACHER_UPDATE_ITER == 0`` apply
+      ``EMA_KEEP_RATE``; nothing happens during burn-in (``it < BURN_UP_STEP``).
+    * ``"after_step"`` -- daod/engine/trainers/source_free_adaptive_teacher_single.py:581 (and ``_mosaic``): after the optimizer
+      step of EVERY iteration, with the fixed keep rate (0.9996 in those trainers); no burn-in copy.
+    """
+
+    def __init__(self, student, teacher, keep_rate: float = 0.9996, period: int = 1, burn_up_step: int = 0, world_size: int = 1,
+                 when: str = "before_step"):
         from .ema import TeacherEMA
+        if when not in ("before_step", "after_step"):
+            raise ValueError(f"when must be 'before_step' or 'after_step', got {when!r}")
         self._ema = TeacherEMA(student, teacher, world_size=world_size)
-        self._keep_rate, self._period, self._burn = float(keep_rate), int(period), int(burn_up_step)
+        self._keep_rate, self._period, self._burn, self._when = float(keep_rate), int(period), int(burn_up_step), when
+
+    def before_step(self):
+        if self._when != "before_step":
+            return
+        it = self.trainer.iter
+        if it < self._burn:
+            return
+        if it == self._burn:
+            self._ema.step(0.0)
+        elif (it - self._burn) % self._period == 0:
+            self._ema.step(self._keep_rate)
 
     def after_step(self):
-        it = self.trainer.iter
-        if it == self._burn and self._burn > 0:
-            self._ema.step(0.0)
-        elif it >= self._burn and (it - self._burn) % self._period == 0:
+        if self._when == "after_step":
             self._ema.step(self._keep_rate)

@@ -380,39 +380,62 @@ def test_teacher_step_has_one_host_sync_per_batch(teacher, cuda_device):
 
 
 @pytest.mark.gpu
-def test_teacher_ema_hook_on_the_trainer_protocol(cuda_device):
-    """The mean-teacher update driven through detectron2's hook protocol (engine.TrainerBase / HookBase): burn-in copy at
-    iteration `burn_up_step` (keep rate 0 through the same formula), then keep_rate every iteration."""
+@pytest.mark.parametrize("when", ["before_step", "after_step"])
+def test_teacher_ema_hook_on_the_trainer_protocol(cuda_device, when):
+    """The mean-teacher update driven through detectron2's hook protocol (engine.TrainerBase / HookBase).
+    before_step = reference adaptive_teacher.py:215-223: at the START of iteration BURN_UP_STEP the teacher becomes a copy of the
+    student (keep rate 0 through the same formula), i.e. teacher == student before run_step(BURN); later iterations apply
+    keep_rate before the step.  after_step = source_free_adaptive_teacher_single.py:581: keep_rate after every step."""
     import torch
     from torch import nn
     from sfod_b200.engine import TeacherEMAHook, TrainerBase
     torch.manual_seed(3)
     student = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.Linear(4, 5)).to(cuda_device)
     teacher = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.Linear(4, 5)).to(cuda_device)
-    ref_t = {k: v.clone() for k, v in teacher.state_dict().items()}
+    burn = 2 if when == "before_step" else 0
+    seen = {}
 
     class Loop(TrainerBase):
         def run_step(self):
+            if self.iter == burn and when == "before_step":
+                seen["equal_at_burn"] = all(torch.equal(a, b) for a, b in zip(student.state_dict().values(), teacher.state_dict().values()))
             with torch.no_grad():
                 for p in student.parameters():
                     p.add_(0.01)            # the student moves every iteration
 
+    def ema(expect, s_sd, keep):
+        for k in expect:
+            if expect[k].is_floating_point():
+                expect[k] = s_sd[k] * (1 - keep) + expect[k] * keep
+            else:
+                expect[k] = (s_sd[k] * (1 - keep) + expect[k] * keep).to(expect[k].dtype)
+
     loop = Loop()
-    loop.register_hooks([TeacherEMAHook(student, teacher, keep_rate=0.75, period=1, burn_up_step=2)])
-    expect = {k: v.clone() for k, v in ref_t.items()}
+    loop.register_hooks([TeacherEMAHook(student, teacher, keep_rate=0.75, period=1, burn_up_step=burn, when=when)])
+    expect = {k: v.clone() for k, v in teacher.state_dict().items()}
     s_sd = {k: v.clone() for k, v in student.state_dict().items()}
+    params = dict(student.named_parameters())
     for it in range(5):                      # the same schedule in plain torch
+        if when == "before_step" and it >= burn:
+            ema(expect, s_sd, 0.0 if it == burn else 0.75)
         for k, v in s_sd.items():
-            if v.is_floating_point() and k in dict(student.named_parameters()):
+            if k in params:
                 s_sd[k] = v + 0.01
-        keep = None if it < 2 else (0.0 if it == 2 else 0.75)
-        if keep is not None:
-            for k in expect:
-                if expect[k].is_floating_point():
-                    expect[k] = s_sd[k] * (1 - keep) + expect[k] * keep
-                else:
-                    expect[k] = (s_sd[k].float() * (1 - keep) + expect[k].float() * keep).to(expect[k].dtype)
+        if when == "after_step":
+            ema(expect, s_sd, 0.75)
     loop.train(0, 5)
+    if when == "before_step":
+        assert seen["equal_at_burn"]
     got = teacher.state_dict()
     for k in expect:
         assert torch.allclose(got[k].float(), expect[k].float(), rtol=1e-6, atol=1e-7), k
+    # the plan is cached between steps and rebuilt when a storage is replaced (reset_bn_stats does that to the running statistics)
+    hook = loop._hooks[0]
+    plan = hook._ema._plan
+    hook._ema.step(0.5)
+    assert hook._ema._plan is plan
+    teacher[1].running_mean = nn.Parameter(torch.zeros_like(teacher[1].running_mean), requires_grad=False)
+    hook._ema.step(0.5)
+    assert hook._ema._plan is not plan
+    assert torch.allclose(teacher[1].running_mean, 0.5 * student[1].running_mean)
+
