@@ -416,9 +416,51 @@ def test_frcnn_postprocess_vs_reference_faithful_oracle(ops, cuda_device):
     a = set(zip(ref["kept_rows"].tolist(), ref["pred_classes"].tolist()))
     b = set(zip(out["rows"][0, :k].cpu().tolist(), out["classes"][0, :k].cpu().tolist()))
     assert len(a ^ b) <= 2
-    if a == b and torch.equal(ref["kept_rows"], out["rows"][0, :k].cpu()):
-        _close(out["boxes"][0, :k], ref["pred_boxes"], rtol=1e-5, atol_scale=1e-6)
-        _close(out["scores"][0, :k], ref["scores"], rtol=1e-5, atol_scale=0)
+    # boxes / scores of the detections both sides kept: 1e-5 relative, whether or not a flip occurred
+    got_keys = list(zip(out["rows"][0, :k].cpu().tolist(), out["classes"][0, :k].cpu().tolist()))
+    ref_keys = list(zip(ref["kept_rows"].tolist(), ref["pred_classes"].tolist()))
+    pos = {v: j for j, v in enumerate(got_keys)}
+    ri = [j for j, v in enumerate(ref_keys) if v in pos]
+    gi = [pos[ref_keys[j]] for j in ri]
+    assert len(ri) >= len(ref_keys) - 2
+    _close(out["boxes"][0][gi], ref["pred_boxes"][ri], rtol=1e-5, atol_scale=1e-6)
+    _close(out["scores"][0][gi], ref["scores"][ri], rtol=1e-5, atol_scale=0)
+
+
+def test_frcnn_postprocess_vs_reference_executed_fixture(ops, cuda_device):
+    """tests/golden/ref_exec.npz holds what the REFERENCE'S OWN functions returned (fast_rcnn.py:88-142,
+    source_free_adaptive_teacher.py:150-183, executed by tests/golden/make_golden_ref.py) for head outputs decoded with ATen
+    exp / softmax.  The CUDA path runs from the same head outputs: identical detections and pseudo-label sets (rows, classes),
+    boxes / scores within 1e-5 -- up to the measured, rare 1-ulp flips (tests/test_gpu_flip_rate.py), none on this fixture."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_exec.npz"))
+    rows = g["frcnn_rows"].tolist()
+    sizes = [tuple(int(v) for v in g[f"frcnn_{i}_image_size"]) for i in range(len(rows))]
+    t = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    out = ops.frcnn_postprocess(t("frcnn_cls").to(cuda_device), t("frcnn_deltas").to(cuda_device), t("frcnn_proposals").to(cuda_device),
+                                rows, sizes, pseudo_thresh=0.8)
+    cnt, pc = out["count"].cpu().tolist(), out["pseudo_count"].cpu().tolist()
+    total_pl = 0
+    for i in range(len(rows)):
+        k = cnt[i]
+        assert k == len(g[f"frcnn_{i}_out_scores"])
+        assert torch.equal(out["rows"][i, :k].cpu(), t(f"frcnn_{i}_out_kept_rows")) and torch.equal(out["classes"][i, :k].cpu(), t(f"frcnn_{i}_out_pred_classes"))
+        _close(out["boxes"][i, :k], t(f"frcnn_{i}_out_pred_boxes"), rtol=1e-5, atol_scale=1e-6)
+        _close(out["scores"][i, :k], t(f"frcnn_{i}_out_scores"), rtol=1e-5, atol_scale=0)
+        assert pc[i] == len(g[f"frcnn_{i}_pl_scores"])                                    # pseudo-label set = reference's threshold_bbox
+        assert torch.equal(out["classes"][i, :pc[i]].cpu(), t(f"frcnn_{i}_pl_gt_classes"))
+        _close(out["boxes"][i, :pc[i]], t(f"frcnn_{i}_pl_gt_boxes"), rtol=1e-5, atol_scale=1e-6)
+        total_pl += pc[i]
+    assert total_pl >= 20
+    # EMA against the reference's _update_teacher_model + load_state_dict (bit-exact, incl. the int64 buffer)
+    names = [k[len("ema_s_"):] for k in g.files if k.startswith("ema_s_")]
+    for tag, rate in (("a", 0.9996), ("b", 0.999696), ("c", 0.0)):
+        sd = {n: t("ema_s_" + n).to(cuda_device) for n in names}
+        td = {n: t("ema_t_" + n).to(cuda_device) for n in names}
+        ops.EmaPlan([(sd[n], td[n]) for n in names]).step(rate)
+        for n in names:
+            want = t(f"ema_out_{tag}_{n}")
+            assert (_bits_equal(td[n], want) if want.dtype == torch.float32 else torch.equal(td[n].cpu(), want)), (tag, n)
 
 
 def test_threshold_select(ops, cuda_device):

@@ -246,6 +246,92 @@ def test_teacher_end_to_end_against_cpu_pipeline(teacher, cuda_device):
             assert v.item() == sd[k].item()
 
 
+def test_teacher_plugin_chain_bit_equal_nonempty_pseudo_labels(cfg, cuda_device):
+    """The whole teacher branch through the plugin objects -- PseudoLabRPN -> ROIPooler -> box head -> box_predictor.inference
+    -> process_pseudo_label -- with confident heads, so that the pseudo-label sets are NOT empty, against the oracle.
+
+    The dense layers (cuDNN / cuBLAS vs ATen-CPU) cannot agree bit for bit, so the oracle is fed the dense OUTPUTS the GPU run
+    produced (RPN head maps, backbone feature, class logits / box deltas, captured with forward hooks) and must then reproduce
+    every discrete and floating-point result of the hand-written kernels in between: proposals (boxes, logits, order) bit-equal,
+    pooled features to 1e-5, detections (rows, classes, scores, boxes) bit-equal, pseudo-label sets bit-equal and non-empty."""
+    torch.manual_seed(123)
+    model = registry.build_model(cfg)
+    model.train()
+    N = 2
+    img = torch.randint(0, 256, (N, 3, 600, 1200), dtype=torch.uint8, generator=torch.Generator().manual_seed(9))
+    cap = {}
+    hooks = [
+        model.proposal_generator.rpn_head.register_forward_hook(lambda m, i, out: cap.__setitem__("rpn_head", out)),
+        model.roi_heads.box_head.register_forward_pre_hook(lambda m, i: cap.__setitem__("pooled", i[0])),
+        model.roi_heads.box_predictor.register_forward_hook(lambda m, i, out: cap.__setitem__("pred", out)),
+        model.backbone.register_forward_hook(lambda m, i, out: cap.__setitem__("feat", out)),
+    ]
+    try:
+        with torch.no_grad():
+            # give the random-init heads the spread of a trained detector: objectness / anchor deltas / class logits / box deltas
+            model(img.to(cuda_device), branch="unsup_data_weak")
+            obj, dl = cap["rpn_head"]
+            cls, reg = cap["pred"]
+            rh, bp = model.proposal_generator.rpn_head, model.roi_heads.box_predictor
+            rh.objectness_logits.weight.mul_(1.0 / max(obj[0].std().item(), 1e-12))
+            rh.anchor_deltas.weight.mul_(0.5 / max(dl[0].std().item(), 1e-12))
+            bp.cls_score.weight.mul_(4.0 / max(cls.std().item(), 1e-12))
+            bp.bbox_pred.weight.mul_(1.0 / max(reg.std().item(), 1e-12))
+            _, p_rpn, p_roih = model(img.to(cuda_device), branch="unsup_data_weak")
+            pl, avg = engine.process_pseudo_label(p_roih, 0.8, "roih", "thresholding")
+    finally:
+        for h in hooks:
+            h.remove()
+    sizes = [(600, 1200)] * N
+    obj, dl = [t.cpu() for t in cap["rpn_head"][0]], [t.cpu() for t in cap["rpn_head"][1]]
+    feat = cap["feat"]["vgg4"].cpu()
+    # --- RPN: reference rpn.py:28-41 flatten + d2 predict_proposals (teacher in train mode: 12000 / 2000)
+    lg, dd = o.rpn_flatten_head_outputs(obj, dl)
+    anchors = o.grid_anchors(tuple(feat.shape[-2:]), 32, o.generate_cell_anchors())
+    r_rpn = o.rpn_predict_proposals([anchors], lg, dd, sizes, 0.7, 12000, 2000, 0.0, True, exp=o.exp_correctly_rounded)
+    counts = []
+    for g, r in zip(p_rpn, r_rpn):
+        assert torch.equal(g.proposal_boxes.tensor.cpu(), r["proposal_boxes"]) and torch.equal(g.objectness_logits.cpu(), r["objectness_logits"])
+        counts.append(len(r["proposal_boxes"]))
+    assert all(50 < c <= 2000 for c in counts), counts
+    # --- ROIAlignV2 (reference ...roi_heads.py:117): the pooled rows of each image's valid proposals, 1e-5 relative
+    P = cap["pooled"].shape[0] // N
+    want = o.roi_pooler(feat, [r["proposal_boxes"] for r in r_rpn], 7, 1 / 32, 0, "ROIAlignV2")
+    got = torch.cat([cap["pooled"][i * P:i * P + c] for i, c in enumerate(counts)]).cpu()
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+    # --- box_predictor.inference (reference ...roi_heads.py:161) on the logits / deltas of the valid rows
+    cls = torch.cat([cap["pred"][0][i * P:i * P + c] for i, c in enumerate(counts)]).cpu()
+    reg = torch.cat([cap["pred"][1][i * P:i * P + c] for i, c in enumerate(counts)]).cpu()
+    r_det = o.box_predictor_inference(cls, reg, [r["proposal_boxes"] for r in r_rpn], sizes, 0.05, 0.5, 100,
+                                      exp=o.exp_correctly_rounded, softmax=o.softmax_defined)
+    for g, r in zip(p_roih, r_det):
+        assert torch.equal(g.pred_classes.cpu(), r["pred_classes"]) and torch.equal(g.scores.cpu(), r["scores"])
+        assert torch.equal(g.pred_boxes.tensor.cpu(), r["pred_boxes"])
+    # --- threshold_bbox / process_pseudo_label (reference source_free_adaptive_teacher.py:150-183, 256-280)
+    r_pl, r_avg = o.process_pseudo_label(r_det, 0.8, "roih", "thresholding")
+    assert avg == r_avg
+    n_pl = 0
+    for g, r in zip(pl, r_pl):
+        assert torch.equal(g.gt_boxes.tensor.cpu(), r["gt_boxes"]) and torch.equal(g.gt_classes.cpu(), r["gt_classes"]) and torch.equal(g.scores.cpu(), r["scores"])
+        n_pl += len(r["scores"])
+    assert n_pl >= 20, n_pl                                 # the property that matters is tested on a NON-EMPTY set
+    assert any(len(r["scores"]) < len(d["scores"]) for r, d in zip(r_pl, r_det))   # and the filter actually removed something
+    # --- the same inputs through the ATen-faithful oracle (torch.exp / torch.softmax): identical here up to rare 1-ulp flips,
+    #     boxes / scores of the common detections within 1e-5 (unconditional)
+    a_rpn = o.rpn_predict_proposals([anchors], lg, dd, sizes, 0.7, 12000, 2000, 0.0, True)
+    for r, a in zip(r_rpn, a_rpn):
+        sa, sr = set(a["src_index"].tolist()), set(r["src_index"].tolist())
+        assert len(sa ^ sr) <= 2
+    a_det = o.box_predictor_inference(cls, reg, [r["proposal_boxes"] for r in r_rpn], sizes, 0.05, 0.5, 100)
+    for r, a in zip(r_det, a_det):
+        kr = list(zip(r["kept_rows"].tolist(), r["pred_classes"].tolist())); ka = list(zip(a["kept_rows"].tolist(), a["pred_classes"].tolist()))
+        assert len(set(kr) ^ set(ka)) <= 2
+        pos = {v: j for j, v in enumerate(kr)}
+        ia = [j for j, v in enumerate(ka) if v in pos]; ir = [pos[ka[j]] for j in ia]
+        assert torch.allclose(r["pred_boxes"][ir], a["pred_boxes"][ia], rtol=1e-5, atol=1e-4)
+        assert torch.allclose(r["scores"][ir], a["scores"][ia], rtol=1e-5, atol=0)
+
+
 def test_student_step_through_plugins_forward_backward(cfg, cuda_device):
     """SURVEY.md 8f rank 1 + 8a-a6: a student training step through the same plugins -- RPN/ROI losses in plain torch,
     ROIAlign forward AND backward on the sm_100a kernels -- produces finite losses and gradients, and its ROI-head losses
