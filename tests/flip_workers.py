@@ -21,12 +21,12 @@ IMAGE = (600, 1200)
 
 
 def frcnn_inputs(kind: str, seed: int, R: int = 2000, K: int = 8):
-    """Fast R-CNN head outputs + proposals.  'random': logits N(0,4), deltas N(0,1), uniformly random proposals (SURVEY.md 8d);
+    """Fast R-CNN head outputs + proposals.  'random': logits N(0,1.5), deltas N(0,1), uniformly random proposals (SURVEY.md 8d);
     'clustered': 200 object centres x ~10 jittered proposals each, every cluster confident in one class -- the high-suppression
     distribution a trained detector produces."""
     from sfod_b200 import synth
     if kind == "random":
-        cls, dl = synth.box_head_outputs(R, K, seed, 4.0, 1.0)
+        cls, dl = synth.box_head_outputs(R, K, seed, 1.5, 1.0)   # top-100 scores straddle the 0.8 pseudo-label threshold
         props = synth.random_rois(1, R, seed + 1)[:, 1:].contiguous()
         return cls, dl, props
     g = torch.Generator().manual_seed(seed)
@@ -40,7 +40,7 @@ def frcnn_inputs(kind: str, seed: int, R: int = 2000, K: int = 8):
                          torch.maximum(props[:, 0], props[:, 2]) + 1.0, torch.maximum(props[:, 1], props[:, 3]) + 1.0], dim=1).contiguous()
     cls_of = torch.randint(0, K, (clusters,), generator=g)
     cls = torch.randn(R, K + 1, generator=g)
-    cls[torch.arange(R), cls_of[which]] += 5.0 + torch.rand(R, generator=g) * 3.0
+    cls[torch.arange(R), cls_of[which]] += 1.0 + torch.rand(R, generator=g) * 3.5
     dl = torch.randn(R, 4 * K, generator=g) * 0.3
     return cls.contiguous(), dl.contiguous(), props
 

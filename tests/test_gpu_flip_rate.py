@@ -33,9 +33,11 @@ MAX_ELEMENTS_DIFFERING = 5e-4  # fraction of kept proposals / detections that di
 MAX_PSEUDO_SETS_DIFFERING = 0.02
 
 
-def _rel_close(a: torch.Tensor, b: torch.Tensor, rtol=1e-5) -> bool:
+def _rel_close(a: torch.Tensor, b: torch.Tensor, rtol=1e-5, scale: float = 1200.0) -> bool:
+    """|a - b| <= 1e-5 |b| + 1e-6 * scale: 1e-5 relative fp32 (BASELINE.json), with an absolute floor of 1e-6 of the coordinate
+    range for box corners that are small differences of large terms (x1 = ctr - w/2: one ulp of w is not relative to x1)."""
     a, b = a.double(), b.double()
-    return bool(((a - b).abs() <= rtol * b.abs().clamp_min(1e-30) + 1e-6 * rtol).all())
+    return bool(((a - b).abs() <= rtol * b.abs() + 1e-6 * scale).all())
 
 
 def _record(name, payload):
@@ -122,7 +124,7 @@ def test_frcnn_detection_and_pseudo_label_flip_rate(cuda_device):
                 pos = {v: j for j, v in enumerate(got_keys)}
                 ri = [j for j, v in enumerate(ref_keys) if v in pos]
                 gi = [pos[ref_keys[j]] for j in ri]
-                assert _rel_close(g_bx[i][gi], ref["pred_boxes"][ri]) and _rel_close(g_sc[i][gi], ref["scores"][ri]), (kind, sd)
+                assert _rel_close(g_bx[i][gi], ref["pred_boxes"][ri]) and _rel_close(g_sc[i][gi], ref["scores"][ri], scale=0.0), (kind, sd)
         summary[kind] = dict(images=SEEDS, detection_sets_differing=n_sets, detections=n_det, detections_differing=n_diff,
                              pseudo_labels=n_pl, pseudo_label_sets_differing=n_pl_sets, bit_exact_vs_defined_oracle=n_exact)
         assert n_pl > 0
