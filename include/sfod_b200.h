@@ -273,6 +273,17 @@ int sfod_bn_finalize_apply(const float *x, const float *pre_bias, float *y, int 
                            float *running_mean, float *running_var, int64_t *num_batches_tracked, double momentum,
                            double eps, int fuse_relu, int fuse_maxpool2, float *save_mean, float *save_invstd,
                            sfod_stream_t stream);
+/* v2 adds (i) `residual` (same shape and layout as x, may be NULL): y = [relu](fl(bn(x)) + residual) -- the tail of a
+ * detectron2 BottleneckBlock (conv3+norm, `out += shortcut`, `relu_`), which the R101-C4 configs of the reference
+ * (configs/r101_c4_cs_foggy_adaptive_teacher_source_free.yaml:5-7, RESNETS.NORM "BN") execute as three elementwise passes;
+ * (ii) `count_on_device` != 0: the element count is read from stats_dev[2*C] on the device (phase 1 writes the local count
+ * there, an all-reduce of the first 2C+1 doubles makes it global), so a multi-GPU AdaBN forward needs no host read between
+ * its two phases (reference daod/engine/trainers/base.py:270-337 on several ranks; SURVEY.md 8e collective 2). */
+int sfod_bn_finalize_apply_v2(const float *x, const float *pre_bias, const float *residual, float *y, int layout, int N, int C,
+                              int H, int W, const double *stats_dev, double total_count, int count_on_device,
+                              const float *weight, const float *bias, float *running_mean, float *running_var,
+                              int64_t *num_batches_tracked, double momentum, double eps, int fuse_relu, int fuse_maxpool2,
+                              float *save_mean, float *save_invstd, sfod_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -28,9 +28,10 @@ __device__ __forceinline__ void flush_channel(double *stats, int c, double sd, d
 }
 
 __global__ void __launch_bounds__(kThreads) bn_stats_nchw_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
-                                                                 int C, long long HW, double *__restrict__ stats) {
+                                                                 int C, long long HW, double *__restrict__ stats, double local_count) {
   __shared__ double red[2][kThreads / 32];
   const int plane = blockIdx.y;          // n * C + c
+  if (local_count > 0.0 && blockIdx.x == 0 && plane == 0 && threadIdx.x == 0) stats[2 * C] = local_count;   // third part of the all-reduce payload
   const int c = plane % C;
   const long long start = (long long)blockIdx.x * kChunk;
   const long long len = min((long long)kChunk, HW - start);
@@ -136,8 +137,10 @@ __global__ void __launch_bounds__(kThreads, 5) bn_stats_nhwc_kernel(const float 
   }
 }
 
-__global__ void __launch_bounds__(128) bn_fold_replicas_kernel(const double *__restrict__ replicas, int C, double *__restrict__ stats) {
+__global__ void __launch_bounds__(128) bn_fold_replicas_kernel(const double *__restrict__ replicas, int C, double *__restrict__ stats,
+                                                               double local_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) stats[2 * C] = local_count;
   if (i >= 2 * C) return;
   double t = 0.0;
 #pragma unroll
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(kThreads) bn_stats_nhwc_scalar_kernel(const fl
 }
 
 // One thread per channel: ATen batch_norm_cpu_update_stats arithmetic in fp64.
-__global__ void bn_finalize_kernel(const double *__restrict__ stats, int C, double n, const float *__restrict__ weight,
+__global__ void bn_finalize_kernel(const double *__restrict__ stats, int C, double n_host, int count_on_device, const float *__restrict__ weight,
                                    const float *__restrict__ bias, float *__restrict__ running_mean,
                                    float *__restrict__ running_var, long long *__restrict__ nbt, double momentum, double eps,
                                    float *__restrict__ save_mean, float *__restrict__ save_invstd, float *__restrict__ scale,
@@ -171,6 +174,7 @@ __global__ void bn_finalize_kernel(const double *__restrict__ stats, int C, doub
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
+  const double n = count_on_device ? stats[2 * C] : n_host;   // all-reduced element count: no host read between the phases
   const double mean = stats[2 * c] / n;
   double var = stats[2 * c + 1] / n - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -193,10 +197,18 @@ __device__ __forceinline__ float bn1(float v, float pb, float sc, float sh) {
   const float y = fmaf(v + pb, sc, sh);   // fl(x + conv_bias) first, exactly the tensor the reference normalises
   return kRelu ? fmaxf(y, 0.f) : y;
 }
-
+// BatchNorm -> (+ residual) -> ReLU of a ResNet bottleneck's last convolution (detectron2 BottleneckBlock.forward:
+// out = conv3(out) [conv + norm]; out += shortcut; out = relu_(out)): the normalised value is rounded to fp32 first,
+// then the shortcut is added, as in the three separate passes it replaces (12 instead of 28 B/element).
 template <bool kRelu>
+__device__ __forceinline__ float bn1r(float v, float pb, float sc, float sh, float r) {
+  const float y = __fadd_rn(fmaf(v + pb, sc, sh), r);
+  return kRelu ? fmaxf(y, 0.f) : y;
+}
+
+template <bool kRelu, bool kRes>
 __global__ void __launch_bounds__(kThreads) bn_apply_nchw_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
-                                                                 float *__restrict__ y, int C, long long HW,
+                                                                 const float *__restrict__ res, float *__restrict__ y, int C, long long HW,
                                                                  const float *__restrict__ scale, const float *__restrict__ shift) {
   const int plane = blockIdx.y;
   const int c = plane % C;
@@ -205,20 +217,30 @@ __global__ void __launch_bounds__(kThreads) bn_apply_nchw_kernel(const float *__
   if (len <= 0) return;
   const float sc = scale[c], sh = shift[c], pb = pre_bias ? pre_bias[c] : 0.f;
   const float *p = x + (size_t)plane * HW + start;
+  const float *r = kRes ? res + (size_t)plane * HW + start : nullptr;   // same 16-byte phase as x (checked by the host)
   float *q = y + (size_t)plane * HW + start;
   const int mis = (int)((reinterpret_cast<uintptr_t>(p) >> 2) & 3);
   const int head = mis ? min((long long)(4 - mis), len) : 0;
-  if (threadIdx.x < head) q[threadIdx.x] = bn1<kRelu>(p[threadIdx.x], pb, sc, sh);
+  if (threadIdx.x < head) q[threadIdx.x] = kRes ? bn1r<kRelu>(p[threadIdx.x], pb, sc, sh, r[threadIdx.x]) : bn1<kRelu>(p[threadIdx.x], pb, sc, sh);
   const float4 *p4 = reinterpret_cast<const float4 *>(p + head);
+  const float4 *r4 = reinterpret_cast<const float4 *>(r + head);
   float4 *q4 = reinterpret_cast<float4 *>(q + head);
   const int n4 = (int)((len - head) >> 2);
 #pragma unroll 4
   for (int i = threadIdx.x; i < n4; i += kThreads) {
     const float4 v = p4[i];
-    q4[i] = make_float4(bn1<kRelu>(v.x, pb, sc, sh), bn1<kRelu>(v.y, pb, sc, sh), bn1<kRelu>(v.z, pb, sc, sh), bn1<kRelu>(v.w, pb, sc, sh));
+    if (kRes) {
+      const float4 w = __ldg(r4 + i);
+      q4[i] = make_float4(bn1r<kRelu>(v.x, pb, sc, sh, w.x), bn1r<kRelu>(v.y, pb, sc, sh, w.y), bn1r<kRelu>(v.z, pb, sc, sh, w.z), bn1r<kRelu>(v.w, pb, sc, sh, w.w));
+    } else {
+      q4[i] = make_float4(bn1<kRelu>(v.x, pb, sc, sh), bn1<kRelu>(v.y, pb, sc, sh), bn1<kRelu>(v.z, pb, sc, sh), bn1<kRelu>(v.w, pb, sc, sh));
+    }
   }
   const int tail0 = head + (n4 << 2);
-  if (tail0 + (int)threadIdx.x < len) q[tail0 + threadIdx.x] = bn1<kRelu>(p[tail0 + threadIdx.x], pb, sc, sh);
+  if (tail0 + (int)threadIdx.x < len) {
+    const int t = tail0 + threadIdx.x;
+    q[t] = kRes ? bn1r<kRelu>(p[t], pb, sc, sh, r[t]) : bn1<kRelu>(p[t], pb, sc, sh);
+  }
 }
 
 // Normalise (+ReLU) fused with the 2x2 / stride-2 max-pool that follows the last BN of every VGG stage
@@ -261,11 +283,12 @@ __global__ void __launch_bounds__(kThreads) bn_apply_pool_nchw_kernel(const floa
   }
 }
 
-template <bool kRelu>
+template <bool kRelu, bool kRes>
 __global__ void __launch_bounds__(kThreads) bn_apply_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
-                                                                 float *__restrict__ y, long long total4, int G,
+                                                                 const float *__restrict__ res, float *__restrict__ y, long long total4, int G,
                                                                  const float *__restrict__ scale, const float *__restrict__ shift) {
   const float4 *x4 = reinterpret_cast<const float4 *>(x);
+  const float4 *r4 = reinterpret_cast<const float4 *>(res);
   float4 *y4 = reinterpret_cast<float4 *>(y);
   const float4 *sc4 = reinterpret_cast<const float4 *>(scale), *sh4 = reinterpret_cast<const float4 *>(shift);
   const float4 *pb4 = reinterpret_cast<const float4 *>(pre_bias);
@@ -273,8 +296,14 @@ __global__ void __launch_bounds__(kThreads) bn_apply_nhwc_kernel(const float *__
     const int g = (int)(i % G);
     const float4 v = x4[i], sc = __ldg(sc4 + g), sh = __ldg(sh4 + g);
     const float4 pb = pre_bias ? __ldg(pb4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-    y4[i] = make_float4(bn1<kRelu>(v.x, pb.x, sc.x, sh.x), bn1<kRelu>(v.y, pb.y, sc.y, sh.y), bn1<kRelu>(v.z, pb.z, sc.z, sh.z),
-                        bn1<kRelu>(v.w, pb.w, sc.w, sh.w));
+    if (kRes) {
+      const float4 w = __ldg(r4 + i);
+      y4[i] = make_float4(bn1r<kRelu>(v.x, pb.x, sc.x, sh.x, w.x), bn1r<kRelu>(v.y, pb.y, sc.y, sh.y, w.y),
+                          bn1r<kRelu>(v.z, pb.z, sc.z, sh.z, w.z), bn1r<kRelu>(v.w, pb.w, sc.w, sh.w, w.w));
+    } else {
+      y4[i] = make_float4(bn1<kRelu>(v.x, pb.x, sc.x, sh.x), bn1<kRelu>(v.y, pb.y, sc.y, sh.y), bn1<kRelu>(v.z, pb.z, sc.z, sh.z),
+                          bn1<kRelu>(v.w, pb.w, sc.w, sh.w));
+    }
   }
 }
 
@@ -307,11 +336,12 @@ __global__ void __launch_bounds__(kThreads) bn_apply_pool_nhwc_kernel(const floa
 
 template <bool kRelu>
 __global__ void __launch_bounds__(kThreads) bn_apply_nhwc_scalar_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
-                                                                        float *__restrict__ y, long long total, int C,
+                                                                        const float *__restrict__ res, float *__restrict__ y, long long total, int C,
                                                                         const float *__restrict__ scale, const float *__restrict__ shift) {
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
     const int c = (int)(i % C);
-    y[i] = bn1<kRelu>(x[i], pre_bias ? pre_bias[c] : 0.f, scale[c], shift[c]);
+    const float pb = pre_bias ? pre_bias[c] : 0.f;
+    y[i] = res ? bn1r<kRelu>(x[i], pb, scale[c], shift[c], res[i]) : bn1<kRelu>(x[i], pb, scale[c], shift[c]);
   }
 }
 
@@ -320,8 +350,6 @@ __global__ void __launch_bounds__(kThreads) bn_apply_nhwc_scalar_kernel(const fl
 SFOD_API size_t sfod_bn_stats_bytes(int C) {
   return C > 0 ? sfod_align_up((size_t)C * (4 + 2 * kStatReplicas) * sizeof(double), 256) : 256;
 }
-// stats_dev layout: [0, 2C) doubles = (sum x, sum x^2) per channel (the all-reduce payload);
-// [2C, 4C) reused by phase 2 as float scale/shift scratch; [4C, 4C + 2C * kStatReplicas) replica totals of the NHWC pass.
 
 SFOD_API int sfod_bn_partial_stats(const float *x, const float *pre_bias, int layout, int N, int C, int64_t HW, double *stats_dev,
                                    sfod_stream_t stream) {
@@ -336,7 +364,7 @@ SFOD_API int sfod_bn_partial_stats(const float *x, const float *pre_bias, int la
     for (long long p0 = 0; p0 < planes; p0 += step) {
       const long long np = planes - p0 < step ? planes - p0 : step;
       dim3 grid((unsigned)((HW + kChunk - 1) / kChunk), (unsigned)np);
-      bn_stats_nchw_kernel<<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, pre_bias, C, HW, stats_dev);
+      bn_stats_nchw_kernel<<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, pre_bias, C, HW, stats_dev, p0 == 0 ? (double)N * (double)HW : 0.0);
       SFOD_LAUNCH_CHECK();
     }
     return SFOD_OK;
@@ -345,6 +373,8 @@ SFOD_API int sfod_bn_partial_stats(const float *x, const float *pre_bias, int la
   if ((C & 3) || !sfod_aligned16(x) || (pre_bias && !sfod_aligned16(pre_bias))) {
     bn_stats_nhwc_scalar_kernel<<<C, kThreads, 0, st>>>(x, pre_bias, M, C, stats_dev);
     SFOD_LAUNCH_CHECK();
+    const double cnt = (double)M;
+    SFOD_CUDA_TRY(cudaMemcpyAsync(stats_dev + 2 * (size_t)C, &cnt, sizeof(double), cudaMemcpyHostToDevice, st));   // pageable 8 B: staged by the driver
     return SFOD_OK;
   }
   const int G = C >> 2;
@@ -359,23 +389,27 @@ SFOD_API int sfod_bn_partial_stats(const float *x, const float *pre_bias, int la
   SFOD_CUDA_TRY(cudaMemsetAsync(replicas, 0, (size_t)C * 2 * kStatReplicas * sizeof(double), st));   // totals were zeroed above
   bn_stats_nhwc_kernel<<<grid, kThreads, smem, st>>>(x, pre_bias, M, C, cols, rowlanes, nrows, replicas);
   SFOD_LAUNCH_CHECK();
-  bn_fold_replicas_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(replicas, C, stats_dev);
+  bn_fold_replicas_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(replicas, C, stats_dev, (double)N * (double)HW);
   SFOD_LAUNCH_CHECK();
   return SFOD_OK;
 }
 
-SFOD_API int sfod_bn_finalize_apply(const float *x, const float *pre_bias, float *y, int layout, int N, int C, int H, int W,
-                                    const double *stats_dev, double total_count, const float *weight, const float *bias,
-                                    float *running_mean, float *running_var, int64_t *num_batches_tracked, double momentum,
-                                    double eps, int fuse_relu, int fuse_maxpool2, float *save_mean, float *save_invstd,
-                                    sfod_stream_t stream) {
-  if (!stats_dev || N <= 0 || C <= 0 || H <= 0 || W <= 0 || total_count <= 0) return SFOD_ERR_INVALID_ARG;
+// stats_dev layout: [0, 2C) (sum x, sum x^2); [2C] element count of this rank (written by phase 1; with [0, 2C) it forms the
+// 2C+1 all-reduce payload); [2C + 2, ...) float scale / shift scratch of phase 2; [4C, ...) replica totals of the NHWC pass.
+SFOD_API int sfod_bn_finalize_apply_v2(const float *x, const float *pre_bias, const float *residual, float *y, int layout, int N, int C,
+                                       int H, int W, const double *stats_dev, double total_count, int count_on_device,
+                                       const float *weight, const float *bias, float *running_mean, float *running_var,
+                                       int64_t *num_batches_tracked, double momentum, double eps, int fuse_relu, int fuse_maxpool2,
+                                       float *save_mean, float *save_invstd, sfod_stream_t stream) {
+  if (!stats_dev || N <= 0 || C <= 0 || H <= 0 || W <= 0 || (!count_on_device && total_count <= 0)) return SFOD_ERR_INVALID_ARG;
   if (layout != SFOD_NCHW && layout != SFOD_NHWC) return SFOD_ERR_INVALID_ARG;
+  if (residual && fuse_maxpool2) return SFOD_ERR_INVALID_ARG;
+  if (residual && x && ((reinterpret_cast<uintptr_t>(residual) ^ reinterpret_cast<uintptr_t>(x)) & 15u)) return SFOD_ERR_ALIGNMENT;
   cudaStream_t st = sfod_cu(stream);
   const long long HW = (long long)H * W;
-  float *scale = reinterpret_cast<float *>(const_cast<double *>(stats_dev) + 2 * (size_t)C);
+  float *scale = reinterpret_cast<float *>(const_cast<double *>(stats_dev) + 2 * (size_t)C + 2);
   float *shift = scale + sfod_align_up((size_t)C, 4);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_dev, C, total_count, weight, bias, running_mean, running_var,
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_dev, C, total_count, count_on_device, weight, bias, running_mean, running_var,
                                                       reinterpret_cast<long long *>(num_batches_tracked), momentum, eps,
                                                       save_mean, save_invstd, scale, shift);
   SFOD_LAUNCH_CHECK();
@@ -420,8 +454,15 @@ SFOD_API int sfod_bn_finalize_apply(const float *x, const float *pre_bias, float
     for (long long p0 = 0; p0 < planes; p0 += step) {
       const long long np = planes - p0 < step ? planes - p0 : step;
       dim3 grid((unsigned)((HW + kChunk - 1) / kChunk), (unsigned)np);
-      if (fuse_relu) bn_apply_nchw_kernel<true><<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, pre_bias, y + (size_t)p0 * HW, C, HW, scale, shift);
-      else bn_apply_nchw_kernel<false><<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, pre_bias, y + (size_t)p0 * HW, C, HW, scale, shift);
+      const float *xp = x + (size_t)p0 * HW, *rp = residual ? residual + (size_t)p0 * HW : nullptr;
+      float *yp = y + (size_t)p0 * HW;
+      if (residual) {
+        if (fuse_relu) bn_apply_nchw_kernel<true, true><<<grid, kThreads, 0, st>>>(xp, pre_bias, rp, yp, C, HW, scale, shift);
+        else bn_apply_nchw_kernel<false, true><<<grid, kThreads, 0, st>>>(xp, pre_bias, rp, yp, C, HW, scale, shift);
+      } else {
+        if (fuse_relu) bn_apply_nchw_kernel<true, false><<<grid, kThreads, 0, st>>>(xp, pre_bias, rp, yp, C, HW, scale, shift);
+        else bn_apply_nchw_kernel<false, false><<<grid, kThreads, 0, st>>>(xp, pre_bias, rp, yp, C, HW, scale, shift);
+      }
       SFOD_LAUNCH_CHECK();
     }
     return SFOD_OK;
@@ -429,14 +470,28 @@ SFOD_API int sfod_bn_finalize_apply(const float *x, const float *pre_bias, float
   const long long total = (long long)N * HW * C;
   if ((C & 3) || !sfod_aligned16(x) || !sfod_aligned16(y) || (pre_bias && !sfod_aligned16(pre_bias))) {
     const unsigned grid = (unsigned)min((long long)SFOD_NUM_SMS * 8, (total + kThreads - 1) / kThreads);
-    if (fuse_relu) bn_apply_nhwc_scalar_kernel<true><<<grid, kThreads, 0, st>>>(x, pre_bias, y, total, C, scale, shift);
-    else bn_apply_nhwc_scalar_kernel<false><<<grid, kThreads, 0, st>>>(x, pre_bias, y, total, C, scale, shift);
+    if (fuse_relu) bn_apply_nhwc_scalar_kernel<true><<<grid, kThreads, 0, st>>>(x, pre_bias, residual, y, total, C, scale, shift);
+    else bn_apply_nhwc_scalar_kernel<false><<<grid, kThreads, 0, st>>>(x, pre_bias, residual, y, total, C, scale, shift);
   } else {
     const long long total4 = total >> 2;
     const unsigned grid = (unsigned)min((long long)SFOD_NUM_SMS * 16, (total4 + kThreads - 1) / kThreads);
-    if (fuse_relu) bn_apply_nhwc_kernel<true><<<grid, kThreads, 0, st>>>(x, pre_bias, y, total4, C >> 2, scale, shift);
-    else bn_apply_nhwc_kernel<false><<<grid, kThreads, 0, st>>>(x, pre_bias, y, total4, C >> 2, scale, shift);
+    if (residual) {
+      if (fuse_relu) bn_apply_nhwc_kernel<true, true><<<grid, kThreads, 0, st>>>(x, pre_bias, residual, y, total4, C >> 2, scale, shift);
+      else bn_apply_nhwc_kernel<false, true><<<grid, kThreads, 0, st>>>(x, pre_bias, residual, y, total4, C >> 2, scale, shift);
+    } else {
+      if (fuse_relu) bn_apply_nhwc_kernel<true, false><<<grid, kThreads, 0, st>>>(x, pre_bias, residual, y, total4, C >> 2, scale, shift);
+      else bn_apply_nhwc_kernel<false, false><<<grid, kThreads, 0, st>>>(x, pre_bias, residual, y, total4, C >> 2, scale, shift);
+    }
   }
   SFOD_LAUNCH_CHECK();
   return SFOD_OK;
+}
+
+SFOD_API int sfod_bn_finalize_apply(const float *x, const float *pre_bias, float *y, int layout, int N, int C, int H, int W,
+                                    const double *stats_dev, double total_count, const float *weight, const float *bias,
+                                    float *running_mean, float *running_var, int64_t *num_batches_tracked, double momentum,
+                                    double eps, int fuse_relu, int fuse_maxpool2, float *save_mean, float *save_invstd,
+                                    sfod_stream_t stream) {
+  return sfod_bn_finalize_apply_v2(x, pre_bias, nullptr, y, layout, N, C, H, W, stats_dev, total_count, 0, weight, bias, running_mean,
+                                   running_var, num_batches_tracked, momentum, eps, fuse_relu, fuse_maxpool2, save_mean, save_invstd, stream);
 }

@@ -234,6 +234,12 @@ __device__ __forceinline__ void sep_row_fma(float2 (&T)[kPW], const float *__res
   T[6].x = fmaf(w1.z, f.x, T[6].x); T[6].y = fmaf(w1.z, f.y, T[6].y);
 }
 
+// Programmatic dependent launch: the table pre-kernel releases its dependents at once, the forward kernel is launched with
+// programmatic stream serialization and blocks here until the pre-kernel's memory is visible -- launch latency and the
+// prologue of the big kernel overlap the small one.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- per-ROI table records (forward).  A small pre-kernel builds, for every ROI, the record the forward kernel needs:
 //   ints  [0..31]  lim: [0..1] ymin, ymax; [2..3] xmin, xmax; [4..10] / [11..17] first / last row of bin ph;
 //                       [18..24] first column of the compact window of bin pw; [25] window width of the ROI: 2, 3, 4, 6, 8
@@ -253,6 +259,7 @@ __global__ void __launch_bounds__(128) roi_sep_tables_kernel(const float *__rest
   const int rec = sep_rec_floats(H);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + warp;
+  pdl_launch_dependents();   // the forward kernel may start its prologue; it waits (griddepcontrol.wait) before touching recs
   if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;   // work counter of the forward kernel that follows in stream order
   if (r >= R) return;
   float *my = tb_smem + (size_t)warp * rec;
@@ -623,10 +630,16 @@ __global__ void __launch_bounds__(kSepThreads, 3) roi_align_fwd_sep_kernel(const
 constexpr int kSlabCh = 32;
 constexpr int kSlabStage = kSlabCh * kBins;            // 1 568 floats staged per warp
 constexpr int kSlabMaxImages = 1024;                   // presence bitmap (32 words)
+// Pixel stride of the resident slab in floats.  32: the source is channels-last, pixels are copied as they lie (16-byte
+// cp.async).  33: the source is NCHW and is transposed ON THE WAY IN by 4-byte cp.async (lane = pixel of one channel plane,
+// coalesced reads); the odd stride makes both the transposing writes (bank = px + c) and the compute reads (lane = channel)
+// conflict-free, so the separate NCHW->NHWC transpose launch and its 8 B/element of traffic disappear.
+constexpr int kPSNhwc = kSlabCh, kPSNchw = kSlabCh + 1;
 
+__host__ __device__ inline size_t slab_floats(int H, int W, int ps) { return ((size_t)H * W * ps + 31) / 32 * 32; }
 __host__ __device__ inline size_t slab_warp_floats(int H) { return (size_t)kSlabStage + 2 * (size_t)sep_rec_floats(H); }
-__host__ __device__ inline size_t slab_smem_bytes(int H, int W, int warps) {
-  return ((size_t)H * W * kSlabCh + (size_t)warps * slab_warp_floats(H)) * 4 + 40 * 4;
+__host__ __device__ inline size_t slab_smem_bytes(int H, int W, int warps, int ps) {
+  return (slab_floats(H, W, ps) + (size_t)warps * slab_warp_floats(H)) * 4 + 40 * 4;
 }
 
 __device__ __forceinline__ void slab_stage_wait_free() {   // this warp's previous bulk store has finished reading its stage
@@ -666,7 +679,7 @@ __device__ __forceinline__ float slab_lds(unsigned addr) {   // ld.shared with a
   return v;
 }
 
-template <int NX>
+template <int NX, int kPS>
 __device__ __forceinline__ void slab_rows_compact(const float *__restrict__ S, int W, const int *__restrict__ lim,
                                                   const float *__restrict__ Bc, const float *__restrict__ Ad,
                                                   float (&acc)[kPH][kPW]) {
@@ -675,12 +688,12 @@ __device__ __forceinline__ void slab_rows_compact(const float *__restrict__ S, i
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(S);
 #pragma unroll
   for (int b = 0; b < kPW; ++b) {
-    pb[b] = sbase + (unsigned)lim[18 + b] * (kSlabCh * 4);
+    pb[b] = sbase + (unsigned)lim[18 + b] * (kPS * 4);
 #pragma unroll
     for (int j = 0; j < NX; ++j) bw[b][j] = Bc[b * kNXMax + j];
   }
   const int y0 = lim[0], y1 = lim[1];
-  const unsigned rstride = (unsigned)W * (kSlabCh * 4);
+  const unsigned rstride = (unsigned)W * (kPS * 4);
   for (int y = y0; y <= y1; ++y) {
     const float4 a0 = *reinterpret_cast<const float4 *>(Ad + y * 8), a1 = *reinterpret_cast<const float4 *>(Ad + y * 8 + 4);
     const float av[kPH] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z};
@@ -692,26 +705,27 @@ __device__ __forceinline__ void slab_rows_compact(const float *__restrict__ S, i
     for (int b = 0; b < kPW; ++b) {
       const unsigned p = pb[b] + ro;
       T[b] = bw[b][0] * slab_lds<0>(p);
-      if (NX > 1) T[b] = fmaf(bw[b][1 % NX], slab_lds<kSlabCh * 4>(p), T[b]);
-      if (NX > 2) T[b] = fmaf(bw[b][2 % NX], slab_lds<2 * kSlabCh * 4>(p), T[b]);
-      if (NX > 3) T[b] = fmaf(bw[b][3 % NX], slab_lds<3 * kSlabCh * 4>(p), T[b]);
+      if (NX > 1) T[b] = fmaf(bw[b][1 % NX], slab_lds<kPS * 4>(p), T[b]);
+      if (NX > 2) T[b] = fmaf(bw[b][2 % NX], slab_lds<2 * kPS * 4>(p), T[b]);
+      if (NX > 3) T[b] = fmaf(bw[b][3 % NX], slab_lds<3 * kPS * 4>(p), T[b]);
     }
     slab_accumulate(acc, av, T, info);
   }
 }
 
 // wide-bin fallback: dense column table Bd (W x 8, built by the warp in its own stage buffer)
+template <int kPS>
 __device__ __forceinline__ void slab_rows_dense(const float *__restrict__ S, int W, const int *__restrict__ lim,
                                                 const float *__restrict__ Bd, const float *__restrict__ Ad,
                                                 float (&acc)[kPH][kPW]) {
   const int y0 = lim[0], y1 = lim[1], x0 = lim[2], x1 = lim[3];
   for (int y = y0; y <= y1; ++y) {
-    const float *row = S + y * W * kSlabCh;
+    const float *row = S + y * W * kPS;
     float T[kPW];
 #pragma unroll
     for (int b = 0; b < kPW; ++b) T[b] = 0.f;
     for (int x = x0; x <= x1; ++x) {
-      const float f = row[x * kSlabCh];
+      const float f = row[x * kPS];
       const float4 w0 = *reinterpret_cast<const float4 *>(Bd + x * 8), w1 = *reinterpret_cast<const float4 *>(Bd + x * 8 + 4);
       T[0] = fmaf(w0.x, f, T[0]); T[1] = fmaf(w0.y, f, T[1]); T[2] = fmaf(w0.z, f, T[2]); T[3] = fmaf(w0.w, f, T[3]);
       T[4] = fmaf(w1.x, f, T[4]); T[5] = fmaf(w1.y, f, T[5]); T[6] = fmaf(w1.z, f, T[6]);
@@ -722,8 +736,8 @@ __device__ __forceinline__ void slab_rows_dense(const float *__restrict__ S, int
   }
 }
 
-template <int kWarps>
-__global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab_kernel(const float *__restrict__ feat /* NHWC */,
+template <int kWarps, int kPS>
+__global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab_kernel(const float *__restrict__ feat /* kPS == 32: NHWC, 33: NCHW */,
                                                                             const float *__restrict__ rois,
                                                                             const float *__restrict__ recs, int N, int C, int H,
                                                                             int W, int R, float scale, int sampling_ratio,
@@ -733,9 +747,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab_kernel(cons
   const int HW = H * W;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float *slab = sep_smem;
-  float *mine = slab + (size_t)HW * kSlabCh + (size_t)warp * slab_warp_floats(H);
+  float *mine = slab + slab_floats(H, W, kPS) + (size_t)warp * slab_warp_floats(H);
   float *stage = mine, *recbuf = mine + kSlabStage;
-  int *ctrl = reinterpret_cast<int *>(slab + (size_t)HW * kSlabCh + (size_t)kWarps * slab_warp_floats(H));
+  int *ctrl = reinterpret_cast<int *>(slab + slab_floats(H, W, kPS) + (size_t)kWarps * slab_warp_floats(H));
   int *s_ticket = ctrl, *s_invalid = ctrl + 1, *s_span = ctrl + 2;
   unsigned *s_present = reinterpret_cast<unsigned *>(ctrl + 8);   // kSlabMaxImages bits
 
@@ -745,6 +759,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab_kernel(cons
   const long long total = (long long)nslab * R;
   long long lo = total * blockIdx.x / gridDim.x;
   const long long hi = total * (blockIdx.x + 1) / gridDim.x;
+  pdl_wait();   // the table records of the pre-kernel are visible from here on
 
   auto fetch_rec = [&](int r, int b) {   // warp-wide cp.async of one table record
     const float4 *src = reinterpret_cast<const float4 *>(recs + (size_t)r * rec);
@@ -776,13 +791,22 @@ __global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab_kernel(cons
     for (int n = -1; n < N; ++n) {   // n == -1: ROIs with an invalid image index (zero output, no slab needed)
       if (n < 0 ? (*s_invalid == 0) : !((s_present[n >> 5] >> (n & 31)) & 1u)) continue;   // CTA-uniform
       if (n >= 0) {
-        const float *src = feat + (size_t)n * HW * C + cbase;
         const unsigned dst = (unsigned)__cvta_generic_to_shared(slab);
-        const int q4 = nch >> 2;   // 16-byte chunks per pixel
-        for (int idx = tid; idx < HW * 8; idx += kWarps * 32) {
-          const int px = idx >> 3, q = idx & 7;
-          if (q < q4)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * idx), "l"(src + (size_t)px * C + q * 4) : "memory");
+        if (kPS == kPSNhwc) {
+          const float *src = feat + (size_t)n * HW * C + cbase;
+          const int q4 = nch >> 2;   // 16-byte chunks per pixel
+          for (int idx = tid; idx < HW * 8; idx += kWarps * 32) {
+            const int px = idx >> 3, q = idx & 7;
+            if (q < q4)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * idx), "l"(src + (size_t)px * C + q * 4) : "memory");
+          }
+        } else {   // NCHW: one channel plane per warp pass, lanes over pixels; smem word px * 33 + c
+          const float *src = feat + ((size_t)n * C + cbase) * HW;
+          for (int c = warp; c < nch; c += kWarps) {
+            const float *plane = src + (size_t)c * HW;
+            for (int px = lane; px < HW; px += 32)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (unsigned)(px * kPS + c)), "l"(plane + px) : "memory");
+          }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
@@ -823,9 +847,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab_kernel(cons
           const bool empty = n < 0 || lim[1] < lim[0] || lim[3] < lim[2];
           if (!empty) {
             const int nx = lim[25];
-            if (nx <= 2) slab_rows_compact<2>(S, W, lim, rb + 32, rb + kRecHead, acc);
-            else if (nx == 3) slab_rows_compact<3>(S, W, lim, rb + 32, rb + kRecHead, acc);
-            else if (nx == 4) slab_rows_compact<4>(S, W, lim, rb + 32, rb + kRecHead, acc);
+            if (nx <= 2) slab_rows_compact<2, kPS>(S, W, lim, rb + 32, rb + kRecHead, acc);
+            else if (nx == 3) slab_rows_compact<3, kPS>(S, W, lim, rb + 32, rb + kRecHead, acc);
+            else if (nx == 4) slab_rows_compact<4, kPS>(S, W, lim, rb + 32, rb + kRecHead, acc);
             else {   // wide bins: dense column table, built by this warp in its (drained) stage buffer
               slab_stage_wait_free();
               const RoiGeom g = roi_geometry(rois + 5 * (size_t)t, scale, aligned, kPH, kPW, sampling_ratio);
@@ -840,7 +864,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab_kernel(cons
                 }
               }
               __syncwarp();
-              slab_rows_dense(S, W, lim, stage, rb + kRecHead, acc);
+              slab_rows_dense<kPS>(S, W, lim, stage, rb + kRecHead, acc);
               __syncwarp();
             }
           }
@@ -867,6 +891,282 @@ __global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab_kernel(cons
         t = tn; buf ^= 1;
       }
       __syncthreads();   // every warp is done with this slab (and with the ticket counter)
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---- 16-channel slab, two half-warps per ROI (maps whose 32-channel slab does not fit: R101-C4 res4, 38 x 75).
+// One image x 16 channels (H*W*64 B; 182 KB for 38 x 75) stays resident.  A warp still owns one ROI at a time, but its two
+// half-warps take ALTERNATE ROWS of the ROI (lane & 15 = channel): the row stride of the slab is kept odd in pixels, so rows y
+// and y + 1 start in opposite 64-byte halves of the 128-byte bank window and the two 64-byte reads of a warp instruction never
+// collide.  Both halves run the same compact-column code on the same record; the bins fed by the two rows are covered by one
+// warp-uniform switch on the union of their runs (the other half's weights are exact zeros), and the partial sums are
+// combined with 49 shuffles before the (16 x 49) tile leaves as one 3 136 B bulk store.  The next record is prefetched into
+// registers (the slab leaves room for one record per warp).
+constexpr int kS16Ch = 16;
+constexpr int kS16Stage = kS16Ch * kBins;   // 784 floats = 3 136 B per warp
+__host__ __device__ inline int s16_row_px(int W) { return W | 1; }   // odd row stride in pixels
+__host__ __device__ inline size_t s16_slab_floats(int H, int W) { return ((size_t)H * s16_row_px(W) * kS16Ch + 31) / 32 * 32; }
+__host__ __device__ inline size_t s16_warp_floats(int H) { return (size_t)kS16Stage + (size_t)sep_rec_floats(H); }
+__host__ __device__ inline size_t s16_smem_bytes(int H, int W, int warps) {
+  return (s16_slab_floats(H, W) + (size_t)warps * s16_warp_floats(H)) * 4 + 40 * 4;
+}
+
+// acc[a][:] += av[a] * T[:] for a in [first, last]: a loop over the bins with one 7-way switch per bin.  (The fully
+// unrolled switch-on-first-bin of the 32-channel kernel costs ~300 instructions per instance; here one instance serves all
+// window widths, which keeps the row loop inside the instruction cache -- "no instruction" was the top stall before.)
+__device__ __forceinline__ void s16_accumulate(float (&acc)[kPH][kPW], const float (&av)[kPH], const float (&T)[kPW], int first, int last) {
+  for (int a = first; a <= last; ++a) {
+    switch (a) {
+#define SFOD_S16_CASE(A)                                                              \
+      case A:                                                                         \
+        _Pragma("unroll") for (int b = 0; b < kPW; ++b) acc[A][b] = fmaf(av[A], T[b], acc[A][b]); \
+        break;
+      SFOD_S16_CASE(0) SFOD_S16_CASE(1) SFOD_S16_CASE(2) SFOD_S16_CASE(3) SFOD_S16_CASE(4) SFOD_S16_CASE(5)
+      default:
+#pragma unroll
+        for (int b = 0; b < kPW; ++b) acc[6][b] = fmaf(av[6], T[b], acc[6][b]);
+        break;
+#undef SFOD_S16_CASE
+    }
+  }
+}
+
+template <int NX>
+__device__ __forceinline__ void s16_row_T(float (&T)[kPW], const float (&bw)[kPW][kNXMax], const unsigned (&pb)[kPW], unsigned ro) {
+#pragma unroll
+  for (int b = 0; b < kPW; ++b) {
+    const unsigned p = pb[b] + ro;
+    T[b] = bw[b][0] * slab_lds<0>(p);
+    if (NX > 1) T[b] = fmaf(bw[b][1], slab_lds<kS16Ch * 4>(p), T[b]);
+    if (NX > 2) T[b] = fmaf(bw[b][2], slab_lds<2 * kS16Ch * 4>(p), T[b]);
+    if (NX > 3) T[b] = fmaf(bw[b][3], slab_lds<3 * kS16Ch * 4>(p), T[b]);
+    if (NX > 4) T[b] = fmaf(bw[b][4], slab_lds<4 * kS16Ch * 4>(p), T[b]);
+    if (NX > 5) T[b] = fmaf(bw[b][5], slab_lds<5 * kS16Ch * 4>(p), T[b]);
+    if (NX > 6) T[b] = fmaf(bw[b][6], slab_lds<6 * kS16Ch * 4>(p), T[b]);
+    if (NX > 7) T[b] = fmaf(bw[b][7], slab_lds<7 * kS16Ch * 4>(p), T[b]);
+  }
+}
+
+// rows of one ROI, compact column windows of width nx in {2, 3, 4, 6, 8} (warp-uniform, from the record)
+__device__ __forceinline__ void s16_rows_compact(const float *__restrict__ S, int half, int Wp, const int *__restrict__ lim,
+                                                 const float *__restrict__ Bc, const float *__restrict__ Ad, int nx,
+                                                 float (&acc)[kPH][kPW]) {
+  float bw[kPW][kNXMax];
+  unsigned pb[kPW];
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(S);
+#pragma unroll
+  for (int b = 0; b < kPW; ++b) {
+    pb[b] = sbase + (unsigned)lim[18 + b] * (kS16Ch * 4);
+    const float4 w0 = *reinterpret_cast<const float4 *>(Bc + b * kNXMax), w1 = *reinterpret_cast<const float4 *>(Bc + b * kNXMax + 4);
+    bw[b][0] = w0.x; bw[b][1] = w0.y; bw[b][2] = w0.z; bw[b][3] = w0.w; bw[b][4] = w1.x; bw[b][5] = w1.y; bw[b][6] = w1.z; bw[b][7] = w1.w;
+  }
+  const int y0 = lim[0], y1 = lim[1];
+  const unsigned rstride = (unsigned)Wp * (kS16Ch * 4);
+  for (int yy = y0; yy <= y1; yy += 2) {
+    const bool live = yy + half <= y1;
+    const int y = live ? yy + half : y1;        // the idle half re-reads a valid row with zero weights
+    const float4 a0 = *reinterpret_cast<const float4 *>(Ad + y * 8), a1 = *reinterpret_cast<const float4 *>(Ad + y * 8 + 4);
+    const int info = live ? __float_as_int(a1.w) : 0;
+    int first = info ? (info & 0xff) : kPH, last = info ? first + (info >> 8) - 1 : -1;
+    first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, 16));
+    last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, 16));
+    if (last < first) continue;                  // warp-uniform: neither row feeds a bin
+    const float z = live ? 1.0f : 0.0f;
+    const float av[kPH] = {a0.x * z, a0.y * z, a0.z * z, a0.w * z, a1.x * z, a1.y * z, a1.z * z};
+    const unsigned ro = (unsigned)y * rstride;
+    float T[kPW];
+    if (nx <= 2) s16_row_T<2>(T, bw, pb, ro);
+    else if (nx == 3) s16_row_T<3>(T, bw, pb, ro);
+    else if (nx == 4) s16_row_T<4>(T, bw, pb, ro);
+    else if (nx == 6) s16_row_T<6>(T, bw, pb, ro);
+    else s16_row_T<8>(T, bw, pb, ro);
+    s16_accumulate(acc, av, T, first, last);
+  }
+}
+
+// wide-bin fallback (window > kNXMax columns): dense column table Bd (W x 8) built by the warp in its stage buffer
+__device__ __forceinline__ void s16_rows_dense(const float *__restrict__ S, int half, int Wp, const int *__restrict__ lim,
+                                               const float *__restrict__ Bd, const float *__restrict__ Ad,
+                                               float (&acc)[kPH][kPW]) {
+  const int y0 = lim[0], y1 = lim[1], x0 = lim[2], x1 = lim[3];
+  for (int yy = y0; yy <= y1; yy += 2) {
+    const bool live = yy + half <= y1;
+    const int y = live ? yy + half : y1;
+    const float *row = S + y * Wp * kS16Ch;
+    float T[kPW];
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) T[b] = 0.f;
+    for (int x = x0; x <= x1; ++x) {
+      const float f = row[x * kS16Ch];
+      const float4 w0 = *reinterpret_cast<const float4 *>(Bd + x * 8), w1 = *reinterpret_cast<const float4 *>(Bd + x * 8 + 4);
+      T[0] = fmaf(w0.x, f, T[0]); T[1] = fmaf(w0.y, f, T[1]); T[2] = fmaf(w0.z, f, T[2]); T[3] = fmaf(w0.w, f, T[3]);
+      T[4] = fmaf(w1.x, f, T[4]); T[5] = fmaf(w1.y, f, T[5]); T[6] = fmaf(w1.z, f, T[6]);
+    }
+    const float4 a0 = *reinterpret_cast<const float4 *>(Ad + y * 8), a1 = *reinterpret_cast<const float4 *>(Ad + y * 8 + 4);
+    const float z = live ? 1.0f : 0.0f;
+    const float av[kPH] = {a0.x * z, a0.y * z, a0.z * z, a0.w * z, a1.x * z, a1.y * z, a1.z * z};
+#pragma unroll
+    for (int a = 0; a < kPH; ++a)
+#pragma unroll
+      for (int b = 0; b < kPW; ++b) acc[a][b] = fmaf(av[a], T[b], acc[a][b]);   // rare path: all 49, branch-free
+  }
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab16_kernel(const float *__restrict__ feat /* NHWC */,
+                                                                              const float *__restrict__ rois,
+                                                                              const float *__restrict__ recs, int N, int C, int H,
+                                                                              int W, int R, float scale, int sampling_ratio,
+                                                                              int aligned, float *__restrict__ output) {
+  extern __shared__ __align__(128) float sep_smem[];
+  const int rec = sep_rec_floats(H);
+  const int HW = H * W, Wp = s16_row_px(W);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = lane >> 4, ch = lane & 15;
+  float *slab = sep_smem;
+  float *mine = slab + s16_slab_floats(H, W) + (size_t)warp * s16_warp_floats(H);
+  float *stage = mine, *recbuf = mine + kS16Stage;
+  int *ctrl = reinterpret_cast<int *>(slab + s16_slab_floats(H, W) + (size_t)kWarps * s16_warp_floats(H));
+  int *s_ticket = ctrl, *s_invalid = ctrl + 1, *s_span = ctrl + 2;
+  unsigned *s_present = reinterpret_cast<unsigned *>(ctrl + 8);
+
+  unsigned long long l2_stream;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_stream));
+  const int nslab = (C + kS16Ch - 1) / kS16Ch;
+  const long long total = (long long)nslab * R;
+  long long lo = total * blockIdx.x / gridDim.x;
+  const long long hi = total * (blockIdx.x + 1) / gridDim.x;
+  const int rec4 = rec / 4;                     // float4 words of a record; <= 4 per lane (H <= 56)
+  pdl_wait();
+
+  auto ticket = [&]() -> int {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(s_ticket, 1);
+    return __shfl_sync(0xFFFFFFFFu, t, 0);
+  };
+
+  while (lo < hi) {
+    const int sl = (int)(lo / R), r_lo = (int)(lo - (long long)sl * R);
+    const int r_hi = (int)min((long long)R, r_lo + (hi - lo));
+    lo += r_hi - r_lo;
+    const int cbase = sl * kS16Ch, nch = min(kS16Ch, C - cbase);
+    if (tid < kSlabMaxImages / 32) s_present[tid] = 0u;
+    if (tid == 0) *s_invalid = 0;
+    __syncthreads();
+    for (int r = r_lo + tid; r < r_hi; r += kWarps * 32) {
+      const int img = reinterpret_cast<const int *>(recs + (size_t)r * rec)[26];
+      if (img >= 0) atomicOr(&s_present[img >> 5], 1u << (img & 31)); else *s_invalid = 1;
+    }
+    __syncthreads();
+    for (int n = -1; n < N; ++n) {
+      if (n < 0 ? (*s_invalid == 0) : !((s_present[n >> 5] >> (n & 31)) & 1u)) continue;   // CTA-uniform
+      if (n >= 0) {
+        const float *src = feat + (size_t)n * HW * C + cbase;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(slab);
+        const int q4 = nch >> 2;
+        for (int idx = tid; idx < HW * 4; idx += kWarps * 32) {
+          const int px = idx >> 2, q = idx & 3;
+          const int y = px / W, x = px - y * W;
+          if (q < q4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)((y * Wp + x) * 4 + q)), "l"(src + (size_t)px * C + q * 4) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      if (tid == 0) { s_span[0] = r_hi; s_span[1] = r_lo - 1; }
+      __syncthreads();
+      {
+        int first = r_hi, last = r_lo - 1;
+        for (int r = r_lo + tid; r < r_hi; r += kWarps * 32) {
+          const int img = reinterpret_cast<const int *>(recs + (size_t)r * rec)[26];
+          if (img == n || (n < 0 && img < 0)) { first = min(first, r); last = max(last, r); }
+        }
+        first = __reduce_min_sync(0xFFFFFFFFu, first); last = __reduce_max_sync(0xFFFFFFFFu, last);
+        if (lane == 0 && last >= first) { atomicMin(&s_span[0], first); atomicMax(&s_span[1], last); }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      const int t_end = s_span[1] + 1;
+      if (tid == 0) *s_ticket = s_span[0];
+      __syncthreads();
+      const float *S = slab + ch;
+      float4 pre[4];
+      auto load_rec = [&](int r) {   // next record -> registers (lands while the current ROI is accumulated)
+        const float4 *src = reinterpret_cast<const float4 *>(recs + (size_t)r * rec);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (lane + 32 * k < rec4) pre[k] = __ldg(src + lane + 32 * k);
+      };
+      auto put_rec = [&]() {
+        float4 *dst = reinterpret_cast<float4 *>(recbuf);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (lane + 32 * k < rec4) dst[lane + 32 * k] = pre[k];
+        __syncwarp();
+      };
+      int t = ticket();
+      if (t < t_end) { load_rec(t); put_rec(); }
+      while (t < t_end) {
+        const int tn = ticket();
+        if (tn < t_end) load_rec(tn);
+        const float *rb = recbuf;
+        const int *lim = reinterpret_cast<const int *>(rb);
+        if (lim[26] == n || (n < 0 && lim[26] < 0)) {
+          float acc[kPH][kPW];
+#pragma unroll
+          for (int a = 0; a < kPH; ++a)
+#pragma unroll
+            for (int b = 0; b < kPW; ++b) acc[a][b] = 0.f;
+          const bool empty = n < 0 || lim[1] < lim[0] || lim[3] < lim[2];
+          if (!empty) {
+            const int nx = lim[25];
+            if (nx <= kNXMax) s16_rows_compact(S, half, Wp, lim, rb + 32, rb + kRecHead, nx, acc);
+            else {
+              slab_stage_wait_free();
+              const RoiGeom g = roi_geometry(rois + 5 * (size_t)t, scale, aligned, kPH, kPW, sampling_ratio);
+              for (int i = lane; i < W * 8; i += 32) stage[i] = 0.f;
+              __syncwarp();
+              if (lane < kPW) {
+                const float inv = g.gw > 0 ? __fdiv_rn(1.0f, (float)g.gw) : 0.f;
+                for (int ix = 0; ix < g.gw; ++ix) {
+                  int xl, xh; float l, h;
+                  if (!bilinear_1d(sample_coord(g.sw, lane, g.bw, ix, g.gw), W, xl, xh, l, h)) continue;
+                  stage[xl * 8 + lane] += h * inv; stage[xh * 8 + lane] += l * inv;
+                }
+              }
+              __syncwarp();
+              s16_rows_dense(S, half, Wp, lim, stage, rb + kRecHead, acc);
+              __syncwarp();
+            }
+            // the two halves hold the partial sums of the even / odd rows
+#pragma unroll
+            for (int a = 0; a < kPH; ++a)
+#pragma unroll
+              for (int b = 0; b < kPW; ++b) acc[a][b] += __shfl_xor_sync(0xFFFFFFFFu, acc[a][b], 16);
+          }
+          slab_stage_wait_free();
+          if (ch < nch) {   // both halves write the same values to the same words (benign)
+#pragma unroll
+            for (int a = 0; a < kPH; ++a)
+#pragma unroll
+              for (int b = 0; b < kPW; ++b) stage[ch * kBins + a * kPW + b] = acc[a][b];
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            float *dst = output + ((size_t)t * C + cbase) * kBins;
+            const unsigned src = (unsigned)__cvta_generic_to_shared(stage);
+            const unsigned bytes = (unsigned)nch * kBins * 4u;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src), "r"(bytes), "l"(l2_stream) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        __syncwarp();                 // everybody is done reading the current record
+        if (tn < t_end) put_rec();
+        t = tn;
+      }
+      __syncthreads();
     }
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1048,43 +1348,58 @@ SFOD_API int sfod_roi_align_fwd(const float *input, int layout, const float *roi
   const bool fast = !exact && sep_supported(C, H, W, PH, PW) && sfod_aligned16(output);
   const size_t fbytes = (size_t)N * C * H * W * sizeof(float);
   if (fast) {
-    const float *feat = input;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    size_t used = 0;
-    if (layout == SFOD_NCHW) {
-      if (!workspace || workspace_bytes < fbytes) return SFOD_ERR_WORKSPACE_TOO_SMALL;
-      int rc = launch_transpose(input, static_cast<float *>(workspace), N, C, H * W, st);
-      if (rc) return rc;
-      feat = static_cast<const float *>(workspace);
-      used = sfod_align_up(fbytes, 256);
-    }
-    if (!sfod_aligned16(feat)) return SFOD_ERR_ALIGNMENT;
     const size_t rec_bytes = (size_t)sep_rec_floats(H) * sizeof(float);
-    if (!workspace || workspace_bytes < used + 256 + (size_t)R * rec_bytes) return SFOD_ERR_WORKSPACE_TOO_SMALL;
-    if (!sfod_aligned16(ws + used)) return SFOD_ERR_ALIGNMENT;
-    unsigned *counter = reinterpret_cast<unsigned *>(ws + used);
-    float *recs = reinterpret_cast<float *>(ws + used + 256);
-    roi_sep_tables_kernel<<<(R + 3) / 4, 128, 4 * rec_bytes, st>>>(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, recs, counter);
-    SFOD_LAUNCH_CHECK();
-    // slab-resident kernel when one image x 32 channels of the map fits in shared memory next to the warps' buffers
+    const size_t feat_ws = layout == SFOD_NCHW ? sfod_align_up(fbytes, 256) : 0;   // transposed copy (only some paths use it)
+    if (!workspace || workspace_bytes < feat_ws + 256 + (size_t)R * rec_bytes) return SFOD_ERR_WORKSPACE_TOO_SMALL;
+    if (!sfod_aligned16(ws + feat_ws) || !sfod_aligned16(input)) return SFOD_ERR_ALIGNMENT;
+    unsigned *counter = reinterpret_cast<unsigned *>(ws + feat_ws);
+    float *recs = reinterpret_cast<float *>(ws + feat_ws + 256);
     int sms = 0, cur_dev = 0, max_optin = 0;
     SFOD_CUDA_TRY(cudaGetDevice(&cur_dev));
     SFOD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev));
     SFOD_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cur_dev));
-    if (N <= kSlabMaxImages && (size_t)W * 8 <= (size_t)kSlabStage) {
-      const size_t s16 = slab_smem_bytes(H, W, 16), s8 = slab_smem_bytes(H, W, 8);
-      if (s16 <= (size_t)max_optin) {
-        SFOD_CUDA_TRY(cudaFuncSetAttribute(roi_align_fwd_slab_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s16));
-        roi_align_fwd_slab_kernel<16><<<sms, 16 * 32, s16, st>>>(feat, rois, recs, N, C, H, W, R, spatial_scale, sampling_ratio, aligned, output);
-        SFOD_LAUNCH_CHECK();
-        return SFOD_OK;
-      }
-      if (s8 <= (size_t)max_optin) {
-        SFOD_CUDA_TRY(cudaFuncSetAttribute(roi_align_fwd_slab_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8));
-        roi_align_fwd_slab_kernel<8><<<sms, 8 * 32, s8, st>>>(feat, rois, recs, N, C, H, W, R, spatial_scale, sampling_ratio, aligned, output);
-        SFOD_LAUNCH_CHECK();
-        return SFOD_OK;
-      }
+    // Which forward?  (1) 32-channel slab resident in shared memory, read straight from the caller's layout;
+    // (2) 16-channel slab with two half-warps per ROI for larger maps; (3) per-ROI loads from L2.
+    const int ps = layout == SFOD_NCHW ? kPSNchw : kPSNhwc;
+    const bool slab_ok = N <= kSlabMaxImages && (size_t)W * 8 <= (size_t)kSlabStage;
+    const int slab_warps = !slab_ok ? 0 : slab_smem_bytes(H, W, 16, ps) <= (size_t)max_optin ? 16 : slab_smem_bytes(H, W, 8, ps) <= (size_t)max_optin ? 8 : 0;
+    int s16_warps = 0;
+    if (!slab_warps && N <= kSlabMaxImages && (size_t)W * 8 <= (size_t)kS16Stage && sep_rec_floats(H) <= 512 && (C % 16) == 0)
+      s16_warps = s16_smem_bytes(H, W, 12) <= (size_t)max_optin ? 12
+                  : s16_smem_bytes(H, W, 10) <= (size_t)max_optin ? 10 : s16_smem_bytes(H, W, 8) <= (size_t)max_optin ? 8 : 0;
+    const float *feat = input;   // what the main kernel reads
+    if (!slab_warps && layout == SFOD_NCHW) {   // paths (2) and (3) read channels-last
+      int rc = launch_transpose(input, static_cast<float *>(workspace), N, C, H * W, st);
+      if (rc) return rc;
+      feat = static_cast<const float *>(workspace);
+    }
+    roi_sep_tables_kernel<<<(R + 3) / 4, 128, 4 * rec_bytes, st>>>(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, recs, counter);
+    SFOD_LAUNCH_CHECK();
+    if (slab_warps || s16_warps) {
+      // launched with programmatic stream serialization: its prologue overlaps the table kernel (griddepcontrol.wait inside)
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.gridDim = dim3(sms); cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+#define SFOD_SLAB_LAUNCH(KERN, WARPS, SMEM)                                                                                  \
+      do {                                                                                                                   \
+        SFOD_CUDA_TRY(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));                 \
+        cfg.blockDim = dim3((WARPS) * 32); cfg.dynamicSmemBytes = (SMEM);                                                    \
+        SFOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, KERN, feat, rois, (const float *)recs, N, C, H, W, R, spatial_scale,          \
+                                         sampling_ratio, aligned, output));                                                  \
+      } while (0)
+      if (slab_warps == 16 && ps == kPSNchw) SFOD_SLAB_LAUNCH((roi_align_fwd_slab_kernel<16, kPSNchw>), 16, slab_smem_bytes(H, W, 16, ps));
+      else if (slab_warps == 16) SFOD_SLAB_LAUNCH((roi_align_fwd_slab_kernel<16, kPSNhwc>), 16, slab_smem_bytes(H, W, 16, ps));
+      else if (slab_warps == 8 && ps == kPSNchw) SFOD_SLAB_LAUNCH((roi_align_fwd_slab_kernel<8, kPSNchw>), 8, slab_smem_bytes(H, W, 8, ps));
+      else if (slab_warps == 8) SFOD_SLAB_LAUNCH((roi_align_fwd_slab_kernel<8, kPSNhwc>), 8, slab_smem_bytes(H, W, 8, ps));
+      else if (s16_warps == 12) SFOD_SLAB_LAUNCH((roi_align_fwd_slab16_kernel<12>), 12, s16_smem_bytes(H, W, 12));
+      else if (s16_warps == 10) SFOD_SLAB_LAUNCH((roi_align_fwd_slab16_kernel<10>), 10, s16_smem_bytes(H, W, 10));
+      else SFOD_SLAB_LAUNCH((roi_align_fwd_slab16_kernel<8>), 8, s16_smem_bytes(H, W, 8));
+#undef SFOD_SLAB_LAUNCH
+      SFOD_LAUNCH_CHECK();
+      return SFOD_OK;
     }
     const size_t smem = sep_fwd_smem_bytes(H, W);
     const int items = R * ((C + kCT - 1) / kCT);

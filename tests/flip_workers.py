@@ -40,7 +40,7 @@ def frcnn_inputs(kind: str, seed: int, R: int = 2000, K: int = 8):
                          torch.maximum(props[:, 0], props[:, 2]) + 1.0, torch.maximum(props[:, 1], props[:, 3]) + 1.0], dim=1).contiguous()
     cls_of = torch.randint(0, K, (clusters,), generator=g)
     cls = torch.randn(R, K + 1, generator=g)
-    cls[torch.arange(R), cls_of[which]] += 1.0 + torch.rand(R, generator=g) * 3.5
+    cls[torch.arange(R), cls_of[which]] += torch.rand(R, generator=g) * 3.2
     dl = torch.randn(R, 4 * K, generator=g) * 0.3
     return cls.contiguous(), dl.contiguous(), props
 

@@ -200,21 +200,27 @@ def test_roi_align_kat_and_api(ops, cuda_device):
         ops.roi_align(xs.to(d), torch.zeros(3, 4, device=d), 7)
 
 
-def test_roi_align_forward_any_image_order_and_invalid_index(ops, cuda_device):
-    """The slab-resident forward serves the ROIs of one image at a time from shared memory: ROIs must be accepted in any
-    image order (detectron2 passes them grouped by image, torchvision's API does not require it), images without ROIs
-    are skipped, and an out-of-range batch index yields zeros (library contract; torchvision reads out of bounds)."""
-    cfg = synth.V
-    N, R = 5, 700
+@pytest.mark.parametrize("cfg", [synth.V, synth.R101, dict(name="mid-even-W", C=48, H=40, W=50, stride=16)], ids=["V", "R", "mid"])
+def test_roi_align_forward_any_image_order_and_invalid_index(ops, cuda_device, cfg):
+    """The slab-resident forwards (32-channel slab: V; 16-channel slab with two half-warps per ROI: R101-C4 and the 40 x 50 map,
+    whose even row length is padded to an odd stride) serve the ROIs of one image at a time from shared memory: ROIs must be
+    accepted in any image order (detectron2 passes them grouped by image, torchvision's API does not require it), images
+    without ROIs are skipped, and an out-of-range batch index yields zeros (library contract; torchvision reads out of bounds)."""
+    N, R = (5, 700) if cfg["C"] <= 512 else (3, 260)
     x = synth.features(cfg, N, 51)
     rois = synth.random_rois(N, R, 52)
     rois[:, 0] = torch.randint(0, N, (R,), generator=torch.Generator().manual_seed(53)).float()
     rois[rois[:, 0] == 3, 0] = 1.0                      # image 3 has no ROI at all
-    ref = torchvision.ops.roi_align(x, rois, (7, 7), 1 / 32, 0, True)
-    got = ops.roi_align(x.to(cuda_device), rois.to(cuda_device), (7, 7), 1 / 32, 0, True).cpu()
+    sc = 1.0 / cfg["stride"]
+    if cfg["stride"] == 16 and cfg["W"] == 50:
+        rois[:, 1::2] *= 50 * 16 / 1200.0; rois[:, 2::2] *= 40 * 16 / 600.0     # keep the boxes on the smaller map
+    ref = torchvision.ops.roi_align(x, rois, (7, 7), sc, 0, True)
+    got = ops.roi_align(x.to(cuda_device), rois.to(cuda_device), (7, 7), sc, 0, True).cpu()
     _close(got, ref)
+    got_cl = ops.roi_align(x.to(cuda_device).contiguous(memory_format=torch.channels_last), rois.to(cuda_device), (7, 7), sc, 0, True).cpu()
+    assert torch.equal(got_cl, got)
     bad = rois.clone(); bad[::7, 0] = float(N + 2); bad[3::11, 0] = -1.0
-    got = ops.roi_align(x.to(cuda_device), bad.to(cuda_device), (7, 7), 1 / 32, 0, True).cpu()
+    got = ops.roi_align(x.to(cuda_device), bad.to(cuda_device), (7, 7), sc, 0, True).cpu()
     invalid = (bad[:, 0] < 0) | (bad[:, 0] >= N)
     assert torch.count_nonzero(got[invalid]) == 0
     _close(got[~invalid], ref[~invalid])

@@ -206,7 +206,7 @@ if __name__ == "__main__":
     sel = set(a.only.split(",")) if a.only else None
     print(json.dumps(dict(gpu=torch.cuda.get_device_name(0), peak_gbs=peak_gbs())))
     if not sel or "roi" in sel:
-        bench_roi(synth.V, 1, 2000); bench_roi(synth.V, 8, 2000); bench_roi(synth.R101, 1, 2000, tv=True)
+        bench_roi(synth.V, 1, 2000); bench_roi(synth.V, 8, 2000); bench_roi(synth.R101, 1, 2000, tv=True); bench_roi(synth.R101, 8, 2000, tv=False)
     if not sel or "nms" in sel:
         bench_nms()
     if not sel or "det" in sel:
