@@ -11,7 +11,10 @@
  * Conventions (all entry points):
  *   - plain pointers and sizes only; no torch / C++ types; `int` status return
  *     (0 = SFOD_OK, otherwise an sfod_status value; >= 1000 encodes 1000 + cudaError_t);
- *   - no exceptions, no logging, no global mutable state, re-entrant;
+ *   - no exceptions, no logging, re-entrant; the only process-wide state is (i) a monotonically increasing diagnostic
+ *     launch counter (sfod_debug_launch_count) and (ii) two write-once capability caches (the largest thread-block cluster
+ *     the device accepts for the NMS kernels, csrc/nms.cuh) whose initialisation is idempotent -- nothing a kernel result
+ *     depends on is kept between calls;
  *   - every buffer is owned by the caller (inputs, outputs, workspace); workspace sizes
  *     come from the matching *_workspace_bytes() query; all device pointers must be
  *     valid on the current CUDA device; fp32 buffers must be 16-byte aligned unless noted;
@@ -284,6 +287,15 @@ int sfod_bn_finalize_apply_v2(const float *x, const float *pre_bias, const float
                               const float *weight, const float *bias, float *running_mean, float *running_var,
                               int64_t *num_batches_tracked, double momentum, double eps, int fuse_relu, int fuse_maxpool2,
                               float *save_mean, float *save_invstd, sfod_stream_t stream);
+/* FrozenBatchNorm2d / eval-mode BatchNorm with the same fusions: y = [relu](x * scale + shift [+ residual]),
+ * scale = weight / sqrt(running_var + eps), shift = bias - running_mean * scale.  detectron2 freezes the stem and res2 of
+ * the R101-C4 backbone (MODEL.BACKBONE.FREEZE_AT = 2 is not overridden by configs/r101_c4_cs_foggy_adaptive_teacher_source_free.yaml),
+ * so 11 of its 94 norm layers run in this mode even while the teacher is in train().  `scratch` holds
+ * sfod_bn_frozen_scratch_bytes(C) bytes. */
+size_t sfod_bn_frozen_scratch_bytes(int C);
+int sfod_bn_frozen_apply(const float *x, const float *residual, float *y, int layout, int N, int C, int H, int W,
+                         const float *weight, const float *bias, const float *running_mean, const float *running_var,
+                         double eps, int fuse_relu, void *scratch, sfod_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,39 @@ def backbone_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: boo
 
 
 @torch.no_grad()
+def resnet_c4_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = True, momentum: float = 0.1, eps: float = 1e-5,
+                      blocks=(3, 4, 23)):
+    """detectron2 ResNet-C4 (BasicStem + res2..res4 BottleneckBlocks, STRIDE_IN_1X1) from a state_dict with detectron2's keys
+    (``backbone.stem.conv1.*``, ``backbone.res{s}.{i}.{shortcut,conv1,conv2,conv3}.*``) -- the backbone of reference
+    configs/r101_c4_cs_foggy_adaptive_teacher_source_free.yaml.  A norm layer WITHOUT ``num_batches_tracked`` in the state_dict
+    is a FrozenBatchNorm2d (detectron2 ``FREEZE_AT``) and always uses its stored statistics; the others are nn.BatchNorm2d in
+    train() mode when ``training`` (batch statistics, running-stat update)."""
+    def norm(t, pre):
+        frozen = (pre + ".num_batches_tracked") not in sd
+        if training and not frozen:
+            sd[pre + ".num_batches_tracked"] += 1
+        return F.batch_norm(t, sd[pre + ".running_mean"], sd[pre + ".running_var"], sd[pre + ".weight"], sd[pre + ".bias"],
+                            training and not frozen, momentum, eps)
+
+    def conv(t, pre, stride=1, padding=0):
+        return norm(F.conv2d(t, sd[pre + ".weight"], None, stride, padding), pre + ".norm")
+
+    x = F.relu_(conv(x, "backbone.stem.conv1", 2, 3))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    for s, n in zip((2, 3, 4), blocks):
+        for i in range(n):
+            pre = f"backbone.res{s}.{i}"
+            stride = 2 if (i == 0 and s > 2) else 1
+            out = F.relu_(conv(x, pre + ".conv1", stride))          # STRIDE_IN_1X1: the stride sits on the first 1x1
+            out = F.relu_(conv(out, pre + ".conv2", 1, 1))
+            out = conv(out, pre + ".conv3")
+            shortcut = conv(x, pre + ".shortcut", stride) if (pre + ".shortcut.weight") in sd else x
+            out += shortcut
+            x = F.relu_(out)
+    return x  # res4
+
+
+@torch.no_grad()
 def teacher_pseudo_label(sd: Dict[str, torch.Tensor], images_u8: torch.Tensor, *, training: bool = True, num_classes: int = 8,
                          bbox_threshold: float = 0.8, pixel_mean=(103.530, 116.280, 123.675), pixel_std=(1.0, 1.0, 1.0),
                          sizes=(32, 64, 128, 256, 512), ratios=(0.5, 1.0, 2.0), stride: int = 32,
@@ -65,7 +98,10 @@ def teacher_pseudo_label(sd: Dict[str, torch.Tensor], images_u8: torch.Tensor, *
     N, _, H, W = images_u8.shape
     image_sizes = [(H, W)] * N
     x = (images_u8.float() - torch.tensor(pixel_mean).view(1, 3, 1, 1)) / torch.tensor(pixel_std).view(1, 3, 1, 1)
-    feat = backbone_forward(sd, x, training)
+    if "backbone.stem.conv1.weight" in sd:      # ResNet-C4 (R101-C4 configs): stride 16, anchors 64..512
+        feat = resnet_c4_forward(sd, x, training)
+    else:
+        feat = backbone_forward(sd, x, training)
     # RPN head + flatten (reference rpn.py:27-41)
     t = F.relu(F.conv2d(feat, sd["proposal_generator.rpn_head.conv.weight"], sd["proposal_generator.rpn_head.conv.bias"], padding=1))
     obj = F.conv2d(t, sd["proposal_generator.rpn_head.objectness_logits.weight"], sd["proposal_generator.rpn_head.objectness_logits.bias"])

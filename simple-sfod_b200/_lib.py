@@ -1,7 +1,9 @@
 """ctypes binding of libsfod_b200.so (the C ABI declared in include/sfod_b200.h).
 
-There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
-The product path never imports anything from ``oracle/``.
+There is NO fallback for the operators of this library: if the shared library is missing or a call fails, an exception is
+raised, and every operator of ``ops`` refuses CPU tensors.  (The one place where another implementation runs is an operator
+boundary, not a fallback: ``modeling.SfodBatchNorm2d`` hands the modes the kernels do not serve -- autograd, eval, CPU -- to
+PyTorch's own ``nn.BatchNorm2d``, as documented there.)  The product path never imports anything from ``oracle/``.
 """
 from __future__ import annotations
 
@@ -75,6 +77,9 @@ SIGNATURES = {
     "sfod_bn_partial_stats": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int64, c_ptr, c_ptr]),
     "sfod_bn_finalize_apply": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.c_double, c_ptr, c_ptr,
                                          c_ptr, c_ptr, c_ptr, C.c_double, C.c_double, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
+    "sfod_bn_frozen_scratch_bytes": (C.c_size_t, [C.c_int]),
+    "sfod_bn_frozen_apply": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                       C.c_double, C.c_int, c_ptr, c_ptr]),
     "sfod_bn_finalize_apply_v2": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.c_double, C.c_int,
                                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_double, C.c_double, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
 }

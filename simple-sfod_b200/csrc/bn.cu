@@ -394,26 +394,12 @@ SFOD_API int sfod_bn_partial_stats(const float *x, const float *pre_bias, int la
   return SFOD_OK;
 }
 
-// stats_dev layout: [0, 2C) (sum x, sum x^2); [2C] element count of this rank (written by phase 1; with [0, 2C) it forms the
-// 2C+1 all-reduce payload); [2C + 2, ...) float scale / shift scratch of phase 2; [4C, ...) replica totals of the NHWC pass.
-SFOD_API int sfod_bn_finalize_apply_v2(const float *x, const float *pre_bias, const float *residual, float *y, int layout, int N, int C,
-                                       int H, int W, const double *stats_dev, double total_count, int count_on_device,
-                                       const float *weight, const float *bias, float *running_mean, float *running_var,
-                                       int64_t *num_batches_tracked, double momentum, double eps, int fuse_relu, int fuse_maxpool2,
-                                       float *save_mean, float *save_invstd, sfod_stream_t stream) {
-  if (!stats_dev || N <= 0 || C <= 0 || H <= 0 || W <= 0 || (!count_on_device && total_count <= 0)) return SFOD_ERR_INVALID_ARG;
-  if (layout != SFOD_NCHW && layout != SFOD_NHWC) return SFOD_ERR_INVALID_ARG;
-  if (residual && fuse_maxpool2) return SFOD_ERR_INVALID_ARG;
-  if (residual && x && ((reinterpret_cast<uintptr_t>(residual) ^ reinterpret_cast<uintptr_t>(x)) & 15u)) return SFOD_ERR_ALIGNMENT;
-  cudaStream_t st = sfod_cu(stream);
+namespace {
+// normalise (+residual) (+ReLU) (+2x2 max-pool) with given per-channel scale / shift: the launches shared by the train-mode and
+// the frozen-statistics entry points
+int launch_bn_apply(const float *x, const float *pre_bias, const float *residual, float *y, int layout, int N, int C, int H, int W,
+                    const float *scale, const float *shift, int fuse_relu, int fuse_maxpool2, cudaStream_t st) {
   const long long HW = (long long)H * W;
-  float *scale = reinterpret_cast<float *>(const_cast<double *>(stats_dev) + 2 * (size_t)C + 2);
-  float *shift = scale + sfod_align_up((size_t)C, 4);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_dev, C, total_count, count_on_device, weight, bias, running_mean, running_var,
-                                                      reinterpret_cast<long long *>(num_batches_tracked), momentum, eps,
-                                                      save_mean, save_invstd, scale, shift);
-  SFOD_LAUNCH_CHECK();
-  if (!x || !y) return SFOD_OK;  // statistics-only mode (AdaBN does not need the normalised output of the last layer)
   if (fuse_maxpool2) {
     const int H2 = H / 2, W2 = W / 2;
     if (H2 == 0 || W2 == 0) return SFOD_OK;  // empty pooled map
@@ -486,6 +472,45 @@ SFOD_API int sfod_bn_finalize_apply_v2(const float *x, const float *pre_bias, co
   SFOD_LAUNCH_CHECK();
   return SFOD_OK;
 }
+}  // namespace
+
+// stats_dev layout: [0, 2C) (sum x, sum x^2); [2C] element count of this rank (written by phase 1; with [0, 2C) it forms the
+// 2C+1 all-reduce payload); [2C + 2, ...) float scale / shift scratch of phase 2; [4C, ...) replica totals of the NHWC pass.
+SFOD_API int sfod_bn_finalize_apply_v2(const float *x, const float *pre_bias, const float *residual, float *y, int layout, int N, int C,
+                                       int H, int W, const double *stats_dev, double total_count, int count_on_device,
+                                       const float *weight, const float *bias, float *running_mean, float *running_var,
+                                       int64_t *num_batches_tracked, double momentum, double eps, int fuse_relu, int fuse_maxpool2,
+                                       float *save_mean, float *save_invstd, sfod_stream_t stream) {
+  if (!stats_dev || N <= 0 || C <= 0 || H <= 0 || W <= 0 || (!count_on_device && total_count <= 0)) return SFOD_ERR_INVALID_ARG;
+  if (layout != SFOD_NCHW && layout != SFOD_NHWC) return SFOD_ERR_INVALID_ARG;
+  if (residual && fuse_maxpool2) return SFOD_ERR_INVALID_ARG;
+  if (residual && x && ((reinterpret_cast<uintptr_t>(residual) ^ reinterpret_cast<uintptr_t>(x)) & 15u)) return SFOD_ERR_ALIGNMENT;
+  cudaStream_t st = sfod_cu(stream);
+  const long long HW = (long long)H * W;
+  float *scale = reinterpret_cast<float *>(const_cast<double *>(stats_dev) + 2 * (size_t)C + 2);
+  float *shift = scale + sfod_align_up((size_t)C, 4);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_dev, C, total_count, count_on_device, weight, bias, running_mean, running_var,
+                                                      reinterpret_cast<long long *>(num_batches_tracked), momentum, eps,
+                                                      save_mean, save_invstd, scale, shift);
+  SFOD_LAUNCH_CHECK();
+  if (!x || !y) return SFOD_OK;  // statistics-only mode (AdaBN does not need the normalised output of the last layer)
+  return launch_bn_apply(x, pre_bias, residual, y, layout, N, C, H, W, scale, shift, fuse_relu, fuse_maxpool2, st);
+}
+
+namespace {
+// FrozenBatchNorm2d / eval-mode BatchNorm coefficients: y = x * scale + shift with scale = w / sqrt(running_var + eps),
+// shift = b - running_mean * scale (detectron2 layers/batch_norm.py FrozenBatchNorm2d.forward, fp32 like the reference).
+__global__ void bn_frozen_coeffs_kernel(int C, const float *__restrict__ weight, const float *__restrict__ bias,
+                                        const float *__restrict__ running_mean, const float *__restrict__ running_var, float eps,
+                                        float *__restrict__ scale, float *__restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float w = weight ? weight[c] : 1.0f, b = bias ? bias[c] : 0.0f;
+  const float sc = __fmul_rn(w, __frsqrt_rn(__fadd_rn(running_var[c], eps)));
+  scale[c] = sc;
+  shift[c] = __fsub_rn(b, __fmul_rn(running_mean[c], sc));
+}
+}  // namespace
 
 SFOD_API int sfod_bn_finalize_apply(const float *x, const float *pre_bias, float *y, int layout, int N, int C, int H, int W,
                                     const double *stats_dev, double total_count, const float *weight, const float *bias,
@@ -494,4 +519,20 @@ SFOD_API int sfod_bn_finalize_apply(const float *x, const float *pre_bias, float
                                     sfod_stream_t stream) {
   return sfod_bn_finalize_apply_v2(x, pre_bias, nullptr, y, layout, N, C, H, W, stats_dev, total_count, 0, weight, bias, running_mean,
                                    running_var, num_batches_tracked, momentum, eps, fuse_relu, fuse_maxpool2, save_mean, save_invstd, stream);
+}
+
+SFOD_API size_t sfod_bn_frozen_scratch_bytes(int C) { return C > 0 ? sfod_align_up(2 * sfod_align_up((size_t)C, 4) * sizeof(float), 256) : 256; }
+
+SFOD_API int sfod_bn_frozen_apply(const float *x, const float *residual, float *y, int layout, int N, int C, int H, int W,
+                                  const float *weight, const float *bias, const float *running_mean, const float *running_var,
+                                  double eps, int fuse_relu, void *scratch, sfod_stream_t stream) {
+  if (!x || !y || !running_mean || !running_var || !scratch || N <= 0 || C <= 0 || H <= 0 || W <= 0) return SFOD_ERR_INVALID_ARG;
+  if (layout != SFOD_NCHW && layout != SFOD_NHWC) return SFOD_ERR_INVALID_ARG;
+  if (residual && ((reinterpret_cast<uintptr_t>(residual) ^ reinterpret_cast<uintptr_t>(x)) & 15u)) return SFOD_ERR_ALIGNMENT;
+  cudaStream_t st = sfod_cu(stream);
+  float *scale = static_cast<float *>(scratch);
+  float *shift = scale + sfod_align_up((size_t)C, 4);
+  bn_frozen_coeffs_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, weight, bias, running_mean, running_var, (float)eps, scale, shift);
+  SFOD_LAUNCH_CHECK();
+  return launch_bn_apply(x, nullptr, residual, y, layout, N, C, H, W, scale, shift, fuse_relu, 0, st);
 }

@@ -896,282 +896,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab_kernel(cons
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-// ---- 16-channel slab, two half-warps per ROI (maps whose 32-channel slab does not fit: R101-C4 res4, 38 x 75).
-// One image x 16 channels (H*W*64 B; 182 KB for 38 x 75) stays resident.  A warp still owns one ROI at a time, but its two
-// half-warps take ALTERNATE ROWS of the ROI (lane & 15 = channel): the row stride of the slab is kept odd in pixels, so rows y
-// and y + 1 start in opposite 64-byte halves of the 128-byte bank window and the two 64-byte reads of a warp instruction never
-// collide.  Both halves run the same compact-column code on the same record; the bins fed by the two rows are covered by one
-// warp-uniform switch on the union of their runs (the other half's weights are exact zeros), and the partial sums are
-// combined with 49 shuffles before the (16 x 49) tile leaves as one 3 136 B bulk store.  The next record is prefetched into
-// registers (the slab leaves room for one record per warp).
-constexpr int kS16Ch = 16;
-constexpr int kS16Stage = kS16Ch * kBins;   // 784 floats = 3 136 B per warp
-__host__ __device__ inline int s16_row_px(int W) { return W | 1; }   // odd row stride in pixels
-__host__ __device__ inline size_t s16_slab_floats(int H, int W) { return ((size_t)H * s16_row_px(W) * kS16Ch + 31) / 32 * 32; }
-__host__ __device__ inline size_t s16_warp_floats(int H) { return (size_t)kS16Stage + (size_t)sep_rec_floats(H); }
-__host__ __device__ inline size_t s16_smem_bytes(int H, int W, int warps) {
-  return (s16_slab_floats(H, W) + (size_t)warps * s16_warp_floats(H)) * 4 + 40 * 4;
-}
-
-// acc[a][:] += av[a] * T[:] for a in [first, last]: a loop over the bins with one 7-way switch per bin.  (The fully
-// unrolled switch-on-first-bin of the 32-channel kernel costs ~300 instructions per instance; here one instance serves all
-// window widths, which keeps the row loop inside the instruction cache -- "no instruction" was the top stall before.)
-__device__ __forceinline__ void s16_accumulate(float (&acc)[kPH][kPW], const float (&av)[kPH], const float (&T)[kPW], int first, int last) {
-  for (int a = first; a <= last; ++a) {
-    switch (a) {
-#define SFOD_S16_CASE(A)                                                              \
-      case A:                                                                         \
-        _Pragma("unroll") for (int b = 0; b < kPW; ++b) acc[A][b] = fmaf(av[A], T[b], acc[A][b]); \
-        break;
-      SFOD_S16_CASE(0) SFOD_S16_CASE(1) SFOD_S16_CASE(2) SFOD_S16_CASE(3) SFOD_S16_CASE(4) SFOD_S16_CASE(5)
-      default:
-#pragma unroll
-        for (int b = 0; b < kPW; ++b) acc[6][b] = fmaf(av[6], T[b], acc[6][b]);
-        break;
-#undef SFOD_S16_CASE
-    }
-  }
-}
-
-template <int NX>
-__device__ __forceinline__ void s16_row_T(float (&T)[kPW], const float (&bw)[kPW][kNXMax], const unsigned (&pb)[kPW], unsigned ro) {
-#pragma unroll
-  for (int b = 0; b < kPW; ++b) {
-    const unsigned p = pb[b] + ro;
-    T[b] = bw[b][0] * slab_lds<0>(p);
-    if (NX > 1) T[b] = fmaf(bw[b][1], slab_lds<kS16Ch * 4>(p), T[b]);
-    if (NX > 2) T[b] = fmaf(bw[b][2], slab_lds<2 * kS16Ch * 4>(p), T[b]);
-    if (NX > 3) T[b] = fmaf(bw[b][3], slab_lds<3 * kS16Ch * 4>(p), T[b]);
-    if (NX > 4) T[b] = fmaf(bw[b][4], slab_lds<4 * kS16Ch * 4>(p), T[b]);
-    if (NX > 5) T[b] = fmaf(bw[b][5], slab_lds<5 * kS16Ch * 4>(p), T[b]);
-    if (NX > 6) T[b] = fmaf(bw[b][6], slab_lds<6 * kS16Ch * 4>(p), T[b]);
-    if (NX > 7) T[b] = fmaf(bw[b][7], slab_lds<7 * kS16Ch * 4>(p), T[b]);
-  }
-}
-
-// rows of one ROI, compact column windows of width nx in {2, 3, 4, 6, 8} (warp-uniform, from the record)
-__device__ __forceinline__ void s16_rows_compact(const float *__restrict__ S, int half, int Wp, const int *__restrict__ lim,
-                                                 const float *__restrict__ Bc, const float *__restrict__ Ad, int nx,
-                                                 float (&acc)[kPH][kPW]) {
-  float bw[kPW][kNXMax];
-  unsigned pb[kPW];
-  const unsigned sbase = (unsigned)__cvta_generic_to_shared(S);
-#pragma unroll
-  for (int b = 0; b < kPW; ++b) {
-    pb[b] = sbase + (unsigned)lim[18 + b] * (kS16Ch * 4);
-    const float4 w0 = *reinterpret_cast<const float4 *>(Bc + b * kNXMax), w1 = *reinterpret_cast<const float4 *>(Bc + b * kNXMax + 4);
-    bw[b][0] = w0.x; bw[b][1] = w0.y; bw[b][2] = w0.z; bw[b][3] = w0.w; bw[b][4] = w1.x; bw[b][5] = w1.y; bw[b][6] = w1.z; bw[b][7] = w1.w;
-  }
-  const int y0 = lim[0], y1 = lim[1];
-  const unsigned rstride = (unsigned)Wp * (kS16Ch * 4);
-  for (int yy = y0; yy <= y1; yy += 2) {
-    const bool live = yy + half <= y1;
-    const int y = live ? yy + half : y1;        // the idle half re-reads a valid row with zero weights
-    const float4 a0 = *reinterpret_cast<const float4 *>(Ad + y * 8), a1 = *reinterpret_cast<const float4 *>(Ad + y * 8 + 4);
-    const int info = live ? __float_as_int(a1.w) : 0;
-    int first = info ? (info & 0xff) : kPH, last = info ? first + (info >> 8) - 1 : -1;
-    first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, 16));
-    last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, 16));
-    if (last < first) continue;                  // warp-uniform: neither row feeds a bin
-    const float z = live ? 1.0f : 0.0f;
-    const float av[kPH] = {a0.x * z, a0.y * z, a0.z * z, a0.w * z, a1.x * z, a1.y * z, a1.z * z};
-    const unsigned ro = (unsigned)y * rstride;
-    float T[kPW];
-    if (nx <= 2) s16_row_T<2>(T, bw, pb, ro);
-    else if (nx == 3) s16_row_T<3>(T, bw, pb, ro);
-    else if (nx == 4) s16_row_T<4>(T, bw, pb, ro);
-    else if (nx == 6) s16_row_T<6>(T, bw, pb, ro);
-    else s16_row_T<8>(T, bw, pb, ro);
-    s16_accumulate(acc, av, T, first, last);
-  }
-}
-
-// wide-bin fallback (window > kNXMax columns): dense column table Bd (W x 8) built by the warp in its stage buffer
-__device__ __forceinline__ void s16_rows_dense(const float *__restrict__ S, int half, int Wp, const int *__restrict__ lim,
-                                               const float *__restrict__ Bd, const float *__restrict__ Ad,
-                                               float (&acc)[kPH][kPW]) {
-  const int y0 = lim[0], y1 = lim[1], x0 = lim[2], x1 = lim[3];
-  for (int yy = y0; yy <= y1; yy += 2) {
-    const bool live = yy + half <= y1;
-    const int y = live ? yy + half : y1;
-    const float *row = S + y * Wp * kS16Ch;
-    float T[kPW];
-#pragma unroll
-    for (int b = 0; b < kPW; ++b) T[b] = 0.f;
-    for (int x = x0; x <= x1; ++x) {
-      const float f = row[x * kS16Ch];
-      const float4 w0 = *reinterpret_cast<const float4 *>(Bd + x * 8), w1 = *reinterpret_cast<const float4 *>(Bd + x * 8 + 4);
-      T[0] = fmaf(w0.x, f, T[0]); T[1] = fmaf(w0.y, f, T[1]); T[2] = fmaf(w0.z, f, T[2]); T[3] = fmaf(w0.w, f, T[3]);
-      T[4] = fmaf(w1.x, f, T[4]); T[5] = fmaf(w1.y, f, T[5]); T[6] = fmaf(w1.z, f, T[6]);
-    }
-    const float4 a0 = *reinterpret_cast<const float4 *>(Ad + y * 8), a1 = *reinterpret_cast<const float4 *>(Ad + y * 8 + 4);
-    const float z = live ? 1.0f : 0.0f;
-    const float av[kPH] = {a0.x * z, a0.y * z, a0.z * z, a0.w * z, a1.x * z, a1.y * z, a1.z * z};
-#pragma unroll
-    for (int a = 0; a < kPH; ++a)
-#pragma unroll
-      for (int b = 0; b < kPW; ++b) acc[a][b] = fmaf(av[a], T[b], acc[a][b]);   // rare path: all 49, branch-free
-  }
-}
-
-template <int kWarps>
-__global__ void __launch_bounds__(kWarps * 32, 1) roi_align_fwd_slab16_kernel(const float *__restrict__ feat /* NHWC */,
-                                                                              const float *__restrict__ rois,
-                                                                              const float *__restrict__ recs, int N, int C, int H,
-                                                                              int W, int R, float scale, int sampling_ratio,
-                                                                              int aligned, float *__restrict__ output) {
-  extern __shared__ __align__(128) float sep_smem[];
-  const int rec = sep_rec_floats(H);
-  const int HW = H * W, Wp = s16_row_px(W);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int half = lane >> 4, ch = lane & 15;
-  float *slab = sep_smem;
-  float *mine = slab + s16_slab_floats(H, W) + (size_t)warp * s16_warp_floats(H);
-  float *stage = mine, *recbuf = mine + kS16Stage;
-  int *ctrl = reinterpret_cast<int *>(slab + s16_slab_floats(H, W) + (size_t)kWarps * s16_warp_floats(H));
-  int *s_ticket = ctrl, *s_invalid = ctrl + 1, *s_span = ctrl + 2;
-  unsigned *s_present = reinterpret_cast<unsigned *>(ctrl + 8);
-
-  unsigned long long l2_stream;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_stream));
-  const int nslab = (C + kS16Ch - 1) / kS16Ch;
-  const long long total = (long long)nslab * R;
-  long long lo = total * blockIdx.x / gridDim.x;
-  const long long hi = total * (blockIdx.x + 1) / gridDim.x;
-  const int rec4 = rec / 4;                     // float4 words of a record; <= 4 per lane (H <= 56)
-  pdl_wait();
-
-  auto ticket = [&]() -> int {
-    int t = 0;
-    if (lane == 0) t = atomicAdd(s_ticket, 1);
-    return __shfl_sync(0xFFFFFFFFu, t, 0);
-  };
-
-  while (lo < hi) {
-    const int sl = (int)(lo / R), r_lo = (int)(lo - (long long)sl * R);
-    const int r_hi = (int)min((long long)R, r_lo + (hi - lo));
-    lo += r_hi - r_lo;
-    const int cbase = sl * kS16Ch, nch = min(kS16Ch, C - cbase);
-    if (tid < kSlabMaxImages / 32) s_present[tid] = 0u;
-    if (tid == 0) *s_invalid = 0;
-    __syncthreads();
-    for (int r = r_lo + tid; r < r_hi; r += kWarps * 32) {
-      const int img = reinterpret_cast<const int *>(recs + (size_t)r * rec)[26];
-      if (img >= 0) atomicOr(&s_present[img >> 5], 1u << (img & 31)); else *s_invalid = 1;
-    }
-    __syncthreads();
-    for (int n = -1; n < N; ++n) {
-      if (n < 0 ? (*s_invalid == 0) : !((s_present[n >> 5] >> (n & 31)) & 1u)) continue;   // CTA-uniform
-      if (n >= 0) {
-        const float *src = feat + (size_t)n * HW * C + cbase;
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(slab);
-        const int q4 = nch >> 2;
-        for (int idx = tid; idx < HW * 4; idx += kWarps * 32) {
-          const int px = idx >> 2, q = idx & 3;
-          const int y = px / W, x = px - y * W;
-          if (q < q4)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)((y * Wp + x) * 4 + q)), "l"(src + (size_t)px * C + q * 4) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-      if (tid == 0) { s_span[0] = r_hi; s_span[1] = r_lo - 1; }
-      __syncthreads();
-      {
-        int first = r_hi, last = r_lo - 1;
-        for (int r = r_lo + tid; r < r_hi; r += kWarps * 32) {
-          const int img = reinterpret_cast<const int *>(recs + (size_t)r * rec)[26];
-          if (img == n || (n < 0 && img < 0)) { first = min(first, r); last = max(last, r); }
-        }
-        first = __reduce_min_sync(0xFFFFFFFFu, first); last = __reduce_max_sync(0xFFFFFFFFu, last);
-        if (lane == 0 && last >= first) { atomicMin(&s_span[0], first); atomicMax(&s_span[1], last); }
-      }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
-      const int t_end = s_span[1] + 1;
-      if (tid == 0) *s_ticket = s_span[0];
-      __syncthreads();
-      const float *S = slab + ch;
-      float4 pre[4];
-      auto load_rec = [&](int r) {   // next record -> registers (lands while the current ROI is accumulated)
-        const float4 *src = reinterpret_cast<const float4 *>(recs + (size_t)r * rec);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (lane + 32 * k < rec4) pre[k] = __ldg(src + lane + 32 * k);
-      };
-      auto put_rec = [&]() {
-        float4 *dst = reinterpret_cast<float4 *>(recbuf);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (lane + 32 * k < rec4) dst[lane + 32 * k] = pre[k];
-        __syncwarp();
-      };
-      int t = ticket();
-      if (t < t_end) { load_rec(t); put_rec(); }
-      while (t < t_end) {
-        const int tn = ticket();
-        if (tn < t_end) load_rec(tn);
-        const float *rb = recbuf;
-        const int *lim = reinterpret_cast<const int *>(rb);
-        if (lim[26] == n || (n < 0 && lim[26] < 0)) {
-          float acc[kPH][kPW];
-#pragma unroll
-          for (int a = 0; a < kPH; ++a)
-#pragma unroll
-            for (int b = 0; b < kPW; ++b) acc[a][b] = 0.f;
-          const bool empty = n < 0 || lim[1] < lim[0] || lim[3] < lim[2];
-          if (!empty) {
-            const int nx = lim[25];
-            if (nx <= kNXMax) s16_rows_compact(S, half, Wp, lim, rb + 32, rb + kRecHead, nx, acc);
-            else {
-              slab_stage_wait_free();
-              const RoiGeom g = roi_geometry(rois + 5 * (size_t)t, scale, aligned, kPH, kPW, sampling_ratio);
-              for (int i = lane; i < W * 8; i += 32) stage[i] = 0.f;
-              __syncwarp();
-              if (lane < kPW) {
-                const float inv = g.gw > 0 ? __fdiv_rn(1.0f, (float)g.gw) : 0.f;
-                for (int ix = 0; ix < g.gw; ++ix) {
-                  int xl, xh; float l, h;
-                  if (!bilinear_1d(sample_coord(g.sw, lane, g.bw, ix, g.gw), W, xl, xh, l, h)) continue;
-                  stage[xl * 8 + lane] += h * inv; stage[xh * 8 + lane] += l * inv;
-                }
-              }
-              __syncwarp();
-              s16_rows_dense(S, half, Wp, lim, stage, rb + kRecHead, acc);
-              __syncwarp();
-            }
-            // the two halves hold the partial sums of the even / odd rows
-#pragma unroll
-            for (int a = 0; a < kPH; ++a)
-#pragma unroll
-              for (int b = 0; b < kPW; ++b) acc[a][b] += __shfl_xor_sync(0xFFFFFFFFu, acc[a][b], 16);
-          }
-          slab_stage_wait_free();
-          if (ch < nch) {   // both halves write the same values to the same words (benign)
-#pragma unroll
-            for (int a = 0; a < kPH; ++a)
-#pragma unroll
-              for (int b = 0; b < kPW; ++b) stage[ch * kBins + a * kPW + b] = acc[a][b];
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            float *dst = output + ((size_t)t * C + cbase) * kBins;
-            const unsigned src = (unsigned)__cvta_generic_to_shared(stage);
-            const unsigned bytes = (unsigned)nch * kBins * 4u;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src), "r"(bytes), "l"(l2_stream) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        }
-        __syncwarp();                 // everybody is done reading the current record
-        if (tn < t_end) put_rec();
-        t = tn;
-      }
-      __syncthreads();
-    }
-  }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
 // Backward of the separable form: gF = A^T . gOut . B per channel pair, accumulated into an NHWC gradient with 8-byte
 // vector reductions (red.global.add.v2.f32): one coalesced 256 B reduction per warp and pixel; same two-pass structure.
 template <int PH0, int NPH, int kC>
@@ -1359,24 +1083,22 @@ SFOD_API int sfod_roi_align_fwd(const float *input, int layout, const float *roi
     SFOD_CUDA_TRY(cudaGetDevice(&cur_dev));
     SFOD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev));
     SFOD_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cur_dev));
-    // Which forward?  (1) 32-channel slab resident in shared memory, read straight from the caller's layout;
-    // (2) 16-channel slab with two half-warps per ROI for larger maps; (3) per-ROI loads from L2.
+    // Which forward?  (1) 32-channel slab resident in shared memory, read straight from the caller's layout; (2) per-ROI
+    // loads from L2 for maps whose slab does not fit (R101-C4 res4: 38 x 75 x 32 x 4 B = 365 KB).  A 16-channel slab with two
+    // half-warps per ROI (182 KB) was built and measured in round 2: parity-green but no faster than (2) -- 177 M warp
+    // instructions at 43 % issue with 10 warps per SM (profiles/r2c_s16_ncu_summary.txt); removed.
     const int ps = layout == SFOD_NCHW ? kPSNchw : kPSNhwc;
     const bool slab_ok = N <= kSlabMaxImages && (size_t)W * 8 <= (size_t)kSlabStage;
     const int slab_warps = !slab_ok ? 0 : slab_smem_bytes(H, W, 16, ps) <= (size_t)max_optin ? 16 : slab_smem_bytes(H, W, 8, ps) <= (size_t)max_optin ? 8 : 0;
-    int s16_warps = 0;
-    if (!slab_warps && N <= kSlabMaxImages && (size_t)W * 8 <= (size_t)kS16Stage && sep_rec_floats(H) <= 512 && (C % 16) == 0)
-      s16_warps = s16_smem_bytes(H, W, 12) <= (size_t)max_optin ? 12
-                  : s16_smem_bytes(H, W, 10) <= (size_t)max_optin ? 10 : s16_smem_bytes(H, W, 8) <= (size_t)max_optin ? 8 : 0;
     const float *feat = input;   // what the main kernel reads
-    if (!slab_warps && layout == SFOD_NCHW) {   // paths (2) and (3) read channels-last
+    if (!slab_warps && layout == SFOD_NCHW) {   // path (2) reads channels-last
       int rc = launch_transpose(input, static_cast<float *>(workspace), N, C, H * W, st);
       if (rc) return rc;
       feat = static_cast<const float *>(workspace);
     }
     roi_sep_tables_kernel<<<(R + 3) / 4, 128, 4 * rec_bytes, st>>>(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, recs, counter);
     SFOD_LAUNCH_CHECK();
-    if (slab_warps || s16_warps) {
+    if (slab_warps) {
       // launched with programmatic stream serialization: its prologue overlaps the table kernel (griddepcontrol.wait inside)
       cudaLaunchConfig_t cfg = {};
       cudaLaunchAttribute attr[1];
@@ -1393,10 +1115,7 @@ SFOD_API int sfod_roi_align_fwd(const float *input, int layout, const float *roi
       if (slab_warps == 16 && ps == kPSNchw) SFOD_SLAB_LAUNCH((roi_align_fwd_slab_kernel<16, kPSNchw>), 16, slab_smem_bytes(H, W, 16, ps));
       else if (slab_warps == 16) SFOD_SLAB_LAUNCH((roi_align_fwd_slab_kernel<16, kPSNhwc>), 16, slab_smem_bytes(H, W, 16, ps));
       else if (slab_warps == 8 && ps == kPSNchw) SFOD_SLAB_LAUNCH((roi_align_fwd_slab_kernel<8, kPSNchw>), 8, slab_smem_bytes(H, W, 8, ps));
-      else if (slab_warps == 8) SFOD_SLAB_LAUNCH((roi_align_fwd_slab_kernel<8, kPSNhwc>), 8, slab_smem_bytes(H, W, 8, ps));
-      else if (s16_warps == 12) SFOD_SLAB_LAUNCH((roi_align_fwd_slab16_kernel<12>), 12, s16_smem_bytes(H, W, 12));
-      else if (s16_warps == 10) SFOD_SLAB_LAUNCH((roi_align_fwd_slab16_kernel<10>), 10, s16_smem_bytes(H, W, 10));
-      else SFOD_SLAB_LAUNCH((roi_align_fwd_slab16_kernel<8>), 8, s16_smem_bytes(H, W, 8));
+      else SFOD_SLAB_LAUNCH((roi_align_fwd_slab_kernel<8, kPSNhwc>), 8, slab_smem_bytes(H, W, 8, ps));
 #undef SFOD_SLAB_LAUNCH
       SFOD_LAUNCH_CHECK();
       return SFOD_OK;

@@ -23,6 +23,15 @@ def allreduce_bn_stats(payload: Tensor, num_channels: int, group=None) -> float:
     return float(payload[2 * num_channels].item())
 
 
+def allreduce_bn_stats_device(payload: Tensor, num_channels: int, group=None) -> None:
+    """The same all-reduce without leaving the device: the global count stays in ``payload[2C]`` and is read there by
+    ``sfod_bn_finalize_apply_v2(count_on_device=1)`` -- no ``.item()``, so a multi-GPU AdaBN / teacher forward enqueues all
+    of its BN layers without a single host synchronisation."""
+    assert payload.dtype == torch.float64 and payload.numel() >= 2 * num_channels + 1
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(payload[: 2 * num_channels + 1], op=dist.ReduceOp.SUM, group=group)
+
+
 def finalize_stats_host(payload: Tensor, num_channels: int, total: float) -> Tuple[Tensor, Tensor]:
     """Host-side restatement of phase 2's first step (mean, biased variance in fp64); used by the gloo tests."""
     st = payload[: 2 * num_channels].reshape(num_channels, 2)

@@ -9,4 +9,5 @@ from .fast_rcnn import FastRCNNOutputLayers, SourceFreeFastRCNNOutputLayers  # n
 from .roi_heads import (FastRCNNConvFCHead, SourceFreeAdaptiveTeacherStandardROIHeads,  # noqa: F401
                         SourceFreeAdaptiveTeacherEvalStandardROIHeads, AdaptiveTeacherStandardROIHeads, build_box_head)
 from .vgg import build_vgg_backbone, vgg_backbone  # noqa: F401
+from .resnet import build_resnet_backbone, ResNet, BottleneckBlock, BasicStem, FrozenBatchNorm2d  # noqa: F401
 from .meta_arch import SourceFreeAdaptiveTeacherGeneralizedRCNN  # noqa: F401

@@ -34,18 +34,28 @@ class SfodBatchNorm2d(nn.BatchNorm2d):
                 and self.track_running_stats and self.momentum is not None)
 
     def forward(self, x: Tensor, fuse_relu: bool = False, inplace: bool = False, pre_bias: Optional[Tensor] = None,
-                fuse_maxpool: bool = False) -> Tensor:
-        """``pre_bias`` / ``fuse_relu`` / ``fuse_maxpool`` let a caller that owns the surrounding ``conv -> BN -> ReLU
-        [-> MaxPool2d(2, 2)]`` chain (``modeling/vgg.py``) hand the neighbours' elementwise work to the BN kernels."""
+                fuse_maxpool: bool = False, residual: Optional[Tensor] = None) -> Tensor:
+        """``pre_bias`` / ``fuse_relu`` / ``fuse_maxpool`` / ``residual`` let a caller that owns the surrounding ``conv -> BN
+        [+ shortcut] -> ReLU [-> MaxPool2d(2, 2)]`` chain (``modeling/vgg.py``, ``modeling/resnet.py``) hand the neighbours'
+        elementwise work to the BN kernels.
+
+        The native kernels serve exactly one mode -- train() under no_grad on CUDA fp32 NCHW/NHWC, the mode of every teacher
+        forward and AdaBN iteration of the reference.  Any other mode (autograd needed: the student; eval: frozen statistics;
+        CPU tensors) is NOT this library's hot path and runs the stock ``nn.BatchNorm2d`` of PyTorch (cuDNN / ATen), i.e. the
+        reference's own operator, with the fused neighbours applied in plain torch.  That is a deliberate operator boundary, not
+        a fallback of the kernels: ``ops.bn_train_forward`` itself raises on anything it does not implement."""
         if self._native_ok(x):
             return ops.bn_train_forward(x, self.weight, self.bias, self.running_mean, self.running_var,
                                         self.num_batches_tracked, self.momentum, self.eps, fuse_relu=fuse_relu,
-                                        inplace=inplace, group=self.process_group, pre_bias=pre_bias, fuse_maxpool=fuse_maxpool)
+                                        inplace=inplace, group=self.process_group, pre_bias=pre_bias, fuse_maxpool=fuse_maxpool,
+                                        residual=residual)
         if pre_bias is not None:
             x = x + pre_bias.view(1, -1, 1, 1)
         y = super().forward(x)
+        if residual is not None:
+            y = y + residual
         if fuse_relu:
-            y = torch.relu_(y)
+            y = torch.relu_(y) if not torch.is_grad_enabled() else torch.relu(y)
         return torch.nn.functional.max_pool2d(y, 2, 2) if fuse_maxpool else y
 
 

@@ -72,6 +72,22 @@ class DetectionBatch:
             kept.append(self.rows[i, :k])
         return res, kept
 
+    def lazy_instances(self) -> List[Instances]:
+        """The same detections as ``instances()[0]`` without touching the host now."""
+        from ..structures import LazyInstances
+
+        def make(i):
+            def materialize(inst):
+                k = self.host_counts()[0][i]
+                inst.pred_boxes = Boxes(self.boxes[i, :k])
+                inst.scores = self.scores[i, :k]
+                inst.pred_classes = self.classes[i, :k]
+            r = LazyInstances(self.image_sizes[i], materialize, source=self, index=i)
+            object.__setattr__(r, "_sfod_batch", self)
+            object.__setattr__(r, "_sfod_index", i)
+            return r
+        return [make(i) for i in range(len(self.image_sizes))]
+
     def pseudo_labels(self) -> List[Instances]:
         """threshold_bbox(proposal_type='roih') of every image: detections are score-descending, so the set with
         ``score > thres`` is the prefix of length pseudo_count."""
@@ -233,9 +249,15 @@ class FastRCNNOutputLayers(nn.Module):
         out = ops.frcnn_postprocess(scores, proposal_deltas, proposal_boxes, rows, image_sizes, **kw)
         return DetectionBatch(out, image_sizes, thr)
 
+    defer_host_read: bool = False   # True: detections are handed out as LazyInstances (no D2H read inside the forward)
+
     def inference(self, predictions: Tuple[Tensor, Tensor], proposals: List[Instances]):
-        """d2 FastRCNNOutputLayers.inference -> (List[Instances{pred_boxes, scores, pred_classes}], List[kept row indices])."""
+        """d2 FastRCNNOutputLayers.inference -> (List[Instances{pred_boxes, scores, pred_classes}], List[kept row indices]).
+        The per-image lengths need the device-side counts on the host: ONE read for the whole batch, here -- or, with
+        ``defer_host_read`` (CUDA-graph capture, engine/graph.py), when somebody first looks at a result."""
         batch = self.inference_batch(predictions, proposals)
+        if self.defer_host_read:
+            return batch.lazy_instances(), [batch.rows[i] for i in range(len(batch.image_sizes))]
         instances, kept = batch.instances()
         for i, inst in enumerate(instances):  # keeps the fused pseudo-label counts reachable from the d2-shaped result
             inst._sfod_batch, inst._sfod_index = batch, i

@@ -24,7 +24,7 @@ DT_F32, DT_I64, DT_U8 = 0, 1, 2   # enum sfod_dtype
 SCALE_CLAMP = math.log(1000.0 / 16)
 COORD_TRICK_MAX_N = 1000  # torchvision CPU switches batched_nms strategy at boxes.numel() > 4000
 
-_ws_cache: Dict[Tuple[str, int], Tensor] = {}
+_ws_cache: Dict[Tuple[str, int, int], Tensor] = {}
 _small_cache: Dict[Tuple, Tensor] = {}
 
 
@@ -97,9 +97,11 @@ def _require_cuda(*ts: Tensor) -> torch.device:
 
 
 def _workspace(dev: torch.device, tag: str, nbytes: int) -> Tensor:
-    """Grow-only per-(device, tag) workspace; stream-ordered reuse is safe because every user of a tag
-    enqueues on the current stream."""
-    key = (tag, dev.index if dev.index is not None else torch.cuda.current_device())
+    """Grow-only workspace per (tag, device, STREAM): reuse is stream-ordered, so a buffer is shared only by calls that are
+    enqueued on the same stream (forward and backward of an op on one stream may share it; another stream -- or a CUDA-graph
+    capture, which runs on its own stream and keeps replaying the addresses it recorded -- gets its own)."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (tag, idx, torch.cuda.current_stream(dev).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
@@ -619,13 +621,16 @@ class EmaPlan:
 def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], running_mean: Optional[Tensor],
                      running_var: Optional[Tensor], num_batches_tracked: Optional[Tensor], momentum: float = 0.1,
                      eps: float = 1e-5, fuse_relu: bool = False, inplace: bool = False, group=None,
-                     compute_output: bool = True, pre_bias: Optional[Tensor] = None, fuse_maxpool: bool = False) -> Optional[Tensor]:
+                     compute_output: bool = True, pre_bias: Optional[Tensor] = None, fuse_maxpool: bool = False,
+                     residual: Optional[Tensor] = None) -> Optional[Tensor]:
     """Train-mode BatchNorm2d forward without autograd (the AdaBN / no_grad-teacher case): batch statistics,
-    running-stat update, normalise(+ReLU)(+2x2 max-pool).  ``pre_bias`` (C) is added to ``x`` first (the bias of the
-    convolution feeding the BN, so the convolution itself can run bias-free).  With ``group`` (a torch.distributed process
-    group) the per-channel (sum, sum^2, count) triple is all-reduced so that all ranks normalise with the statistics of the
-    concatenated batch."""
-    dev = _require_cuda(x, pre_bias)
+    running-stat update, normalise(+residual)(+ReLU)(+2x2 max-pool).  ``pre_bias`` (C) is added to ``x`` first (the bias of the
+    convolution feeding the BN, so the convolution itself can run bias-free); ``residual`` (same shape and layout as ``x``) is
+    added to the normalised value before the ReLU (tail of a ResNet bottleneck).  With ``group`` (a torch.distributed process
+    group, ``True`` = default group) the per-channel (sum, sum^2, count) payload is all-reduced on the device -- the count stays
+    there, phase 2 reads it from the payload -- so that all ranks normalise with the statistics of the concatenated batch
+    without a host read."""
+    dev = _require_cuda(x, pre_bias, residual)
     xin, layout = _layout_of(x.detach())
     if xin.dtype != torch.float32:
         raise TypeError("bn_train_forward computes in float32")
@@ -635,17 +640,26 @@ def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor]
         pb = pre_bias.detach()
         if pb.dtype != torch.float32 or pb.numel() != Cc or not pb.is_contiguous():
             raise ValueError("pre_bias must be a contiguous float32 tensor with one entry per channel")
+    res = None
+    if residual is not None:
+        if fuse_maxpool:
+            raise ValueError("residual and fuse_maxpool are mutually exclusive")
+        res, rl = _layout_of(residual.detach())
+        if res.shape != xin.shape or res.dtype != torch.float32:
+            raise ValueError("residual must have the shape and dtype of x")
+        if rl != layout:
+            res = res.contiguous(memory_format=torch.channels_last if layout == NHWC else torch.contiguous_format)
     L = _lib.lib()
     with torch.cuda.device(dev):
         stats = torch.empty((L.sfod_bn_stats_bytes(Cc) // 8,), dtype=torch.float64, device=dev)
         with _timed("bn_partial_stats"):
             check(L.sfod_bn_partial_stats(xin.data_ptr(), pb.data_ptr() if pb is not None else None, layout, N, Cc, H * W,
                                           stats.data_ptr(), _stream(dev)), "sfod_bn_partial_stats")
-        total = float(N * H * W)
+        on_device = 0
         if group is not None:
-            from .engine.adabn_dist import allreduce_bn_stats
-            stats[2 * Cc] = total
-            total = allreduce_bn_stats(stats, Cc, group=group if group is not True else None)
+            from .engine.adabn_dist import allreduce_bn_stats_device
+            allreduce_bn_stats_device(stats, Cc, group=group if group is not True else None)   # payload [0, 2C] incl. the count
+            on_device = 1
         y = None
         if compute_output:
             if fuse_maxpool:
@@ -653,14 +667,43 @@ def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor]
                 y = torch.empty((N, Cc, H // 2, W // 2), dtype=torch.float32, device=dev, memory_format=fmt)
             else:
                 y = xin if inplace else torch.empty_like(xin)
-        with _timed("bn_finalize_apply_pool" if fuse_maxpool else "bn_finalize_apply"):
-            check(L.sfod_bn_finalize_apply(xin.data_ptr() if compute_output else None, pb.data_ptr() if pb is not None else None,
-                                           y.data_ptr() if y is not None else None, layout, N, Cc, H, W, stats.data_ptr(), total,
-                                           weight.data_ptr() if weight is not None else None,
-                                           bias.data_ptr() if bias is not None else None,
-                                           running_mean.data_ptr() if running_mean is not None else None,
-                                           running_var.data_ptr() if running_var is not None else None,
-                                           num_batches_tracked.data_ptr() if num_batches_tracked is not None else None,
-                                           float(momentum), float(eps), int(fuse_relu), int(fuse_maxpool), None, None, _stream(dev)),
-                  "sfod_bn_finalize_apply")
+        with _timed("bn_finalize_apply_pool" if fuse_maxpool else ("bn_finalize_apply_res" if res is not None else "bn_finalize_apply")):
+            check(L.sfod_bn_finalize_apply_v2(xin.data_ptr() if compute_output else None, pb.data_ptr() if pb is not None else None,
+                                              res.data_ptr() if (res is not None and compute_output) else None,
+                                              y.data_ptr() if y is not None else None, layout, N, Cc, H, W, stats.data_ptr(),
+                                              float(N * H * W), on_device,
+                                              weight.data_ptr() if weight is not None else None,
+                                              bias.data_ptr() if bias is not None else None,
+                                              running_mean.data_ptr() if running_mean is not None else None,
+                                              running_var.data_ptr() if running_var is not None else None,
+                                              num_batches_tracked.data_ptr() if num_batches_tracked is not None else None,
+                                              float(momentum), float(eps), int(fuse_relu), int(fuse_maxpool), None, None, _stream(dev)),
+                  "sfod_bn_finalize_apply_v2")
+    return y
+
+
+def bn_frozen_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], running_mean: Tensor, running_var: Tensor,
+                      eps: float = 1e-5, fuse_relu: bool = False, inplace: bool = False, residual: Optional[Tensor] = None) -> Tensor:
+    """FrozenBatchNorm2d / eval-mode BatchNorm forward with the fused neighbours (ReLU, residual add); no autograd."""
+    dev = _require_cuda(x, residual, running_mean, running_var)
+    xin, layout = _layout_of(x.detach())
+    if xin.dtype != torch.float32:
+        raise TypeError("bn_frozen_forward computes in float32")
+    N, Cc, H, W = xin.shape
+    res = None
+    if residual is not None:
+        res, rl = _layout_of(residual.detach())
+        if res.shape != xin.shape or res.dtype != torch.float32:
+            raise ValueError("residual must have the shape and dtype of x")
+        if rl != layout:
+            res = res.contiguous(memory_format=torch.channels_last if layout == NHWC else torch.contiguous_format)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        scratch = torch.empty((L.sfod_bn_frozen_scratch_bytes(Cc),), dtype=torch.uint8, device=dev)
+        y = xin if inplace else torch.empty_like(xin)
+        with _timed("bn_frozen_apply"):
+            check(L.sfod_bn_frozen_apply(xin.data_ptr(), res.data_ptr() if res is not None else None, y.data_ptr(), layout, N, Cc, H, W,
+                                         weight.data_ptr() if weight is not None else None, bias.data_ptr() if bias is not None else None,
+                                         running_mean.data_ptr(), running_var.data_ptr(), float(eps), int(fuse_relu),
+                                         scratch.data_ptr(), _stream(dev)), "sfod_bn_frozen_apply")
     return y

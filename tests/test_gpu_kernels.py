@@ -642,3 +642,114 @@ def test_normalize_pad_equals_preprocess_image(ops, cuda_device, dtype):
         assert sizesb == [(48, 64)] * 4
         assert gotb.is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
         assert _bits_equal(gotb.cpu().contiguous(), refb)
+
+
+# ------------------------------------------------------------------------------------------------ BN v2: residual fusion, frozen statistics
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("relu", [True, False])
+def test_bn_residual_add_relu_fusion(ops, cuda_device, layout, relu):
+    """Tail of a detectron2 BottleneckBlock (conv3+norm; out += shortcut; relu_) in one pass, vs nn.BatchNorm2d on the CPU:
+    output and running statistics to 1e-5 relative."""
+    g = torch.Generator().manual_seed(81)
+    shape = (2, 36, 19, 23)          # HW not a multiple of 4: head / tail paths of the vector kernel
+    x = torch.randn(shape, generator=g) * 2 + torch.linspace(-20, 20, shape[1]).view(1, -1, 1, 1)
+    r = torch.randn(shape, generator=g)
+    bn = torch.nn.BatchNorm2d(shape[1])
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.uniform_(-1, 1, generator=g)
+        bn.running_mean.normal_(generator=g); bn.running_var.uniform_(0.5, 2.0, generator=g)
+    dv = lambda t: t.to(cuda_device)  # noqa: E731
+    rm, rv, nbt = dv(bn.running_mean.clone()), dv(bn.running_var.clone()), dv(bn.num_batches_tracked.clone())
+    fmt = torch.channels_last if layout == "nhwc" else torch.contiguous_format
+    got = ops.bn_train_forward(dv(x).contiguous(memory_format=fmt), dv(bn.weight.detach()), dv(bn.bias.detach()), rm, rv, nbt,
+                               fuse_relu=relu, residual=dv(r).contiguous(memory_format=fmt))
+    bn.train()
+    with torch.no_grad():
+        ref = bn(x) + r
+        ref = torch.relu(ref) if relu else ref
+    _close(got, ref)
+    _close(rm, bn.running_mean); _close(rv, bn.running_var)
+    assert nbt.item() == 1
+    # frozen statistics (detectron2 FrozenBatchNorm2d / eval mode) with the same fusions
+    bn.eval()
+    with torch.no_grad():
+        ref = bn(x) + r
+        ref = torch.relu(ref) if relu else ref
+    got = ops.bn_frozen_forward(dv(x).contiguous(memory_format=fmt), dv(bn.weight.detach()), dv(bn.bias.detach()), dv(bn.running_mean),
+                                dv(bn.running_var), bn.eps, fuse_relu=relu, residual=dv(r).contiguous(memory_format=fmt))
+    _close(got, ref)
+    got = ops.bn_frozen_forward(dv(x).contiguous(memory_format=fmt), dv(bn.weight.detach()), dv(bn.bias.detach()), dv(bn.running_mean),
+                                dv(bn.running_var), bn.eps, fuse_relu=relu)
+    with torch.no_grad():
+        ref = torch.relu(bn(x)) if relu else bn(x)
+    _close(got, ref)
+
+
+def test_r101_c4_backbone_every_norm_layer_vs_cpu(cuda_device):
+    """BASELINE config [4]: the ResNet-101-C4 backbone (detectron2 key layout, RESNETS.NORM "BN", FREEZE_AT 2) in the teacher's
+    mode -- train() under no_grad.  Every one of its 94 norm layers runs on the native kernels (83 train-mode BatchNorms with
+    the ReLU / residual-add fusions, 11 frozen ones); each is checked against nn.BatchNorm2d / F.batch_norm on the CPU GIVEN THE
+    SAME INPUT (the convolution output captured on the GPU), so that cuDNN-vs-ATen convolution differences do not blur the
+    comparison: fused output and both running statistics to 1e-5 relative."""
+    import copy
+    from sfod_b200 import config, modeling
+    from sfod_b200.modeling.resnet import FrozenBatchNorm2d
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        cfg = config.r101_c4_source_free_cfg()
+        torch.manual_seed(5)
+        bb = modeling.build_resnet_backbone(cfg)
+        g = torch.Generator().manual_seed(6)
+        with torch.no_grad():
+            for m in bb.modules():          # non-trivial affine parameters and statistics everywhere
+                if isinstance(m, (torch.nn.BatchNorm2d, FrozenBatchNorm2d)):
+                    m.weight.uniform_(0.5, 1.5, generator=g); m.bias.uniform_(-0.5, 0.5, generator=g)
+                    m.running_mean.normal_(0, 0.1, generator=g); m.running_var.uniform_(0.5, 1.5, generator=g)
+        ref_state = copy.deepcopy(bb.state_dict())
+        bb.to(cuda_device).train()
+        norms = [(n, m) for n, m in bb.named_modules() if isinstance(m, (torch.nn.BatchNorm2d, FrozenBatchNorm2d))]
+        assert len(norms) == 94 and sum(isinstance(m, FrozenBatchNorm2d) for _, m in norms) == 11
+        cap = {}
+
+        def pre(name):
+            def hook(mod, args, kwargs):
+                cap[name] = dict(x=args[0].detach().clone().cpu(), relu=kwargs.get("fuse_relu", False),
+                                 res=None if kwargs.get("residual") is None else kwargs["residual"].detach().clone().cpu())
+            return hook
+
+        def post(name):
+            def hook(mod, args, kwargs, out):
+                cap[name]["y"] = out.detach().clone().cpu()
+            return hook
+        hs = []
+        for n, m in norms:
+            hs.append(m.register_forward_pre_hook(pre(n), with_kwargs=True)); hs.append(m.register_forward_hook(post(n), with_kwargs=True))
+        x = torch.randn(2, 3, 160, 224, generator=g) * 50
+        l0 = sfod_b200.ops.launch_count()
+        with torch.no_grad():
+            out = bb(x.to(cuda_device))
+        assert sfod_b200.ops.launch_count() - l0 >= 83 * 3 + 11 * 2          # every norm layer went through the library
+        for h in hs:
+            h.remove()
+        assert out["res4"].shape == (2, 1024, 10, 14)
+        gpu_state = {k: v.cpu() for k, v in bb.state_dict().items()}
+        for n, m in norms:
+            c = cap[n]
+            w, bias = ref_state[n + ".weight"], ref_state[n + ".bias"]
+            rm, rv = ref_state[n + ".running_mean"].clone(), ref_state[n + ".running_var"].clone()
+            frozen = isinstance(m, FrozenBatchNorm2d)
+            y = torch.nn.functional.batch_norm(c["x"], rm, rv, w, bias, not frozen, 0.1, 1e-5)
+            if c["res"] is not None:
+                y = y + c["res"]
+            if c["relu"]:
+                y = torch.relu(y)
+            _close(c["y"], y)
+            _close(gpu_state[n + ".running_mean"], rm); _close(gpu_state[n + ".running_var"], rv)
+            if not frozen:
+                assert gpu_state[n + ".num_batches_tracked"].item() == 1
+        # conv3 of every bottleneck carries the residual + ReLU fusion; shortcuts carry neither
+        assert all(cap[n]["res"] is not None and cap[n]["relu"] for n, _ in norms if n.endswith("conv3.norm"))
+        assert all(cap[n]["res"] is None and not cap[n]["relu"] for n, _ in norms if n.endswith("shortcut.norm"))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b

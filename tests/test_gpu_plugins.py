@@ -525,3 +525,38 @@ def test_teacher_ema_hook_on_the_trainer_protocol(cuda_device, when):
     assert hook._ema._plan is not plan
     assert torch.allclose(teacher[1].running_mean, 0.5 * student[1].running_mean)
 
+
+
+def test_cuda_graph_teacher_step_equals_eager(cfg, cuda_device):
+    """engine.graph.GraphedTeacherStep: the sync-free teacher step captured into a CUDA graph (one host call per step) returns the
+    same detections and pseudo-labels as the eager plugin chain, replay after replay, and updates the BN running statistics and
+    the EMA teacher exactly like the eager step."""
+    import copy
+    from sfod_b200.engine.graph import GraphedTeacherStep
+    torch.manual_seed(21)
+    teacher = registry.build_model(cfg); teacher.train()
+    student = registry.build_model(cfg); student.train()
+    with torch.no_grad():       # confident heads: non-empty, image-dependent results
+        teacher.roi_heads.box_predictor.cls_score.weight.mul_(400.0); teacher.roi_heads.box_predictor.bbox_pred.weight.mul_(300.0)
+        teacher.proposal_generator.rpn_head.anchor_deltas.weight.mul_(20.0)
+    t2, s2 = copy.deepcopy(teacher), copy.deepcopy(student)
+    g = torch.Generator().manual_seed(22)
+    batches = [torch.randint(0, 256, (2, 3, 600, 1200), dtype=torch.uint8, generator=g).to(cuda_device) for _ in range(3)]
+    ema_g, ema_e = engine.TeacherEMA(student, teacher), engine.TeacherEMA(s2, t2)
+    gs = GraphedTeacherStep(teacher, batches[0].shape, lambda: ema_g.step(0.9), threshold=0.8, warmup=2)
+    # the capture's warm-up already stepped `teacher` (BN statistics, EMA): bring the eager twin to the same state
+    t2.load_state_dict(teacher.state_dict())
+    for x in batches:
+        dets, pls = gs.run(x)
+        with torch.no_grad():
+            _, _, r = t2(x, branch="unsup_data_weak")
+        pl_e, _ = engine.process_pseudo_label(r, 0.8, "roih", "thresholding")
+        ema_e.step(0.9)
+        for a, b in zip(dets, r):
+            assert len(a) == len(b) and torch.equal(a.pred_boxes.tensor, b.pred_boxes.tensor) and torch.equal(a.scores, b.scores)
+            assert torch.equal(a.pred_classes, b.pred_classes)
+        for a, b in zip(pls, pl_e):
+            assert torch.equal(a.gt_boxes.tensor, b.gt_boxes.tensor) and torch.equal(a.gt_classes, b.gt_classes)
+        assert sum(len(p) for p in dets) > 0
+    for (k, a), b in zip(teacher.state_dict().items(), t2.state_dict().values()):
+        assert torch.equal(a, b), k

@@ -246,3 +246,41 @@ def test_matcher_and_preprocessing_host_paths():
 
 def L_ws(m):
     return _lib.lib().sfod_iou_match_workspace_bytes(m)
+
+
+def test_resnet101_c4_backbone_layout_and_cpu_forward_matches_oracle():
+    """BASELINE config [4]: detectron2's ResNet-101-C4 key layout (a detectron2 checkpoint loads unchanged), FREEZE_AT 2
+    (stem + res2 -> FrozenBatchNorm2d: 11 of the 94 norm layers), and the module's plain-torch mode (CPU) equals the oracle's
+    functional restatement bit for bit, in train (running statistics updated) and eval mode."""
+    import torch
+    from oracle import teacher_cpu
+    from sfod_b200 import config, modeling
+    from sfod_b200.modeling.resnet import FrozenBatchNorm2d
+    cfg = config.r101_c4_source_free_cfg(); cfg.MODEL.DEVICE = "cpu"
+    torch.manual_seed(0)
+    bb = modeling.build_resnet_backbone(cfg)
+    keys = list(bb.state_dict().keys())
+    assert keys[:5] == ["stem.conv1.weight", "stem.conv1.norm.weight", "stem.conv1.norm.bias", "stem.conv1.norm.running_mean",
+                        "stem.conv1.norm.running_var"]                              # frozen stem: no num_batches_tracked
+    assert "res2.0.shortcut.norm.running_var" in keys and "res3.0.conv1.norm.num_batches_tracked" in keys
+    assert "res4.22.conv3.norm.weight" in keys and not any(k.startswith("res5") for k in keys)
+    assert sum(isinstance(m, FrozenBatchNorm2d) for m in bb.modules()) == 11
+    assert sum(isinstance(m, torch.nn.BatchNorm2d) for m in bb.modules()) == 83
+    assert not bb.stem.conv1.weight.requires_grad and not bb.res2[0].conv1.weight.requires_grad and bb.res3[0].conv1.weight.requires_grad
+    assert bb.output_shape()["res4"].stride == 16 and bb.output_shape()["res4"].channels == 1024
+    assert bb.res3[0].conv1.stride == (2, 2) and bb.res3[0].conv2.stride == (1, 1)   # STRIDE_IN_1X1
+    x = torch.randn(2, 3, 64, 96, generator=torch.Generator().manual_seed(1))
+    for training in (True, False):
+        sd = {"backbone." + k: v.clone() for k, v in bb.state_dict().items()}
+        bb.train(training)
+        with torch.no_grad():
+            got = bb(x)["res4"]
+        want = teacher_cpu.resnet_c4_forward(sd, x, training)
+        assert torch.equal(got, want)
+        for k, v in bb.state_dict().items():
+            assert torch.equal(v, sd["backbone." + k]), k
+    # the whole detector of config [4] builds; checkpoint keys carry detectron2's prefixes
+    model = modeling.SourceFreeAdaptiveTeacherGeneralizedRCNN(cfg)
+    sdk = model.state_dict().keys()
+    assert "backbone.res4.22.conv3.norm.running_mean" in sdk and "roi_heads.box_head.fc1.weight" in sdk
+    assert model.roi_heads.box_head.fc1.weight.shape == (2048, 1024 * 7 * 7) and model.proposal_generator.anchor_generator.num_anchors[0] == 12
