@@ -561,11 +561,24 @@ def run_b200(args):
         "bn_finalize_apply_res": 12.0 * bn_elems_res,                         # read x + read shortcut + write y
         "bn_frozen_apply": 8.0 * bn_elems_frozen,                             # (residual variants read 4 B/element more; lower bound)
         "bn_partial_stats": 4.0 * bn_elems,                                   # read x
+        "bn_train_fused": None, "bn_train_fused_res": None,                   # single-launch L2-resident BN: filled in below
         "ema_multi_tensor": 12.0 * ema.numel,                                 # read student, read teacher, write teacher
         "roi_align_fwd": 4.0 * (B * Cf * Hf * Wf + 5 * R + 49 * R * Cf),      # feature map + rois in, (R, C, 7, 7) out
         "rpn_select": B * 20.0 * hwa + 20.0 * R,                              # logits + deltas in, boxes + logit out
         "frcnn_postprocess": 4.0 * R * (4 + 4 * NUM_CLASSES + NUM_CLASSES + 1) + B * T * 28.0,
     }
+    # Layers small enough for the single-launch BatchNorm leave the two-phase tags: split the element counts by what actually ran
+    fused_calls = ktimes.get("bn_train_fused", (0, 0))[0] / args.steps, ktimes.get("bn_train_fused_res", (0, 0))[0] / args.steps
+    if fused_calls[0] or fused_calls[1]:
+        from sfod_b200 import ops as _ops
+        per_layer = bn_layer_elements(args.workload, B)               # [(elements, has_residual, pooled)] of the train-mode BN layers
+        small = [(e, r) for e, r, p in per_layer if not p and 4 * e <= _ops.BN_FUSED_MAX_BYTES]
+        e_f, e_fr = sum(e for e, r in small if not r), sum(e for e, r in small if r)
+        alg["bn_train_fused"], alg["bn_train_fused_res"] = 8.0 * e_f, 12.0 * e_fr      # x once + y (+ shortcut): the re-read comes from L2
+        alg["bn_partial_stats"] -= 4.0 * (e_f + e_fr)
+        alg["bn_finalize_apply"] -= 8.0 * e_f
+        alg["bn_finalize_apply_res"] -= 12.0 * e_fr
+    alg = {k: v for k, v in alg.items() if v}
     kernels = {}
     for tag, (calls, tot_ms) in sorted(ktimes.items()):
         per_step_ms = tot_ms / args.steps
@@ -670,6 +683,22 @@ def bn_activation_elements(workload: str, B: int):
     res4 = (256 + 256 + 1024 + 1024) * s4 + 22 * (256 + 256 + 1024) * s4
     resid = 4 * 512 * s3 + 23 * 1024 * s4                                               # conv3 norm layers (residual + ReLU fusion)
     return (res3 + res4) * B, 0, resid * B, frozen * B
+
+
+def bn_layer_elements(workload: str, B: int):
+    """[(activation elements, residual fusion, max-pool fusion)] of every train-mode BN layer of the backbone, per step."""
+    if workload == "vgg":
+        hw = [(600, 1200)] * 2 + [(300, 600)] * 2 + [(150, 300)] * 3 + [(75, 150)] * 3 + [(37, 75)] * 3
+        ch = [64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512]
+        return [(c * h * w * B, False, i in {1, 3, 6, 9, 12}) for i, (c, (h, w)) in enumerate(zip(ch, hw))]
+    s3, s4 = 75 * 150, 38 * 75
+    out = []
+    for nblk, bc, oc, s in ((4, 128, 512, s3), (23, 256, 1024, s4)):
+        for i in range(nblk):
+            if i == 0:
+                out.append((oc * s * B, False, False))                 # projection shortcut
+            out += [(bc * s * B, False, False), (bc * s * B, False, False), (oc * s * B, True, False)]
+    return out
 
 
 def adabn_record(teacher, dev_batches, B, world, rank, dev, timed, steps, cfg):

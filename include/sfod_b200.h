@@ -248,6 +248,19 @@ int sfod_iou_match(const float *gt_boxes, const float *boxes, int M, int N, cons
                    int num_thresholds, int allow_low_quality, int64_t *matches, int8_t *match_labels, float *matched_vals,
                    void *workspace, size_t workspace_bytes, sfod_stream_t stream);
 
+/* Batched detectron2 `subsample_labels`: for each of `num_segments` label segments
+ * labels[offsets[s] .. offsets[s+1]) (int64; -1 = ignore, bg_label = negative, anything else positive) select
+ * num_pos = min(#positive, max_positive) positives and num_neg = min(#negative, num_samples - num_pos) negatives uniformly at
+ * random, as the per-image calls of ROIHeads._sample_proposals (reference
+ * daod/modeling/roi_heads/source_free_adaptive_teacher_roi_heads.py:177-186) and RPN.label_and_sample_anchors (called at
+ * daod/modeling/proposal_generator/rpn.py:45) do with two torch.randperm + two nonzero host syncs per image.
+ * sampled: (num_segments, num_samples) int64 segment-local indices, positives first, each group in ascending order of the
+ * counter-based key hash(seed, segment, index) (the k smallest keys = a uniform k-subset in random order), padded with -1;
+ * counts: (num_segments, 2) int32 (num_pos, num_neg), on the device.  max_positive = int(num_samples * positive_fraction)
+ * (computed by the caller with Python's float arithmetic, like the reference).  2 * num_samples <= 1024. */
+int sfod_subsample_labels(const int64_t *labels, const int32_t *offsets, int num_segments, int num_samples, int max_positive,
+                          int64_t bg_label, uint64_t seed, int64_t *sampled, int32_t *counts, sfod_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * BatchNorm train-mode forward / AdaBN statistic recomputation.  Replaces the
  * nn.BatchNorm2d train-mode forwards driven by test_refinement
@@ -287,6 +300,14 @@ int sfod_bn_finalize_apply_v2(const float *x, const float *pre_bias, const float
                               const float *weight, const float *bias, float *running_mean, float *running_var,
                               int64_t *num_batches_tracked, double momentum, double eps, int fuse_relu, int fuse_maxpool2,
                               float *save_mean, float *save_invstd, sfod_stream_t stream);
+/* Single-launch variant of phase 1 + phase 2 for NCHW activations that (mostly) fit the 126 MB L2 (late VGG layers, res3 / res4
+ * of R101-C4): a cooperative persistent kernel computes the statistics, crosses one grid barrier and normalises the chunks it has
+ * just read in reverse order, so the second read of x comes from L2 (~8 instead of 12 B/element of HBM traffic, 1 launch instead
+ * of 4).  Same arithmetic as the two-phase path (fp64 totals, ATen's running-stat update).  y may alias x.
+ * SFOD_ERR_UNSUPPORTED: no cooperative launch possible -- use the two-phase entry points. */
+int sfod_bn_train_fused(const float *x, const float *pre_bias, const float *residual, float *y, int N, int C, int H, int W,
+                        double *stats_dev, const float *weight, const float *bias, float *running_mean, float *running_var,
+                        int64_t *num_batches_tracked, double momentum, double eps, int fuse_relu, sfod_stream_t stream);
 /* FrozenBatchNorm2d / eval-mode BatchNorm with the same fusions: y = [relu](x * scale + shift [+ residual]),
  * scale = weight / sqrt(running_var + eps), shift = bias - running_mean * scale.  detectron2 freezes the stem and res2 of
  * the R101-C4 backbone (MODEL.BACKBONE.FREEZE_AT = 2 is not overridden by configs/r101_c4_cs_foggy_adaptive_teacher_source_free.yaml),
@@ -296,6 +317,38 @@ size_t sfod_bn_frozen_scratch_bytes(int C);
 int sfod_bn_frozen_apply(const float *x, const float *residual, float *y, int layout, int N, int C, int H, int W,
                          const float *weight, const float *bias, const float *running_mean, const float *running_var,
                          double eps, int fuse_relu, void *scratch, sfod_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Strong augmentation of the student's input on the device.  Replaces the PIL / torchvision CPU
+ * pipeline of reference daod/data/detection_utils.py:7-37, applied per image at
+ * daod/data/mappers/two_crop_augmentation_mapper.py:141-157: RandomApply(ColorJitter(0.4, 0.4, 0.4, 0.1), 0.8),
+ * RandomGrayscale(0.2), RandomApply(GaussianBlur((0.1, 2.0)), 0.5), 3 x RandomErasing(value="random").
+ * Images are (N, 3, H, W) uint8, RGB planes.  The random decisions are drawn by the caller (as torchvision draws them) and
+ * passed as per-image parameter records in DEVICE memory. */
+typedef struct sfod_jitter_params {
+  int32_t n_ops;          /* 0 = ColorJitter not applied; else 4 */
+  int32_t op[4];          /* order of application: 0 brightness, 1 contrast, 2 saturation, 3 hue */
+  float factor[4];        /* factor of op[k] */
+  float one_minus[4];     /* (float)(1.0 - factor) computed in double (what torchvision's _blend multiplies img2 with) */
+  int32_t grayscale;      /* != 0: RandomGrayscale hit (3-channel gray after the jitter) */
+} sfod_jitter_params;
+/* uint8 tensor arithmetic of torchvision.transforms.functional (adjust_brightness / contrast / saturation / hue,
+ * rgb_to_grayscale), operation by operation.  workspace: N * 8 bytes.  out may alias images. */
+int sfod_color_jitter(const uint8_t *images, int N, int H, int W, const sfod_jitter_params *params_dev, void *workspace,
+                      size_t workspace_bytes, uint8_t *out, sfod_stream_t stream);
+/* Separable Gaussian blur with reflect padding and round-half-even to uint8.  taps_dev: (N, 31) floats, image n uses
+ * taps[n][0 .. 2*radius[n]]; radius_dev[n] = 0 copies the image (RandomApply miss); max_radius = max over n (<= 15). */
+int sfod_gaussian_blur(const uint8_t *images, int N, int H, int W, const float *taps_dev, const int32_t *radius_dev,
+                       int max_radius, uint8_t *out, sfod_stream_t stream);
+typedef struct sfod_erase_params {
+  int32_t n_rects;        /* 0..4 rectangles, applied in order (a later one overwrites an earlier one) */
+  int32_t rect[4][4];     /* (top, left, height, width) */
+} sfod_erase_params;
+/* In place: every rectangle is filled with byte(255 * v), v ~ N(0, 1) from a counter-based generator keyed by `seed`, or
+ * v = noise[n][k][c][y][x] when `noise` ((N, 4, 3, H, W) floats) is given -- what ToTensor -> RandomErasing(value="random") ->
+ * ToPILImage leave in the rectangle. */
+int sfod_random_erase(uint8_t *images, int N, int H, int W, const sfod_erase_params *params_dev, const float *noise,
+                      uint64_t seed, sfod_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,14 @@ class EmaTensor(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class JitterParams(C.Structure):
+    _fields_ = [("n_ops", C.c_int32), ("op", C.c_int32 * 4), ("factor", C.c_float * 4), ("one_minus", C.c_float * 4), ("grayscale", C.c_int32)]
+
+
+class EraseParams(C.Structure):
+    _fields_ = [("n_rects", C.c_int32), ("rect", (C.c_int32 * 4) * 4)]
+
+
 class RpnParams(C.Structure):
     _fields_ = [("N", C.c_int), ("HWA", C.c_int), ("A", C.c_int), ("Hf", C.c_int), ("Wf", C.c_int), ("stride", C.c_int),
                 ("anchor_offset", C.c_float), ("weights", C.c_float * 4), ("scale_clamp", C.c_float),
@@ -73,10 +81,16 @@ SIGNATURES = {
     "sfod_iou_match_workspace_bytes": (C.c_size_t, [C.c_int]),
     "sfod_iou_match": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int, C.c_int,
                                  c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "sfod_color_jitter": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_size_t, c_ptr, c_ptr]),
+    "sfod_gaussian_blur": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr]),
+    "sfod_random_erase": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_uint64, c_ptr]),
+    "sfod_subsample_labels": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_uint64, c_ptr, c_ptr, c_ptr]),
     "sfod_bn_stats_bytes": (C.c_size_t, [C.c_int]),
     "sfod_bn_partial_stats": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int64, c_ptr, c_ptr]),
     "sfod_bn_finalize_apply": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.c_double, c_ptr, c_ptr,
                                          c_ptr, c_ptr, c_ptr, C.c_double, C.c_double, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
+    "sfod_bn_train_fused": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                      C.c_double, C.c_double, C.c_int, c_ptr]),
     "sfod_bn_frozen_scratch_bytes": (C.c_size_t, [C.c_int]),
     "sfod_bn_frozen_apply": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                                        C.c_double, C.c_int, c_ptr, c_ptr]),

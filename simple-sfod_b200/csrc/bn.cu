@@ -8,6 +8,7 @@
 // accumulation): every thread accumulates at most 64 pivot-shifted elements in fp32, everything above
 // that (warp, block, grid, and the E[x^2]-E[x]^2 combination) is fp64.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -345,6 +346,135 @@ __global__ void __launch_bounds__(kThreads) bn_apply_nhwc_scalar_kernel(const fl
   }
 }
 
+
+// ---- single-launch train-mode BatchNorm for activations that (mostly) fit the 126 MB L2: statistics -> grid barrier ->
+// normalise (+residual)(+ReLU), one cooperative persistent kernel.  The unit of work is (chunk of <= 4096 elements of one (n, c)
+// plane) x (one WARP): the late layers this kernel serves have small planes (38 x 75 = 2 850 elements on R101-C4 res4), so a
+// CTA-wide pass per plane would spend its time in block barriers and in the latency of a handful of loads; eight independent
+// warps per CTA keep eight chunks in flight.  Every warp owns a contiguous range of chunks; phase 1 accumulates the fp64 channel
+// totals (<= 64 pivot-shifted fp32 terms per thread between fp64 folds, as in bn_stats_nchw_kernel), phase 2 walks the SAME
+// chunks in reverse order, so the second read of x is served by L2 (most recently touched lines first): HBM sees ~4 B/element of
+// reads + 4 B/element of writes instead of 12, and the layer is one launch instead of four (memset, statistics, finalize, apply).
+constexpr int kFChunk = 4096;
+
+template <bool kRelu, bool kRes>
+__global__ void __launch_bounds__(kThreads, 2) bn_fused_nchw_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
+                                                                    const float *__restrict__ res, float *__restrict__ y, int NC, int C,
+                                                                    long long HW, double *__restrict__ stats, double count,
+                                                                    const float *__restrict__ weight, const float *__restrict__ bias,
+                                                                    float *__restrict__ running_mean, float *__restrict__ running_var,
+                                                                    long long *__restrict__ nbt, double momentum, double eps) {
+  namespace cg = cooperative_groups;
+  const int cpp = (int)((HW + kFChunk - 1) / kFChunk);            // chunks per plane
+  const long long nchunks = (long long)NC * cpp;
+  const int lane = threadIdx.x & 31;
+  const long long wg = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5), nw = (long long)gridDim.x * (kThreads / 32);
+  const long long q0 = nchunks * wg / nw, q1 = nchunks * (wg + 1) / nw;
+  // ---------------- phase 1
+  for (long long q = q0; q < q1; ++q) {
+    const int plane = (int)(q / cpp), c = plane % C;
+    const long long start = (q - (long long)plane * cpp) * kFChunk;
+    const int len = (int)min((long long)kFChunk, HW - start);
+    const float *p = x + (size_t)plane * HW + start;
+    const float pb = pre_bias ? pre_bias[c] : 0.f;
+    const float K = x[(size_t)c * HW] + pb;                       // pivot: first element of the channel in image 0
+    const int mis = (int)((reinterpret_cast<uintptr_t>(p) >> 2) & 3);
+    const int head = mis ? min(4 - mis, len) : 0;
+    const float4 *p4 = reinterpret_cast<const float4 *>(p + head);
+    const int n4 = (len - head) >> 2;
+    const int tail0 = head + (n4 << 2);
+    double ds = 0.0, ds2 = 0.0;
+    {
+      float s = 0.f, s2 = 0.f;
+      if (lane < head) { const float d = (p[lane] + pb) - K; s += d; s2 = fmaf(d, d, s2); }
+      if (tail0 + lane < len) { const float d = (p[tail0 + lane] + pb) - K; s += d; s2 = fmaf(d, d, s2); }
+      ds += (double)s; ds2 += (double)s2;
+    }
+    for (int b = 0; b < n4; b += 32 * 16) {                      // 16 float4 (64 elements) per lane between fp64 folds
+      float s = 0.f, s2 = 0.f;
+      float4 v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { const int i = b + k * 32 + lane; v[k] = i < n4 ? p4[i] : make_float4(K - pb, K - pb, K - pb, K - pb); }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float d0 = (v[k].x + pb) - K, d1 = (v[k].y + pb) - K, d2 = (v[k].z + pb) - K, d3 = (v[k].w + pb) - K;
+        s += (d0 + d1) + (d2 + d3);
+        s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+      }
+      ds += (double)s; ds2 += (double)s2;
+    }
+    ds = warp_sum(ds); ds2 = warp_sum(ds2);
+    if (lane == 0) flush_channel(stats, c, ds, ds2, (double)len, (double)K);
+  }
+  __threadfence();
+  cg::this_grid().sync();
+  // ---------------- phase 2: reverse order; the coefficients of up to 32 chunks are computed by the 32 lanes in parallel
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
+  for (long long qq = q1; qq > q0; qq -= 32) {
+    float sc_l = 0.f, sh_l = 0.f;
+    {
+      const long long myq = qq - 1 - lane;
+      if (myq >= q0) {
+        const int plane = (int)(myq / cpp), c = plane % C;
+        const double mean = __ldcg(stats + 2 * c) / count;
+        double var = __ldcg(stats + 2 * c + 1) / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double invstd = 1.0 / sqrt(var + eps);
+        const double w = weight ? (double)weight[c] : 1.0, b = bias ? (double)bias[c] : 0.0;
+        sc_l = (float)(w * invstd);
+        sh_l = (float)(b - mean * w * invstd);
+        if (plane < C && myq - (long long)plane * cpp == 0) {     // image 0, first chunk: owner of channel c's running statistics
+          const float mean_f = (float)mean;
+          if (running_mean) running_mean[c] = (float)(momentum * (double)mean_f + (1.0 - momentum) * (double)running_mean[c]);
+          if (running_var) {
+            const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+            running_var[c] = (float)(momentum * unbiased + (1.0 - momentum) * (double)running_var[c]);
+          }
+        }
+      }
+    }
+    const int nq = (int)min((long long)32, qq - q0);
+    for (int j = 0; j < nq; ++j) {
+      const long long q = qq - 1 - j;
+      const float sc = __shfl_sync(0xFFFFFFFFu, sc_l, j), sh = __shfl_sync(0xFFFFFFFFu, sh_l, j);
+      const int plane = (int)(q / cpp), c = plane % C;
+      const long long start = (q - (long long)plane * cpp) * kFChunk;
+      const int len = (int)min((long long)kFChunk, HW - start);
+      const float pb = pre_bias ? pre_bias[c] : 0.f;
+      const float *p = x + (size_t)plane * HW + start;
+      const float *r = kRes ? res + (size_t)plane * HW + start : nullptr;
+      float *o = y + (size_t)plane * HW + start;
+      const int mis = (int)((reinterpret_cast<uintptr_t>(p) >> 2) & 3);
+      const int head = mis ? min(4 - mis, len) : 0;
+      const float4 *p4 = reinterpret_cast<const float4 *>(p + head);
+      const float4 *r4 = reinterpret_cast<const float4 *>(r + head);
+      float4 *o4 = reinterpret_cast<float4 *>(o + head);
+      const int n4 = (len - head) >> 2;
+      const int tail0 = head + (n4 << 2);
+      if (lane < head) o[lane] = kRes ? bn1r<kRelu>(p[lane], pb, sc, sh, r[lane]) : bn1<kRelu>(p[lane], pb, sc, sh);
+      if (tail0 + lane < len) { const int t = tail0 + lane; o[t] = kRes ? bn1r<kRelu>(p[t], pb, sc, sh, r[t]) : bn1<kRelu>(p[t], pb, sc, sh); }
+      for (int b = 0; b < n4; b += 32 * 8) {
+        float4 v[8], w4[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = b + k * 32 + lane;
+          if (i < n4) { v[k] = p4[i]; if (kRes) w4[k] = __ldg(r4 + i); }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = b + k * 32 + lane;
+          if (i < n4) {
+            if (kRes) o4[i] = make_float4(bn1r<kRelu>(v[k].x, pb, sc, sh, w4[k].x), bn1r<kRelu>(v[k].y, pb, sc, sh, w4[k].y),
+                                          bn1r<kRelu>(v[k].z, pb, sc, sh, w4[k].z), bn1r<kRelu>(v[k].w, pb, sc, sh, w4[k].w));
+            else o4[i] = make_float4(bn1<kRelu>(v[k].x, pb, sc, sh), bn1<kRelu>(v[k].y, pb, sc, sh), bn1<kRelu>(v[k].z, pb, sc, sh),
+                                     bn1<kRelu>(v[k].w, pb, sc, sh));
+          }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 SFOD_API size_t sfod_bn_stats_bytes(int C) {
@@ -535,4 +665,42 @@ SFOD_API int sfod_bn_frozen_apply(const float *x, const float *residual, float *
   bn_frozen_coeffs_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, weight, bias, running_mean, running_var, (float)eps, scale, shift);
   SFOD_LAUNCH_CHECK();
   return launch_bn_apply(x, nullptr, residual, y, layout, N, C, H, W, scale, shift, fuse_relu, 0, st);
+}
+
+// Single-launch train-mode BatchNorm (statistics + running-stat update + normalise [+ residual] [+ ReLU]) for NCHW activations;
+// see bn_fused_nchw_kernel.  Returns SFOD_ERR_UNSUPPORTED when the cooperative grid cannot be formed (the caller then uses the
+// two-phase entry points, which is also the path for multi-GPU statistics and for the max-pool fusion).
+SFOD_API int sfod_bn_train_fused(const float *x, const float *pre_bias, const float *residual, float *y, int N, int C, int H, int W,
+                                 double *stats_dev, const float *weight, const float *bias, float *running_mean, float *running_var,
+                                 int64_t *num_batches_tracked, double momentum, double eps, int fuse_relu, sfod_stream_t stream) {
+  if (!x || !y || !stats_dev || N <= 0 || C <= 0 || H <= 0 || W <= 0) return SFOD_ERR_INVALID_ARG;
+  if (residual && ((reinterpret_cast<uintptr_t>(residual) ^ reinterpret_cast<uintptr_t>(x)) & 15u)) return SFOD_ERR_ALIGNMENT;
+  if (((reinterpret_cast<uintptr_t>(y) ^ reinterpret_cast<uintptr_t>(x)) & 15u)) return SFOD_ERR_ALIGNMENT;
+  cudaStream_t st = sfod_cu(stream);
+  const long long HW = (long long)H * W;
+  const long long nchunks = (long long)N * C * ((HW + kFChunk - 1) / kFChunk);
+  if ((long long)N * C > 0x7FFFFFFFll) return SFOD_ERR_UNSUPPORTED;
+  int dev = 0, sms = 0, per_sm = 0, coop = 0;
+  SFOD_CUDA_TRY(cudaGetDevice(&dev));
+  SFOD_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!coop) return SFOD_ERR_UNSUPPORTED;
+  SFOD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const void *kern = residual ? (fuse_relu ? (const void *)bn_fused_nchw_kernel<true, true> : (const void *)bn_fused_nchw_kernel<false, true>)
+                              : (fuse_relu ? (const void *)bn_fused_nchw_kernel<true, false> : (const void *)bn_fused_nchw_kernel<false, false>);
+  SFOD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+  if (per_sm < 1) return SFOD_ERR_UNSUPPORTED;
+  long long grid = (long long)sms * per_sm;
+  const long long want = (nchunks + kThreads / 32 - 1) / (kThreads / 32);   // one chunk per warp at least
+  if (grid > want) grid = want;
+  SFOD_CUDA_TRY(cudaMemsetAsync(stats_dev, 0, (size_t)C * 2 * sizeof(double), st));
+  int NC = N * C;
+  double count = (double)N * (double)HW;
+  long long hw = HW;
+  long long *nbt = reinterpret_cast<long long *>(num_batches_tracked);
+  void *args[] = {(void *)&x, (void *)&pre_bias, (void *)&residual, (void *)&y, (void *)&NC, (void *)&C, (void *)&hw, (void *)&stats_dev,
+                  (void *)&count, (void *)&weight, (void *)&bias, (void *)&running_mean, (void *)&running_var, (void *)&nbt,
+                  (void *)&momentum, (void *)&eps};
+  SFOD_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(kThreads), args, 0, st));
+  sfod_count_launch();
+  return SFOD_OK;
 }

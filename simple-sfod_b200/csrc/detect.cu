@@ -7,6 +7,7 @@
 #include "rpn.cuh"
 #include "frcnn.cuh"
 #include "match.cuh"
+#include "sample.cuh"
 
 // ===================================================================== generic torchvision-style NMS
 namespace {
@@ -458,5 +459,20 @@ SFOD_API int sfod_iou_match(const float *gt_boxes, const float *boxes, int M, in
                                                                   reinterpret_cast<signed char *>(match_labels));
     SFOD_LAUNCH_CHECK();
   }
+  return SFOD_OK;
+}
+
+// ===================================================================== batched subsample_labels
+SFOD_API int sfod_subsample_labels(const int64_t *labels, const int32_t *offsets, int num_segments, int num_samples, int max_positive,
+                                   int64_t bg_label, uint64_t seed, int64_t *sampled, int32_t *counts, sfod_stream_t stream) {
+  if (num_segments < 0 || num_samples <= 0 || max_positive < 0 || max_positive > num_samples) return SFOD_ERR_INVALID_ARG;
+  // selection buffer: the negatives start at num_pos and are padded to a power of two: num_pos + 2 (num_samples - num_pos) <= 2 num_samples
+  if (2 * num_samples > samplek::kMaxSamples) return SFOD_ERR_UNSUPPORTED;
+  if (num_segments == 0) return SFOD_OK;
+  if (!labels || !offsets || !sampled || !counts) return SFOD_ERR_INVALID_ARG;
+  samplek::subsample_kernel<<<num_segments, samplek::kThreads, 0, sfod_cu(stream)>>>(
+      reinterpret_cast<const long long *>(labels), offsets, num_samples, max_positive, (long long)bg_label,
+      (unsigned long long)seed, reinterpret_cast<long long *>(sampled), counts);
+  SFOD_LAUNCH_CHECK();
   return SFOD_OK;
 }

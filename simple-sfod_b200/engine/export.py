@@ -88,3 +88,41 @@ def prediction_to_gt(predictions: List[dict], dataset: dict, score_thresh: float
     out = copy.copy(dataset)
     out["annotations"] = ground_truths
     return out
+
+
+def load_pseudo_label_annotations(dataset: dict, image_sizes: Optional[Dict[int, tuple]] = None, device=None,
+                                  filter_empty: bool = True) -> Dict[int, Instances]:
+    """What the fixed-pseudo-label stage sees when it trains on the json written above: the reference registers that file with
+    ``register_coco_instances`` (reference daod/data/datasets.py:46-63), i.e. detectron2's ``load_coco_json`` +
+    ``annotations_to_instances`` -- XYWH_ABS boxes become XYXY ``gt_boxes``, COCO category ids are mapped to contiguous
+    ``gt_classes`` in sorted-id order.  Returns {image_id: Instances(gt_boxes, gt_classes)} (images without annotations get an
+    empty Instances when ``dataset["images"]`` lists them).  ``image_sizes`` overrides / supplies (height, width) per image id.
+    ``filter_empty``: drop boxes without area, as detectron2's DatasetMapper does (``utils.filter_empty_instances``) -- a
+    zero-width pseudo-label (a detection clipped at the image border) would otherwise put log(0) into the regression targets."""
+    from ..structures import Boxes
+    cats = sorted(c["id"] for c in dataset.get("categories", []))
+    if not cats:
+        cats = sorted({a["category_id"] for a in dataset["annotations"]})
+    cat_to_contiguous = {c: i for i, c in enumerate(cats)}
+    sizes = {im["id"]: (int(im.get("height", 0)), int(im.get("width", 0))) for im in dataset.get("images", [])}
+    if image_sizes:
+        sizes.update(image_sizes)
+    per_image: Dict[int, list] = {i: [] for i in sizes}
+    for a in dataset["annotations"]:
+        per_image.setdefault(a["image_id"], []).append(a)
+    out = {}
+    for img_id, anns in per_image.items():
+        inst = Instances(sizes.get(img_id, (0, 0)))
+        b = torch.tensor([a["bbox"] for a in anns], dtype=torch.float32).reshape(-1, 4)
+        b[:, 2] += b[:, 0]
+        b[:, 3] += b[:, 1]
+        c = torch.tensor([cat_to_contiguous[a["category_id"]] for a in anns], dtype=torch.int64)
+        if device is not None:
+            b, c = b.to(device), c.to(device)
+        if filter_empty and len(anns):
+            keep = ((b[:, 2] - b[:, 0]) > 1e-5) & ((b[:, 3] - b[:, 1]) > 1e-5)
+            b, c = b[keep], c[keep]
+        inst.gt_boxes = Boxes(b)
+        inst.gt_classes = c
+        out[img_id] = inst
+    return out

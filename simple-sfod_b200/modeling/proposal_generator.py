@@ -147,10 +147,13 @@ class RPN(nn.Module):
 
     @torch.no_grad()
     def label_and_sample_anchors(self, anchors: List[Boxes], gt_instances: List[Instances]):
-        """d2 RPN.label_and_sample_anchors -> (gt_labels: List[(R,) in {-1, 0, 1}], matched_gt_boxes: List[(R, 4)])."""
+        """d2 RPN.label_and_sample_anchors -> (gt_labels: List[(R,) in {-1, 0, 1}], matched_gt_boxes: List[(R, 4)]).
+        On CUDA the per-image ``_subsample_labels`` calls (two ``nonzero`` syncs + two randperm each) become one sampler launch
+        for the whole batch followed by a scatter of the sampled positions -- no host synchronisation at all."""
         anchors = Boxes.cat(anchors)
         gt_boxes = [x.gt_boxes for x in gt_instances]
         gt_labels, matched_gt_boxes = [], []
+        batched = anchors.tensor.is_cuda and hasattr(self.anchor_matcher, "match_boxes")
         for gt_boxes_i in gt_boxes:
             if hasattr(self.anchor_matcher, "match_boxes"):   # fused pairwise_iou + Matcher on the device
                 matched_idxs, gt_labels_i = self.anchor_matcher.match_boxes(gt_boxes_i, anchors)
@@ -159,14 +162,38 @@ class RPN(nn.Module):
             gt_labels_i = gt_labels_i.to(device=gt_boxes_i.device)
             if self.anchor_boundary_thresh >= 0:
                 raise NotImplementedError("RPN.BOUNDARY_THRESH >= 0 is not used by any shipped config")
-            gt_labels_i = self._subsample_labels(gt_labels_i)
+            if not batched:
+                gt_labels_i = self._subsample_labels(gt_labels_i)
             if len(gt_boxes_i) == 0:
                 matched_gt_boxes_i = torch.zeros_like(anchors.tensor)
             else:
                 matched_gt_boxes_i = gt_boxes_i[matched_idxs].tensor
             gt_labels.append(gt_labels_i)
             matched_gt_boxes.append(matched_gt_boxes_i)
+        if batched and len(gt_labels):
+            gt_labels = list(self._subsample_labels_batched(torch.stack(gt_labels)))
         return gt_labels, matched_gt_boxes
+
+    _sample_calls = 0
+
+    def _sampling_seed(self) -> int:
+        """Key of the counter-based sampler: a function of torch's seed and of how many batches were sampled so far."""
+        type(self)._sample_calls += 1
+        return (torch.initial_seed() * 0x9E3779B97F4A7C15 + 0x5DEECE66D * type(self)._sample_calls) & ((1 << 64) - 1)
+
+    def _subsample_labels_batched(self, labels: Tensor) -> Tensor:
+        """labels (N, R) int8 in {-1, 0, 1} -> the same with everything but the sampled positives (1) / negatives (0) set to -1."""
+        N, R = labels.shape
+        sampled, counts = ops.subsample_labels_batched(labels.reshape(-1).to(torch.int64), [R] * N, self.batch_size_per_image,
+                                                       self.positive_fraction, 0, self._sampling_seed())
+        S = sampled.shape[1]
+        ar = torch.arange(S, device=labels.device).unsqueeze(0)
+        nfg, ntot = counts[:, 0:1].to(torch.int64), counts.sum(dim=1, keepdim=True).to(torch.int64)
+        vals = (ar < nfg).to(labels.dtype)                                   # 1 for the sampled positives, 0 for the negatives
+        idx = torch.where(ar < ntot, sampled, torch.full_like(sampled, R))   # padding goes to a scratch column
+        out = labels.new_full((N, R + 1), -1)
+        out.scatter_(1, idx, vals)
+        return out[:, :R]
 
     def losses(self, anchors: List[Boxes], pred_objectness_logits: List[Tensor], gt_labels: List[Tensor],
                pred_anchor_deltas: List[Tensor], gt_boxes: List[Tensor]) -> Dict[str, Tensor]:

@@ -133,12 +133,23 @@ class _StandardROIHeadsBase(nn.Module):
         sampled_idxs = torch.cat([sampled_fg_idxs, sampled_bg_idxs], dim=0)
         return sampled_idxs, gt_classes[sampled_idxs]
 
+    _sample_calls = 0   # advances the counter-based sampling key of the batched path (one value per call)
+
+    def _sampling_seed(self) -> int:
+        type(self)._sample_calls += 1
+        return (torch.initial_seed() * 0x9E3779B97F4A7C15 + type(self)._sample_calls) & ((1 << 64) - 1)
+
     @torch.no_grad()
     def label_and_sample_proposals(self, proposals: List[Instances], targets: List[Instances], branch: str = "") -> List[Instances]:
-        """reference source_free_adaptive_teacher_roi_heads.py:165-215."""
+        """reference source_free_adaptive_teacher_roi_heads.py:165-215.  On CUDA the whole batch is labelled and sampled with
+        one fused matcher call per image (no sync), ONE sampler launch for all images and ONE device->host read of the
+        (num_fg, num_bg) counts -- the reference's loop synchronises ~4 times per image (two ``nonzero`` in subsample_labels,
+        two ``.item()`` for the logged counts).  Elsewhere (CPU tensors) the per-image torch steps run as in detectron2."""
         gt_boxes = [x.gt_boxes for x in targets]
         if self.proposal_append_gt:
             proposals = add_ground_truth_to_proposals(gt_boxes, proposals)
+        if len(proposals) and proposals[0].proposal_boxes.tensor.is_cuda and hasattr(self.proposal_matcher, "match_boxes"):
+            return self._label_and_sample_batched(proposals, targets, branch)
         proposals_with_gt, num_fg_samples, num_bg_samples = [], [], []
         for proposals_per_image, targets_per_image in zip(proposals, targets):
             has_gt = len(targets_per_image) > 0
@@ -164,6 +175,44 @@ class _StandardROIHeadsBase(nn.Module):
         storage.put_scalar("roi_head/num_target_fg_samples_" + branch, np.mean(num_fg_samples))
         storage.put_scalar("roi_head/num_target_bg_samples_" + branch, np.mean(num_bg_samples))
         return proposals_with_gt
+
+    def _label_and_sample_batched(self, proposals: List[Instances], targets: List[Instances], branch: str) -> List[Instances]:
+        from .. import ops
+        matched, classes = [], []
+        for proposals_per_image, targets_per_image in zip(proposals, targets):
+            matched_idxs, matched_labels = self.proposal_matcher.match_boxes(targets_per_image.gt_boxes, proposals_per_image.proposal_boxes)
+            if len(targets_per_image) > 0:                       # d2 ROIHeads._sample_proposals, labelling half
+                gt_classes = targets_per_image.gt_classes[matched_idxs]
+                gt_classes = torch.where(matched_labels == 0, torch.full_like(gt_classes, self.num_classes), gt_classes)
+                gt_classes = torch.where(matched_labels == -1, torch.full_like(gt_classes, -1), gt_classes)
+            else:
+                gt_classes = torch.zeros_like(matched_idxs) + self.num_classes
+            matched.append(matched_idxs)
+            classes.append(gt_classes)
+        lengths = [int(c.numel()) for c in classes]
+        sampled, counts = ops.subsample_labels_batched(torch.cat(classes), lengths, self.batch_size_per_image, self.positive_fraction,
+                                                       self.num_classes, self._sampling_seed())
+        host = counts.cpu().tolist()                              # the ONE device->host read of the batch
+        out, num_fg_samples, num_bg_samples = [], [], []
+        for i, (proposals_per_image, targets_per_image) in enumerate(zip(proposals, targets)):
+            nfg, nbg = host[i]
+            sampled_idxs = sampled[i, : nfg + nbg]
+            gt_classes = classes[i][sampled_idxs]
+            proposals_per_image = proposals_per_image[sampled_idxs]
+            proposals_per_image.gt_classes = gt_classes
+            if len(targets_per_image) > 0:
+                sampled_targets = matched[i][sampled_idxs]
+                for (trg_name, trg_value) in targets_per_image.get_fields().items():
+                    if trg_name.startswith("gt_") and not proposals_per_image.has(trg_name):
+                        proposals_per_image.set(trg_name, trg_value[sampled_targets])
+            else:
+                proposals_per_image.gt_boxes = Boxes(targets_per_image.gt_boxes.tensor.new_zeros((len(sampled_idxs), 4)))
+            num_fg_samples.append(nfg); num_bg_samples.append(nbg)
+            out.append(proposals_per_image)
+        storage = get_event_storage()
+        storage.put_scalar("roi_head/num_target_fg_samples_" + branch, np.mean(num_fg_samples))
+        storage.put_scalar("roi_head/num_target_bg_samples_" + branch, np.mean(num_bg_samples))
+        return out
 
     def _wants_loss(self, compute_loss: bool, compute_val_loss: bool) -> bool:
         return (self.training and compute_loss) or compute_val_loss

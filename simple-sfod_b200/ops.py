@@ -17,12 +17,13 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import EmaTensor, FrcnnParams, RpnParams, check
+from ._lib import EmaTensor, EraseParams, FrcnnParams, JitterParams, RpnParams, check
 
 NCHW, NHWC = 0, 1
 DT_F32, DT_I64, DT_U8 = 0, 1, 2   # enum sfod_dtype
 SCALE_CLAMP = math.log(1000.0 / 16)
 COORD_TRICK_MAX_N = 1000  # torchvision CPU switches batched_nms strategy at boxes.numel() > 4000
+BN_FUSED_MAX_BYTES = 100 * 1024 * 1024   # activations up to this size take the single-launch L2-resident BatchNorm (0 disables it)
 
 _ws_cache: Dict[Tuple[str, int, int], Tensor] = {}
 _small_cache: Dict[Tuple, Tensor] = {}
@@ -415,6 +416,52 @@ def normalize_pad(images: Union[Tensor, Sequence[Tensor]], pixel_mean: Sequence[
     return out, sizes
 
 
+# ----------------------------------------------------------------------------------------------- label sub-sampling
+_MASK64 = (1 << 64) - 1
+
+
+def sample_hash(seed: int, seg, idx):
+    """The counter-based key of ``sfod_subsample_labels`` (csrc/sample.cuh ``sample_hash``) restated on the host (numpy uint64):
+    splitmix64 finaliser of ``seed + golden * (seg << 32 | idx)``, upper 32 bits.  Pure arithmetic, used to derive the
+    permutation the kernel realises (tests, RNG-parity callers)."""
+    import numpy as np
+    with np.errstate(over="ignore"):
+        seg = np.asarray(seg, dtype=np.uint64); idx = np.asarray(idx, dtype=np.uint64)
+        x = np.uint64(seed & _MASK64) + np.uint64(0x9E3779B97F4A7C15) * ((seg << np.uint64(32)) | idx)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return (x >> np.uint64(32)).astype(np.uint32)
+
+
+def subsample_labels_batched(labels: Tensor, lengths: Sequence[int], num_samples: int, positive_fraction: float, bg_label: int,
+                             seed: int) -> Tuple[Tensor, Tensor]:
+    """detectron2 ``subsample_labels`` for all segments of ``labels`` (1-D int64, segment s = ``lengths[s]`` consecutive entries)
+    in one launch and without host synchronisation: returns (sampled (S, num_samples) int64 segment-local indices padded with
+    -1 -- positives first --, counts (S, 2) int32 (num_pos, num_neg)), both on the device."""
+    dev = _require_cuda(labels)
+    lab = labels.detach()
+    if lab.dtype != torch.int64:
+        lab = lab.to(torch.int64)
+    lab = lab.contiguous()
+    S = len(lengths)
+    if sum(int(v) for v in lengths) != lab.numel():
+        raise ValueError("lengths must sum to labels.numel()")
+    offs = [0]
+    for v in lengths:
+        offs.append(offs[-1] + int(v))
+    sampled = torch.empty((S, int(num_samples)), dtype=torch.int64, device=dev)
+    counts = torch.empty((S, 2), dtype=torch.int32, device=dev)
+    if S == 0:
+        return sampled, counts
+    max_pos = int(num_samples * positive_fraction)
+    with torch.cuda.device(dev), _timed("subsample_labels"):
+        check(_lib.lib().sfod_subsample_labels(lab.data_ptr(), _small_i32(dev, offs).data_ptr(), S, int(num_samples), max_pos, int(bg_label),
+                                               int(seed) & _MASK64, sampled.data_ptr(), counts.data_ptr(), _stream(dev)),
+              "sfod_subsample_labels")
+    return sampled, counts
+
+
 # ----------------------------------------------------------------------------------------------- box matching
 def iou_match(gt_boxes: Tensor, boxes: Tensor, thresholds: Sequence[float], labels: Sequence[int],
               allow_low_quality_matches: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
@@ -652,6 +699,22 @@ def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor]
     L = _lib.lib()
     with torch.cuda.device(dev):
         stats = torch.empty((L.sfod_bn_stats_bytes(Cc) // 8,), dtype=torch.float64, device=dev)
+        if (group is None and layout == NCHW and compute_output and not fuse_maxpool and xin.numel() * 4 <= BN_FUSED_MAX_BYTES
+                and BN_FUSED_MAX_BYTES > 0):
+            # activation fits L2: statistics -> grid barrier -> normalise in ONE cooperative launch (second read of x from L2)
+            y = xin if inplace else torch.empty_like(xin)
+            with _timed("bn_train_fused_res" if res is not None else "bn_train_fused"):
+                rc = L.sfod_bn_train_fused(xin.data_ptr(), pb.data_ptr() if pb is not None else None,
+                                           res.data_ptr() if res is not None else None, y.data_ptr(), N, Cc, H, W, stats.data_ptr(),
+                                           weight.data_ptr() if weight is not None else None, bias.data_ptr() if bias is not None else None,
+                                           running_mean.data_ptr() if running_mean is not None else None,
+                                           running_var.data_ptr() if running_var is not None else None,
+                                           num_batches_tracked.data_ptr() if num_batches_tracked is not None else None,
+                                           float(momentum), float(eps), int(fuse_relu), _stream(dev))
+            if rc == 0:
+                return y
+            if rc != 3:   # SFOD_ERR_UNSUPPORTED: no cooperative grid -> the two-phase path below
+                check(rc, "sfod_bn_train_fused")
         with _timed("bn_partial_stats"):
             check(L.sfod_bn_partial_stats(xin.data_ptr(), pb.data_ptr() if pb is not None else None, layout, N, Cc, H * W,
                                           stats.data_ptr(), _stream(dev)), "sfod_bn_partial_stats")
@@ -707,3 +770,109 @@ def bn_frozen_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor
                                          running_mean.data_ptr(), running_var.data_ptr(), float(eps), int(fuse_relu),
                                          scratch.data_ptr(), _stream(dev)), "sfod_bn_frozen_apply")
     return y
+
+
+# ----------------------------------------------------------------------------------------------- strong augmentation (8f rank 3)
+def _u8_batch(images: Tensor) -> Tuple[Tensor, torch.device]:
+    dev = _require_cuda(images)
+    if images.dim() != 4 or images.shape[1] != 3 or images.dtype != torch.uint8:
+        raise ValueError("images must be a (N, 3, H, W) uint8 tensor")
+    return images.contiguous(), dev
+
+
+def _struct_array_to_device(arr, dev: torch.device) -> Tensor:
+    raw = bytes(arr)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+
+
+def color_jitter(images: Tensor, params: Sequence[dict]) -> Tensor:
+    """torchvision ColorJitter (+ RandomGrayscale) on a uint8 batch with per-image decisions ``params[n] = dict(order=[...],
+    factors=[...], grayscale=bool)``: ``order`` lists op codes (0 brightness, 1 contrast, 2 saturation, 3 hue) in application
+    order with their ``factors`` (Python floats); an empty order = jitter not applied."""
+    x, dev = _u8_batch(images)
+    N, _, H, W = x.shape
+    if len(params) != N:
+        raise ValueError("one parameter record per image")
+    arr = (JitterParams * max(N, 1))()
+    for n, p in enumerate(params):
+        order, fac = list(p.get("order", [])), list(p.get("factors", []))
+        if len(order) != len(fac) or len(order) > 4 or any(o not in (0, 1, 2, 3) for o in order):
+            raise ValueError("order / factors: up to four ops from {0, 1, 2, 3} with one factor each")
+        arr[n].n_ops = len(order)
+        for k, (o, f) in enumerate(zip(order, fac)):
+            arr[n].op[k], arr[n].factor[k], arr[n].one_minus[k] = int(o), float(f), 1.0 - float(f)
+        arr[n].grayscale = int(bool(p.get("grayscale", False)))
+    out = torch.empty_like(x)
+    if N == 0:
+        return out
+    with torch.cuda.device(dev), _timed("color_jitter"):
+        rec = _struct_array_to_device(arr, dev)
+        ws = _workspace(dev, "jitter", 8 * N)
+        check(_lib.lib().sfod_color_jitter(x.data_ptr(), N, H, W, rec.data_ptr(), ws.data_ptr(), ws.numel(), out.data_ptr(), _stream(dev)),
+              "sfod_color_jitter")
+    return out
+
+
+def gaussian_kernel1d(kernel_size: int, sigma: float) -> Tensor:
+    """torchvision.transforms._functional_tensor._get_gaussian_kernel1d (float32, CPU)."""
+    ksize_half = (kernel_size - 1) * 0.5
+    x = torch.linspace(-ksize_half, ksize_half, steps=kernel_size)
+    pdf = torch.exp(-0.5 * (x / sigma).pow(2))
+    return pdf / pdf.sum()
+
+
+def gaussian_blur(images: Tensor, sigmas: Sequence[Optional[float]], kernel_sizes: Optional[Sequence[int]] = None) -> Tensor:
+    """Separable Gaussian blur of a uint8 batch; ``sigmas[n] is None`` leaves image n untouched.  The kernel size defaults to
+    ``2 * ceil(3 sigma) + 1`` (support +-3 sigma); taps are torchvision's ``_get_gaussian_kernel1d``; reflect padding."""
+    x, dev = _u8_batch(images)
+    N, _, H, W = x.shape
+    if len(sigmas) != N:
+        raise ValueError("one sigma (or None) per image")
+    taps = torch.zeros((max(N, 1), 31), dtype=torch.float32)
+    radius = [0] * N
+    for n, sg in enumerate(sigmas):
+        if sg is None:
+            continue
+        ks = int(kernel_sizes[n]) if kernel_sizes is not None else 2 * max(1, math.ceil(3.0 * float(sg))) + 1
+        if ks % 2 == 0 or ks < 3 or ks > 31:
+            raise ValueError("kernel size must be odd, 3..31")
+        radius[n] = (ks - 1) // 2
+        taps[n, :ks] = gaussian_kernel1d(ks, float(sg))
+    out = torch.empty_like(x)
+    if N == 0:
+        return out
+    with torch.cuda.device(dev), _timed("gaussian_blur"):
+        taps_dev, radius_dev = taps.to(dev), _small_i32(dev, radius)      # named: both must outlive the launch call
+        check(_lib.lib().sfod_gaussian_blur(x.data_ptr(), N, H, W, taps_dev.data_ptr(), radius_dev.data_ptr(), max(radius),
+                                            out.data_ptr(), _stream(dev)), "sfod_gaussian_blur")
+    return out
+
+
+def random_erase_(images: Tensor, rects: Sequence[Sequence[Tuple[int, int, int, int]]], noise: Optional[Tensor] = None, seed: int = 0) -> Tensor:
+    """In place RandomErasing(value="random") on a uint8 batch: ``rects[n]`` = up to four (top, left, height, width) rectangles
+    applied in order; the fill is ``byte(255 * v)`` with v ~ N(0, 1) (device generator keyed by ``seed``), or
+    ``v = noise[n, k, c, y, x]`` ((N, 4, 3, H, W) float32) when given."""
+    dev = _require_cuda(images, noise)
+    if images.dim() != 4 or images.shape[1] != 3 or images.dtype != torch.uint8 or not images.is_contiguous():
+        raise ValueError("images must be a contiguous (N, 3, H, W) uint8 tensor (modified in place)")
+    N, _, H, W = images.shape
+    if len(rects) != N:
+        raise ValueError("one rectangle list per image")
+    arr = (EraseParams * max(N, 1))()
+    for n, rl in enumerate(rects):
+        if len(rl) > 4:
+            raise ValueError("at most four rectangles per image")
+        arr[n].n_rects = len(rl)
+        for k, (i, j, h, w) in enumerate(rl):
+            if i < 0 or j < 0 or h < 0 or w < 0 or i + h > H or j + w > W:
+                raise ValueError(f"rectangle {(i, j, h, w)} outside the image")
+            arr[n].rect[k][0], arr[n].rect[k][1], arr[n].rect[k][2], arr[n].rect[k][3] = int(i), int(j), int(h), int(w)
+    if noise is not None and (noise.shape != (N, 4, 3, H, W) or noise.dtype != torch.float32 or not noise.is_contiguous()):
+        raise ValueError("noise must be a contiguous (N, 4, 3, H, W) float32 tensor")
+    if N == 0:
+        return images
+    with torch.cuda.device(dev), _timed("random_erase"):
+        rec = _struct_array_to_device(arr, dev)
+        check(_lib.lib().sfod_random_erase(images.data_ptr(), N, H, W, rec.data_ptr(), noise.data_ptr() if noise is not None else None,
+                                           int(seed) & _MASK64, _stream(dev)), "sfod_random_erase")
+    return images

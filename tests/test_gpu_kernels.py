@@ -480,9 +480,19 @@ def test_threshold_select(ops, cuda_device):
 
 
 # ------------------------------------------------------------------------------------------------ BatchNorm / AdaBN
-@pytest.mark.parametrize("shape", [(2, 64, 75, 150), (2, 512, 37, 75), (1, 128, 64, 96), (3, 24, 17, 19)])
+@pytest.fixture(params=["two_phase", "fused_l2"])
+def bn_path(request, ops):
+    """Both BatchNorm implementations: statistics kernel + finalize/apply kernel, and the single cooperative launch that serves
+    activations <= ops.BN_FUSED_MAX_BYTES (NCHW) from L2."""
+    old = ops.BN_FUSED_MAX_BYTES
+    ops.BN_FUSED_MAX_BYTES = 0 if request.param == "two_phase" else 1 << 40
+    yield request.param
+    ops.BN_FUSED_MAX_BYTES = old
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 75, 150), (2, 512, 37, 75), (1, 128, 64, 96), (3, 24, 17, 19), (2, 3, 200, 331)])
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
-def test_bn_train_forward(ops, cuda_device, shape, layout):
+def test_bn_train_forward(ops, cuda_device, shape, layout, bn_path):
     g = torch.Generator().manual_seed(71)
     x = torch.randn(shape, generator=g) * 3 + torch.linspace(-50, 50, shape[1]).view(1, -1, 1, 1)
     bn = torch.nn.BatchNorm2d(shape[1])
@@ -505,6 +515,22 @@ def test_bn_train_forward(ops, cuda_device, shape, layout):
     assert nbt.item() == 1
     yr = ops.bn_train_forward(xd, bn.weight.detach().to(d), bn.bias.detach().to(d), None, None, None, 0.1, 1e-5, fuse_relu=True)
     _close(yr, torch.relu(yref), rtol=1e-5, atol_scale=1e-5)
+    if layout == "nchw":      # the path under test really ran
+        ops.timers.start()
+        ops.bn_train_forward(xd, None, None, None, None, None)
+        tags = set(ops.timers.stop())
+        assert tags == ({"bn_train_fused"} if bn_path == "fused_l2" else {"bn_partial_stats", "bn_finalize_apply"}), tags
+    # conv bias folded in + in place
+    cb = torch.randn(shape[1], generator=g)
+    bn2 = torch.nn.BatchNorm2d(shape[1]).train()
+    with torch.no_grad():
+        yref2 = torch.relu(bn2(x + cb.view(1, -1, 1, 1)))
+    rm2, rv2 = torch.zeros(shape[1], device=d), torch.ones(shape[1], device=d)
+    xin = xd.clone()
+    y2 = ops.bn_train_forward(xin, None, None, rm2, rv2, None, 0.1, 1e-5, fuse_relu=True, inplace=True, pre_bias=cb.to(d))
+    assert y2.data_ptr() == xin.data_ptr()
+    _close(y2, yref2, rtol=1e-5, atol_scale=1e-5)
+    _close(rm2, bn2.running_mean, rtol=1e-5, atol_scale=1e-6); _close(rv2, bn2.running_var, rtol=1e-5, atol_scale=0)
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 76, 152), (2, 32, 75, 150), (1, 16, 37, 75), (2, 8, 5, 3)])
@@ -647,7 +673,7 @@ def test_normalize_pad_equals_preprocess_image(ops, cuda_device, dtype):
 # ------------------------------------------------------------------------------------------------ BN v2: residual fusion, frozen statistics
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
 @pytest.mark.parametrize("relu", [True, False])
-def test_bn_residual_add_relu_fusion(ops, cuda_device, layout, relu):
+def test_bn_residual_add_relu_fusion(ops, cuda_device, layout, relu, bn_path):
     """Tail of a detectron2 BottleneckBlock (conv3+norm; out += shortcut; relu_) in one pass, vs nn.BatchNorm2d on the CPU:
     output and running statistics to 1e-5 relative."""
     g = torch.Generator().manual_seed(81)
@@ -729,7 +755,7 @@ def test_r101_c4_backbone_every_norm_layer_vs_cpu(cuda_device):
         l0 = sfod_b200.ops.launch_count()
         with torch.no_grad():
             out = bb(x.to(cuda_device))
-        assert sfod_b200.ops.launch_count() - l0 >= 83 * 3 + 11 * 2          # every norm layer went through the library
+        assert sfod_b200.ops.launch_count() - l0 >= 83 + 11 * 2              # every norm layer went through the library (>= 1 launch each)
         for h in hs:
             h.remove()
         assert out["res4"].shape == (2, 1024, 10, 14)
@@ -753,3 +779,183 @@ def test_r101_c4_backbone_every_norm_layer_vs_cpu(cuda_device):
         assert all(cap[n]["res"] is None and not cap[n]["relu"] for n, _ in norms if n.endswith("shortcut.norm"))
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
+# ------------------------------------------------------------------------------------------------ batched subsample_labels (8f rank 1)
+def _perm_from_hash(ops, seed, seg, cand):
+    """The permutation `randperm(len(cand))` must return for detectron2's subsample_labels to reproduce the kernel: candidates
+    ordered by (hash, index)."""
+    h = ops.sample_hash(seed, seg, cand.numpy())
+    order = np.lexsort((cand.numpy(), h))
+    return torch.from_numpy(order.astype(np.int64))
+
+
+def test_subsample_labels_batched_equals_detectron2_with_the_same_permutation(ops, cuda_device):
+    """sfod_subsample_labels vs oracle.subsample_labels (detectron2's) fed the permutation the kernel's counter-based keys
+    define: identical index lists (order included), for ROI-head style labels (bg = 8, ignore = -1) and RPN style ({-1, 0, 1},
+    bg = 0), segments with no / few / many positives, empty segments, 34 200 anchors."""
+    g = torch.Generator().manual_seed(91)
+    def roi_seg(n, p_fg, p_ign):
+        u = torch.rand(n, generator=g)
+        lab = torch.full((n,), 8, dtype=torch.int64)
+        lab[u < p_fg] = torch.randint(0, 8, (int((u < p_fg).sum()),), generator=g)
+        lab[u > 1 - p_ign] = -1
+        return lab
+    cases = [
+        (8, 512, 0.25, [roi_seg(2003, 0.3, 0.05), roi_seg(2000, 0.01, 0.0), roi_seg(2000, 0.0, 0.0), roi_seg(37, 0.5, 0.2),
+                        torch.full((50,), -1, dtype=torch.int64), torch.zeros(0, dtype=torch.int64), roi_seg(700, 1.0, 0.0)]),
+        (0, 256, 0.5, [(torch.rand(34200, generator=g) < q).to(torch.int64) - (torch.rand(34200, generator=g) < 0.1).to(torch.int64) * 0
+                       for q in (0.01, 0.0005, 0.3)]),
+    ]
+    for bg, num_samples, frac, segs in cases:
+        if bg == 0:   # RPN labels: 1 positive, 0 negative, -1 ignore
+            segs = [torch.where(torch.rand(s.numel(), generator=g) < 0.2, torch.full_like(s, -1), s) for s in segs]
+        seed = 0xC0FFEE1234 + bg
+        lab = torch.cat(segs)
+        sampled, counts = ops.subsample_labels_batched(lab.to(cuda_device), [s.numel() for s in segs], num_samples, frac, bg, seed)
+        sampled, counts = sampled.cpu(), counts.cpu().tolist()
+        for i, s in enumerate(segs):
+            calls = []
+            def randperm(n, device=None, _i=i, _s=s):
+                cand = ((_s != -1) & (_s != bg)).nonzero().flatten() if not calls else (_s == bg).nonzero().flatten()
+                calls.append(1)
+                assert cand.numel() == n
+                return _perm_from_hash(ops, seed, _i, cand)
+            pos, neg = o.subsample_labels(s, num_samples, frac, bg, randperm=randperm)
+            assert counts[i] == [pos.numel(), neg.numel()], (i, counts[i], pos.numel(), neg.numel())
+            assert torch.equal(sampled[i, :pos.numel()], pos) and torch.equal(sampled[i, pos.numel():pos.numel() + neg.numel()], neg)
+            assert (sampled[i, pos.numel() + neg.numel():] == -1).all()
+
+
+def test_subsample_labels_batched_is_uniform(ops, cuda_device):
+    """Every candidate is selected with probability k / n (binomial 5-sigma band over 4000 independent keys)."""
+    n, k, trials = 200, 20, 4000
+    lab = torch.zeros(n, dtype=torch.int64).repeat(trials)            # all negatives, bg = 0
+    sampled, counts = ops.subsample_labels_batched(lab.to(cuda_device), [n] * trials, k, 0.0, 0, 99)
+    assert (counts.cpu() == torch.tensor([0, k])).all()
+    freq = torch.bincount(sampled.cpu().flatten(), minlength=n).double()
+    p = k / n
+    sigma = (trials * p * (1 - p)) ** 0.5
+    assert (freq - trials * p).abs().max() < 5 * sigma
+    # first position uniform too (random ORDER, not just a random subset)
+    first = torch.bincount(sampled[:, 0].cpu(), minlength=n).double()
+    assert (first - trials / n).abs().max() < 6 * (trials / n) ** 0.5
+
+
+# ------------------------------------------------------------------------------------------------ strong augmentation (8f rank 3)
+def _aug_images(N=3, H=97, W=131, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randint(0, 256, (N, 3, H, W), dtype=torch.uint8, generator=g)
+    x[0, :, :10, :10] = 0; x[0, :, 10:20, :10] = 255; x[0, :, 20:30, :10] = 77        # flat patches (maxc == minc in rgb2hsv)
+    return x
+
+
+def _tv_jitter(img, p):
+    import torchvision.transforms.functional as TF
+    for o, f in zip(p["order"], p["factors"]):
+        img = (TF.adjust_brightness, TF.adjust_contrast, TF.adjust_saturation, TF.adjust_hue)[o](img, f)
+    if p.get("grayscale"):
+        img = TF.rgb_to_grayscale(img, num_output_channels=3)
+    return img
+
+
+def test_color_jitter_equals_torchvision_tensor_ops(ops, cuda_device):
+    """ColorJitter(0.4, 0.4, 0.4, 0.1) + RandomGrayscale of reference daod/data/detection_utils.py:13-16 vs
+    torchvision.transforms.functional on uint8 CPU tensors.  Parity definition: brightness / saturation / hue / grayscale are
+    bit-exact; a sequence containing contrast may differ by ONE level on <= 0.01 % of the pixels (the image mean is an exact
+    integer sum here and a float32 cascade sum in ATen)."""
+    x = _aug_images()
+    g = torch.Generator().manual_seed(3)
+    recs = []
+    for o in range(4):                                           # every op alone, extreme factors
+        lo, hi = [(0.6, 1.4), (0.6, 1.4), (0.6, 1.4), (-0.1, 0.1)][o]
+        for f in (lo, hi, (lo + hi) / 2 + 0.0123):
+            recs.append(dict(order=[o], factors=[f]))
+    for _ in range(12):                                          # full random sequences as ColorJitter.get_params draws them
+        order = torch.randperm(4, generator=g).tolist()
+        vals = [float(torch.empty(1).uniform_(0.6, 1.4, generator=g)) for _ in range(3)] + [float(torch.empty(1).uniform_(-0.1, 0.1, generator=g))]
+        recs.append(dict(order=order, factors=[vals[k] for k in order], grayscale=bool(torch.rand(1, generator=g) < 0.3)))
+    recs += [dict(order=[], factors=[], grayscale=True), dict(order=[], factors=[])]
+    for r0 in range(0, len(recs), 3):
+        batch = recs[r0:r0 + 3]
+        imgs = x[:len(batch)]
+        got = ops.color_jitter(imgs.to(cuda_device), batch).cpu()
+        for n, p in enumerate(batch):
+            want = _tv_jitter(imgs[n], p)
+            diff = (got[n].int() - want.int()).abs()
+            if 1 in p["order"]:
+                assert diff.max() <= 1 and (diff > 0).float().mean() <= 1e-4, (p, int(diff.max()), float((diff > 0).float().mean()))
+            else:
+                assert diff.max() == 0, (p, int(diff.max()), int((diff > 0).sum()))
+
+
+def test_gaussian_blur_vs_torchvision_and_pil(ops, cuda_device):
+    """GaussianBlur((0.1, 2.0)) of reference daod/data/transforms/augmentations.py:6-21 (PIL ImageFilter.GaussianBlur(radius=sigma)).
+    Parity definition: (a) against torchvision's tensor gaussian_blur with the same kernel size and sigma (a true Gaussian, reflect
+    padding): at most one level on <= 0.5 % of the pixels (separable vs 2-D summation order); (b) against PIL's 3-pass box
+    approximation, the filter the reference actually runs: mean |difference| <= 1.5 levels on a natural-statistics image interior
+    (the two are different discretisations of the same Gaussian)."""
+    import torchvision.transforms.functional as TF
+    from PIL import Image, ImageFilter
+    g = torch.Generator().manual_seed(5)
+    base = torch.rand(3, 3, 25, 33, generator=g)
+    x = (torch.nn.functional.interpolate(base, size=(97, 131), mode="bilinear") * 255).to(torch.uint8)     # smooth image
+    x[1] = torch.randint(0, 256, (3, 97, 131), dtype=torch.uint8, generator=g)                              # white noise image
+    sigmas = [0.1, 0.77, 2.0]
+    got = ops.gaussian_blur(x.to(cuda_device), sigmas).cpu()
+    for n, s in enumerate(sigmas):
+        ks = 2 * max(1, int(np.ceil(3 * s))) + 1
+        want = TF.gaussian_blur(x[n], [ks, ks], [s, s])
+        diff = (got[n].int() - want.int()).abs()
+        assert diff.max() <= 1 and (diff > 0).float().mean() <= 5e-3, (s, int(diff.max()), float((diff > 0).float().mean()))
+    pil = Image.fromarray(x[0].permute(1, 2, 0).numpy(), "RGB").filter(ImageFilter.GaussianBlur(radius=2.0))
+    pil = torch.from_numpy(np.array(pil)).permute(2, 0, 1)
+    got2 = ops.gaussian_blur(x[:1].to(cuda_device), [2.0]).cpu()[0]
+    inner = (slice(None), slice(8, -8), slice(8, -8))
+    assert (got2[inner].float() - pil[inner].float()).abs().mean() <= 1.5
+    # RandomApply miss: untouched
+    same = ops.gaussian_blur(x.to(cuda_device), [None, 1.0, None]).cpu()
+    assert torch.equal(same[0], x[0]) and torch.equal(same[2], x[2]) and not torch.equal(same[1], x[1])
+
+
+def test_random_erase_equals_totensor_erase_topil(ops, cuda_device):
+    """3 x RandomErasing(value="random") between ToTensor and ToPILImage (reference daod/data/detection_utils.py:18-33) with the
+    SAME noise: bit-exact, including the wrap-around of byte(255 * v) for v outside [0, 1] and overlapping rectangles; with the
+    device generator: pixels outside the rectangles untouched, the fill looks like wrapped N(0, 255^2) noise."""
+    import torchvision.transforms.functional as TF
+    x = _aug_images(2, 80, 120, 9)
+    rects = [[(5, 7, 30, 40), (20, 30, 25, 50), (0, 0, 3, 3)], [(10, 10, 60, 100)]]
+    g = torch.Generator().manual_seed(11)
+    noise = torch.randn(2, 4, 3, 80, 120, generator=g)
+    got = ops.random_erase_(x.clone().to(cuda_device), rects, noise=noise.to(cuda_device)).cpu()
+    for n in range(2):
+        t = x[n].to(torch.float32).div(255)                        # ToTensor
+        for k, (i, j, h, w) in enumerate(rects[n]):
+            t = TF.erase(t, i, j, h, w, noise[n, k, :, i:i + h, j:j + w])
+        want = t.mul(255).byte()                                   # ToPILImage
+        assert torch.equal(got[n], want), int((got[n] != want).sum())
+    dev = ops.random_erase_(x.clone().to(cuda_device), rects, seed=1234).cpu()
+    mask = torch.zeros(2, 80, 120, dtype=torch.bool)
+    for n in range(2):
+        for (i, j, h, w) in rects[n]:
+            mask[n, i:i + h, j:j + w] = True
+    m3 = mask.unsqueeze(1).expand(-1, 3, -1, -1)
+    assert torch.equal(dev[~m3], x[~m3])
+    fill = dev[m3].float()
+    assert abs(fill.mean().item() - 127.5) < 4 and 65 < fill.std().item() < 82             # ~uniform bytes
+    again = ops.random_erase_(x.clone().to(cuda_device), rects, seed=1234).cpu()
+    assert torch.equal(again, dev)                                                           # counter-based: reproducible
+
+
+def test_strong_augment_pipeline(cuda_device):
+    from sfod_b200 import engine
+    x = _aug_images(6, 120, 200, 13).to(cuda_device)
+    g = torch.Generator().manual_seed(99)
+    params = engine.draw_strong_augmentation_params(6, 120, 200, g)
+    y = engine.strong_augment(x, params=params, seed=5)
+    assert y.shape == x.shape and y.dtype == torch.uint8 and y.data_ptr() != x.data_ptr()
+    y2 = engine.strong_augment(x, params=params, seed=5)
+    assert torch.equal(y, y2)
+    for n, p in enumerate(params):
+        if not p["order"] and not p["grayscale"] and p["sigma"] is None and not p["rects"]:
+            assert torch.equal(y[n], x[n])

@@ -560,3 +560,130 @@ def test_cuda_graph_teacher_step_equals_eager(cfg, cuda_device):
         assert sum(len(p) for p in dets) > 0
     for (k, a), b in zip(teacher.state_dict().items(), t2.state_dict().values()):
         assert torch.equal(a, b), k
+
+
+def test_pseudo_label_export_round_trip_from_fused_batch(cfg, cuda_device, tmp_path):
+    """SURVEY.md 8f rank 4 on the GPU path: a REAL fused DetectionBatch (AdaBN-stage inference of the teacher) -> COCO result json
+    with one D2H copy (batch_to_coco_json == per-image instances_to_coco_json of reference sim_cocoevaluator.py:65-123) ->
+    prediction_to_gt (reference cityscapes-to-coco-conversion/prediction_to_gt.py:21-45, score >= 0.7) -> json on disk -> loaded
+    back as the annotations of the fixed-pseudo-label stage (reference daod/data/datasets.py:46-63) -> a student training step
+    on those targets through the plugins."""
+    import json
+    from sfod_b200.utils.events import EventStorage
+    torch.manual_seed(31)
+    model = registry.build_model(cfg)
+    with torch.no_grad():
+        model.roi_heads.box_predictor.cls_score.weight.mul_(400.0); model.roi_heads.box_predictor.bbox_pred.weight.mul_(300.0)
+    model.eval()                                                   # the export stage runs plain inference
+    imgs = torch.randint(0, 256, (2, 3, 320, 480), dtype=torch.uint8, generator=torch.Generator().manual_seed(32))
+    with torch.no_grad():
+        res = model(imgs.to(cuda_device))
+    insts = [r["instances"] for r in res]
+    batch = insts[0]._sfod_batch
+    image_ids = [101, 202]
+    id_map = {i: 24 + i for i in range(8)}                          # contiguous class -> Cityscapes category id
+    fused = engine.batch_to_coco_json(batch, image_ids, id_map)
+    per_image = [r for inst, i in zip(insts, image_ids) for r in engine.instances_to_coco_json(inst.to("cpu") if hasattr(inst, "to") else inst, i, id_map)]
+    assert len(fused) == len(per_image) == sum(len(i) for i in insts) > 0
+    for a, b in zip(fused, per_image):
+        assert a["image_id"] == b["image_id"] and a["category_id"] == b["category_id"]
+        assert a["bbox"] == pytest.approx(b["bbox"]) and a["score"] == pytest.approx(b["score"])
+    dataset = {"images": [{"id": 101, "height": 320, "width": 480}, {"id": 202, "height": 320, "width": 480}],
+               "categories": [{"id": 24 + i, "name": f"c{i}"} for i in range(8)], "annotations": []}
+    gt = engine.prediction_to_gt(fused, dataset, 0.7)
+    n_conf = sum(1 for r in fused if r["score"] >= 0.7)
+    assert len(gt["annotations"]) == n_conf > 0 and [a["id"] for a in gt["annotations"]] == list(range(1, n_conf + 1))
+    path = tmp_path / "instancesonly_filtered_gtFine_train_foggy_beta_0.02.json"
+    path.write_text(json.dumps(gt, indent=4))
+    loaded = engine.load_pseudo_label_annotations(json.loads(path.read_text()), device=cuda_device)
+    assert set(loaded) == {101, 202}
+    for inst, i in zip(insts, image_ids):
+        bx = inst.pred_boxes.tensor
+        keep = (inst.scores >= 0.7) & ((bx[:, 2] - bx[:, 0]) > 1e-5) & ((bx[:, 3] - bx[:, 1]) > 1e-5)   # filter_empty_instances
+        t = loaded[i]
+        assert len(t) == int(keep.sum())
+        assert torch.allclose(t.gt_boxes.tensor, inst.pred_boxes.tensor[keep], rtol=1e-6, atol=1e-3)   # XYXY -> XYWH -> json -> XYXY
+        assert torch.equal(t.gt_classes, inst.pred_classes[keep])
+    # ... and the fixed-pseudo-label stage trains on them
+    student = registry.build_model(cfg); student.train()
+    batched = [{"image": imgs[k].float(), "instances": loaded[i]} for k, i in enumerate(image_ids)]
+    with EventStorage():
+        losses, _, _, _ = student(batched, branch="supervised_target")
+        sum(losses.values()).backward()
+    assert all(torch.isfinite(v) for v in losses.values())
+
+
+def test_label_and_sample_batched_equals_oracle_with_kernel_permutation(cfg, cuda_device):
+    """SURVEY.md 8f rank 1, sampling half: ``label_and_sample_proposals`` (reference ...roi_heads.py:165-215) and
+    ``label_and_sample_anchors`` (d2, called at reference rpn.py:45) on the batched device path -- fused matcher, ONE sampler launch
+    for all images, one host read of the counts -- against the oracle's per-image detectron2 restatement fed the permutation the
+    kernel's counter-based keys define: sampled proposals, classes, matched gt boxes and anchor labels are identical."""
+    import numpy as np
+    import warnings
+    from sfod_b200 import ops
+    from sfod_b200.utils.events import EventStorage
+    torch.manual_seed(41)
+    model = registry.build_model(cfg); model.train()
+    heads, rpn = model.roi_heads, model.proposal_generator
+    g = torch.Generator().manual_seed(42)
+    N = 3
+    props, tgts, oprops, otgts = [], [], [], []
+    for i in range(N):
+        b = synth.random_rois(1, 1500 + 100 * i, 50 + i)[:, 1:].contiguous()
+        lg = torch.randn(len(b), generator=g)
+        gt = synth.random_rois(1, [5, 0, 9][i], 60 + i)[:, 1:].contiguous()
+        gc = torch.randint(0, 8, (len(gt),), generator=g)
+        p = Instances((600, 1200)); p.proposal_boxes = Boxes(b.to(cuda_device)); p.objectness_logits = lg.to(cuda_device)
+        t = Instances((600, 1200)); t.gt_boxes = Boxes(gt.to(cuda_device)); t.gt_classes = gc.to(cuda_device)
+        props.append(p); tgts.append(t)
+        oprops.append(dict(proposal_boxes=b, objectness_logits=lg, image_size=(600, 1200))); otgts.append(dict(gt_boxes=gt, gt_classes=gc))
+    seed = 0xABCDEF
+    heads._sampling_seed = lambda: seed
+    with EventStorage() as st, warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        torch.cuda.set_sync_debug_mode("warn")
+        try:
+            got = heads.label_and_sample_proposals(props, tgts, branch="b")
+        finally:
+            torch.cuda.set_sync_debug_mode("default")
+    syncs = [x for x in w if "synchroniz" in str(x.message).lower()]
+    assert len(syncs) <= 1, [str(x.message)[:100] for x in syncs]          # the one read of the (num_fg, num_bg) counts
+    state = {"img": 0, "call": 0}
+
+    def randperm_for(labels_of_image, bg):
+        def randperm(n, device=None):
+            lab = labels_of_image[state["img"]]
+            cand = ((lab != -1) & (lab != bg)).nonzero().flatten() if state["call"] == 0 else (lab == bg).nonzero().flatten()
+            assert cand.numel() == n
+            h = ops.sample_hash(seed, state["img"], cand.numpy())
+            state["call"] += 1
+            if state["call"] == 2:
+                state["call"] = 0; state["img"] += 1
+            return torch.from_numpy(np.lexsort((cand.numpy(), h)).astype(np.int64))
+        return randperm
+    # the labels the sampler saw, recomputed by the oracle (matcher on proposals + appended gt)
+    cls_per_image = []
+    for p, t in zip(oprops, otgts):
+        boxes = torch.cat([p["proposal_boxes"], t["gt_boxes"]])
+        idx, lab = o.matcher(o.pairwise_iou(t["gt_boxes"], boxes), [0.5], [0, 1], False)
+        if t["gt_classes"].numel():
+            c = t["gt_classes"][idx].clone(); c[lab == 0] = 8; c[lab == -1] = -1
+        else:
+            c = torch.zeros_like(idx) + 8
+        cls_per_image.append(c)
+    want = o.label_and_sample_proposals(oprops, otgts, 8, heads.batch_size_per_image, heads.positive_fraction, True,
+                                        randperm=randperm_for(cls_per_image, 8))
+    for a, b in zip(got, want):
+        assert torch.equal(a.proposal_boxes.tensor.cpu(), b["proposal_boxes"]) and torch.equal(a.gt_classes.cpu(), b["gt_classes"])
+        assert torch.equal(a.gt_boxes.tensor.cpu(), b["gt_boxes"])
+    assert st.latest()["roi_head/num_target_fg_samples_b"] == np.mean([int((b["gt_classes"] != 8).sum()) for b in want])
+    # RPN anchors
+    anchors = o.grid_anchors((18, 37), 32, o.generate_cell_anchors())
+    rpn._sampling_seed = lambda: seed
+    labels, boxes = rpn.label_and_sample_anchors([Boxes(anchors.to(cuda_device))], tgts)
+    raw = [o.matcher(o.pairwise_iou(t["gt_boxes"], anchors), [0.3, 0.7], [0, -1, 1], True)[1].to(torch.int64) for t in otgts]
+    state.update(img=0, call=0)
+    want_l, want_b = o.rpn_label_and_sample_anchors(anchors, [t["gt_boxes"] for t in otgts], rpn.batch_size_per_image, rpn.positive_fraction,
+                                                    randperm=randperm_for(raw, 0))
+    for a, b, c, d in zip(labels, want_l, boxes, want_b):
+        assert torch.equal(a.cpu().to(torch.int64), b.to(torch.int64)) and torch.equal(c.cpu(), d)

@@ -284,3 +284,24 @@ def test_resnet101_c4_backbone_layout_and_cpu_forward_matches_oracle():
     sdk = model.state_dict().keys()
     assert "backbone.res4.22.conv3.norm.running_mean" in sdk and "roi_heads.box_head.fc1.weight" in sdk
     assert model.roi_heads.box_head.fc1.weight.shape == (2048, 1024 * 7 * 7) and model.proposal_generator.anchor_generator.num_anchors[0] == 12
+
+
+def test_strong_augmentation_parameter_draws_follow_the_reference_distributions():
+    """Host half of SURVEY.md 8f rank 3: decisions drawn as reference daod/data/detection_utils.py:7-37 specifies
+    (RandomApply 0.8 / RandomGrayscale 0.2 / blur 0.5 / erasers 0.7, 0.5, 0.3; factor and rectangle ranges)."""
+    import torch
+    from sfod_b200 import engine
+    g = torch.Generator().manual_seed(1)
+    ps = engine.draw_strong_augmentation_params(4000, 600, 1200, g)
+    frac = lambda f: sum(1 for p in ps if f(p)) / len(ps)  # noqa: E731
+    assert abs(frac(lambda p: bool(p["order"])) - 0.8) < 0.03 and abs(frac(lambda p: p["grayscale"]) - 0.2) < 0.03
+    assert abs(frac(lambda p: p["sigma"] is not None) - 0.5) < 0.03
+    assert abs(sum(len(p["rects"]) for p in ps) / len(ps) - (0.7 + 0.5 + 0.3)) < 0.06
+    for p in ps:
+        assert sorted(p["order"]) in ([], [0, 1, 2, 3])
+        for o, f in zip(p["order"], p["factors"]):
+            lo, hi = [(0.6, 1.4), (0.6, 1.4), (0.6, 1.4), (-0.1, 0.1)][o]
+            assert lo <= f <= hi
+        assert p["sigma"] is None or 0.1 <= p["sigma"] <= 2.0
+        for (i, j, h, w) in p["rects"]:
+            assert 0 <= i and i + h <= 600 and 0 <= j and j + w <= 1200 and 0.015 * 720000 <= h * w <= 0.21 * 720000
