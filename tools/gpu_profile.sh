@@ -2,7 +2,7 @@
 # ncu --set full captures of the hot-path kernels inside one bench step (1 GPU only), exported to CSV on the box so that
 # gpurun_out stays small.  Usage: bash tools/gpu_profile.sh <tag>
 set -u
-TAG=${1:-r1}
+TAG=${1:-r2}
 mkdir -p gpurun_out
 cap() {  # name, kernel regex, launch count
   timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$2" -c $3 \
@@ -15,5 +15,5 @@ cap() {  # name, kernel regex, launch count
   if [ "$sz" -gt 6000000 ]; then rm -f gpurun_out/prof_${TAG}_$1.ncu-rep; fi
 }
 cap det 'roi_align|roi_sep|ema_multi|nms_|bitonic|rpn_|frcnn_|transpose' 41
-cap bn 'bn_apply|bn_stats|bn_finalize' 39
+cap bn 'bn_apply|bn_stats|bn_finalize|bn_fused|bn_frozen' 39
 du -sh gpurun_out
