@@ -249,7 +249,8 @@ int sfod_iou_match(const float *gt_boxes, const float *boxes, int M, int N, cons
                    void *workspace, size_t workspace_bytes, sfod_stream_t stream);
 
 /* Batched detectron2 `subsample_labels`: for each of `num_segments` label segments
- * labels[offsets[s] .. offsets[s+1]) (int64; -1 = ignore, bg_label = negative, anything else positive) select
+ * labels[offsets[s] .. offsets[s+1]) (labels: int64 on the device; offsets: num_segments + 1 ints in HOST memory, passed to the
+ * kernel by value; -1 = ignore, bg_label = negative, anything else positive) select
  * num_pos = min(#positive, max_positive) positives and num_neg = min(#negative, num_samples - num_pos) negatives uniformly at
  * random, as the per-image calls of ROIHeads._sample_proposals (reference
  * daod/modeling/roi_heads/source_free_adaptive_teacher_roi_heads.py:177-186) and RPN.label_and_sample_anchors (called at

@@ -470,9 +470,17 @@ SFOD_API int sfod_subsample_labels(const int64_t *labels, const int32_t *offsets
   if (2 * num_samples > samplek::kMaxSamples) return SFOD_ERR_UNSUPPORTED;
   if (num_segments == 0) return SFOD_OK;
   if (!labels || !offsets || !sampled || !counts) return SFOD_ERR_INVALID_ARG;
-  samplek::subsample_kernel<<<num_segments, samplek::kThreads, 0, sfod_cu(stream)>>>(
-      reinterpret_cast<const long long *>(labels), offsets, num_samples, max_positive, (long long)bg_label,
-      (unsigned long long)seed, reinterpret_cast<long long *>(sampled), counts);
-  SFOD_LAUNCH_CHECK();
+  // `offsets` is a HOST array: it travels in the kernel parameters, <= 255 segments per launch (the hash key uses the
+  // segment index within the call, so a split call keeps keys distinct through the seed)
+  for (int s0 = 0; s0 < num_segments; s0 += samplek::kMaxSegments) {
+    const int ns = num_segments - s0 < samplek::kMaxSegments ? num_segments - s0 : samplek::kMaxSegments;
+    samplek::Offsets off;
+    for (int i = 0; i <= ns; ++i) off.v[i] = offsets[s0 + i];
+    samplek::subsample_kernel<<<ns, samplek::kThreads, 0, sfod_cu(stream)>>>(
+        reinterpret_cast<const long long *>(labels), off, num_samples, max_positive, (long long)bg_label,
+        (unsigned long long)seed + 0x632BE59BD9B4E019ull * (unsigned long long)(s0 / samplek::kMaxSegments),
+        reinterpret_cast<long long *>(sampled) + (size_t)s0 * num_samples, counts + 2 * (size_t)s0);
+    SFOD_LAUNCH_CHECK();
+  }
   return SFOD_OK;
 }

@@ -20,6 +20,8 @@ namespace samplek {
 
 constexpr int kThreads = 1024;
 constexpr int kMaxSamples = 1024;
+constexpr int kMaxSegments = 255;     // segment offsets travel in the kernel parameters (host array in, no device copy, no sync)
+struct Offsets { int v[kMaxSegments + 1]; };
 
 __host__ __device__ __forceinline__ unsigned int sample_hash(unsigned long long seed, unsigned int seg, unsigned int idx) {
   unsigned long long x = seed + 0x9E3779B97F4A7C15ull * ((((unsigned long long)seg) << 32) | idx);
@@ -32,7 +34,7 @@ __host__ __device__ __forceinline__ unsigned int sample_hash(unsigned long long 
 // class of a label: 0 = positive (foreground), 1 = negative (== bg_label), 2 = ignored (-1)
 __device__ __forceinline__ int label_class(long long l, long long bg) { return l == bg ? 1 : (l == -1 ? 2 : 0); }
 
-__global__ void __launch_bounds__(kThreads) subsample_kernel(const long long *__restrict__ labels, const int *__restrict__ offsets,
+__global__ void __launch_bounds__(kThreads) subsample_kernel(const long long *__restrict__ labels, const Offsets offsets,
                                                              int num_samples, int max_pos, long long bg_label,
                                                              unsigned long long seed, long long *__restrict__ sampled,
                                                              int *__restrict__ counts) {
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(kThreads) subsample_kernel(const long long *__
   __shared__ unsigned int eq_idx[64];                  // indices whose hash equals the threshold hash (ties; practically <= 1)
   __shared__ int s_eq;
   const int seg = blockIdx.x, tid = threadIdx.x;
-  const int beg = offsets[seg], n = offsets[seg + 1] - beg;
+  const int beg = offsets.v[seg], n = offsets.v[seg + 1] - beg;
   const long long *lab = labels + beg;
   if (tid < 2) s_cnt[tid] = 0;
   __syncthreads();

@@ -456,7 +456,8 @@ def subsample_labels_batched(labels: Tensor, lengths: Sequence[int], num_samples
         return sampled, counts
     max_pos = int(num_samples * positive_fraction)
     with torch.cuda.device(dev), _timed("subsample_labels"):
-        check(_lib.lib().sfod_subsample_labels(lab.data_ptr(), _small_i32(dev, offs).data_ptr(), S, int(num_samples), max_pos, int(bg_label),
+        offs_host = (C.c_int32 * len(offs))(*offs)      # host array: passed to the kernel by value (no H2D copy, no sync)
+        check(_lib.lib().sfod_subsample_labels(lab.data_ptr(), offs_host, S, int(num_samples), max_pos, int(bg_label),
                                                int(seed) & _MASK64, sampled.data_ptr(), counts.data_ptr(), _stream(dev)),
               "sfod_subsample_labels")
     return sampled, counts
