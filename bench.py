@@ -189,7 +189,7 @@ def run_reference(args):
             "warmup": w_done, "ms_per_step": round(1e3 * dt / k_run, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "images_per_gpu": args.batch, "images_per_step": args.batch,
-                       "image_hw": list(IMAGE_HW), "num_classes": NUM_CLASSES,
+                       "global_batch": args.batch, "image_hw": list(IMAGE_HW), "num_classes": NUM_CLASSES,
                        "note": "CPU arm runs on rank 0 only, all host cores; same batch per step as the GPU arm, bounded number of steps"},
             "cpu_baseline": info,
             "e2e": {"value": info["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

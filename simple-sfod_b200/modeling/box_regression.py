@@ -40,5 +40,31 @@ class Box2BoxTransform:
         return deltas
 
     def apply_deltas(self, deltas: Tensor, boxes: Tensor) -> Tensor:
-        """deltas (N, k*4), boxes (N, 4) -> (N, k*4); fp32, dw/dh clamped to ``scale_clamp``."""
+        """deltas (N, k*4), boxes (N, 4) -> (N, k*4); fp32, dw/dh clamped to ``scale_clamp``.
+        Pseudo-labelling (no autograd) runs the native decode.  When a gradient is asked for (detectron2's decode is
+        differentiable: giou / diou box losses, the reference's ``bpc_loss`` on ``convert_bbox_scores`` outputs) the same formula
+        runs as torch ops -- the kernel has no backward, and silently returning a non-differentiable result would be wrong."""
+        if torch.is_grad_enabled() and (deltas.requires_grad or boxes.requires_grad):
+            return self._apply_deltas_torch(deltas, boxes)
         return ops.apply_deltas(deltas.float(), boxes.to(torch.float32), self.weights, self.scale_clamp)
+
+    def _apply_deltas_torch(self, deltas: Tensor, boxes: Tensor) -> Tensor:
+        """detectron2 Box2BoxTransform.apply_deltas, operation by operation."""
+        deltas = deltas.float()
+        boxes = boxes.to(deltas.dtype)
+        widths = boxes[:, 2] - boxes[:, 0]
+        heights = boxes[:, 3] - boxes[:, 1]
+        ctr_x = boxes[:, 0] + 0.5 * widths
+        ctr_y = boxes[:, 1] + 0.5 * heights
+        wx, wy, ww, wh = self.weights
+        dx = deltas[:, 0::4] / wx
+        dy = deltas[:, 1::4] / wy
+        dw = torch.clamp(deltas[:, 2::4] / ww, max=self.scale_clamp)
+        dh = torch.clamp(deltas[:, 3::4] / wh, max=self.scale_clamp)
+        pred_ctr_x = dx * widths[:, None] + ctr_x[:, None]
+        pred_ctr_y = dy * heights[:, None] + ctr_y[:, None]
+        pred_w = torch.exp(dw) * widths[:, None]
+        pred_h = torch.exp(dh) * heights[:, None]
+        x1, y1 = pred_ctr_x - 0.5 * pred_w, pred_ctr_y - 0.5 * pred_h
+        x2, y2 = pred_ctr_x + 0.5 * pred_w, pred_ctr_y + 0.5 * pred_h
+        return torch.stack((x1, y1, x2, y2), dim=-1).reshape(deltas.shape)

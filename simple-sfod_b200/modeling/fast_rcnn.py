@@ -227,6 +227,8 @@ class FastRCNNOutputLayers(nn.Module):
     def predict_probs(self, predictions: Tuple[Tensor, Tensor], proposals: List[Instances]) -> Tuple[Tensor, ...]:
         scores, _ = predictions
         num_inst_per_image = [len(p) for p in proposals]
+        if torch.is_grad_enabled() and scores.requires_grad:   # differentiable in detectron2; the kernel has no backward
+            return torch.softmax(scores, dim=-1).split(num_inst_per_image, dim=0)
         return ops.softmax_lastdim(scores).split(num_inst_per_image, dim=0)
 
     @torch.no_grad()

@@ -305,3 +305,19 @@ def test_strong_augmentation_parameter_draws_follow_the_reference_distributions(
         assert p["sigma"] is None or 0.1 <= p["sigma"] <= 2.0
         for (i, j, h, w) in p["rects"]:
             assert 0 <= i and i + h <= 600 and 0 <= j and j + w <= 1200 and 0.015 * 720000 <= h * w <= 0.21 * 720000
+
+
+def test_box_decode_and_probs_are_differentiable_when_a_gradient_is_requested():
+    """detectron2's predict_boxes / predict_probs are differentiable (giou/diou losses, bpc_loss on convert_bbox_scores
+    outputs); with autograd on, the mirror runs the same formula as torch ops instead of the (backward-less) kernels."""
+    import torch
+    from oracle import d2_cpu as o
+    from sfod_b200.modeling import Box2BoxTransform
+    g = torch.Generator().manual_seed(0)
+    boxes = torch.rand(20, 4, generator=g) * 100; boxes[:, 2:] += boxes[:, :2] + 1
+    deltas = (torch.randn(20, 32, generator=g) * 0.5).requires_grad_(True)
+    t = Box2BoxTransform(weights=(10.0, 10.0, 5.0, 5.0))
+    out = t.apply_deltas(deltas, boxes)
+    assert out.requires_grad and torch.equal(out.detach(), o.apply_deltas(deltas.detach(), boxes, (10.0, 10.0, 5.0, 5.0)))
+    out.sum().backward()
+    assert deltas.grad is not None and torch.isfinite(deltas.grad).all() and deltas.grad.abs().sum() > 0
