@@ -371,17 +371,26 @@ def run_b200(args):
     host_batches = [synth_images(B, 1234 + rank * 1000 + i).pin_memory() for i in range(n_rot)]
     dev_batches = [h.to(dev) for h in host_batches]
 
-    def pseudo_label(images_dev):
+    # The teacher forward hands out lazy results (no host read inside the forward), so the EMA launch is enqueued BEHIND the
+    # forward's kernels and the step's single device->host read (the counts) comes after every launch of the step.
+    teacher.roi_heads.box_predictor.defer_host_read = True
+
+    def teacher_forward(images_dev):
         with torch.no_grad():
             _, proposals_rpn, proposals_roih = teacher(images_dev.to(memory_format=torch.channels_last) if args.channels_last else images_dev,
                                                        branch="unsup_data_weak")
+        return proposals_rpn, proposals_roih
+
+    def pseudo_label(images_dev):
+        proposals_rpn, proposals_roih = teacher_forward(images_dev)
         pl, _ = engine.process_pseudo_label(proposals_roih, thr, "roih", "thresholding")
         return proposals_rpn, proposals_roih, pl
 
     def step_resident(i):
-        out = pseudo_label(dev_batches[i % n_rot])
+        proposals_rpn, proposals_roih = teacher_forward(dev_batches[i % n_rot])
         ema.step(cfg.SEMISUPNET.EMA_KEEP_RATE)
-        return out
+        pl, _ = engine.process_pseudo_label(proposals_roih, thr, "roih", "thresholding")     # the one host read of the step
+        return proposals_rpn, proposals_roih, pl
 
     # pinned result buffers of the end-to-end arm (what a trainer reads back: the pseudo-labels of every image)
     T = cfg.TEST.DETECTIONS_PER_IMAGE
@@ -392,14 +401,15 @@ def run_b200(args):
 
     def step_e2e(i):
         imgs = host_batches[i % n_rot].to(dev, non_blocking=True)
-        _, dets, pl = pseudo_label(imgs)
+        rpn, dets = teacher_forward(imgs)
         batch = dets[0]._sfod_batch
         res_host["boxes"].copy_(batch.boxes, non_blocking=True)
         res_host["scores"].copy_(batch.scores, non_blocking=True)
         res_host["classes"].copy_(batch.classes, non_blocking=True)
         ema.step(cfg.SEMISUPNET.EMA_KEEP_RATE)
+        pl, _ = engine.process_pseudo_label(dets, thr, "roih", "thresholding")               # reads the counts: the step's host sync
         torch.cuda.current_stream().synchronize()
-        return _, dets, pl
+        return rpn, dets, pl
 
     def barrier():
         if world > 1:
@@ -559,7 +569,7 @@ def run_b200(args):
         "bn_finalize_apply": 8.0 * (bn_elems - bn_elems_pool - bn_elems_res),  # read x + write y (normalise + ReLU, in place)
         "bn_finalize_apply_pool": 5.0 * bn_elems_pool,                        # read x + write the 2x2-pooled y (1/4 of the elements)
         "bn_finalize_apply_res": 12.0 * bn_elems_res,                         # read x + read shortcut + write y
-        "bn_frozen_apply": 8.0 * bn_elems_frozen,                             # (residual variants read 4 B/element more; lower bound)
+        "bn_frozen_apply": 8.0 * bn_elems_frozen + (4.0 * 3 * 256 * 150 * 300 * B if args.workload == "r101" else 0.0),   # + shortcut reads of res2's conv3
         "bn_partial_stats": 4.0 * bn_elems,                                   # read x
         "bn_train_fused": None, "bn_train_fused_res": None,                   # single-launch L2-resident BN: filled in below
         "ema_multi_tensor": 12.0 * ema.numel,                                 # read student, read teacher, write teacher
