@@ -243,24 +243,24 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // ---- per-ROI table records (forward).  A small pre-kernel builds, for every ROI, the record the forward kernel needs:
 //   ints  [0..31]  lim: [0..1] ymin, ymax; [2..3] xmin, xmax; [4..10] / [11..17] first / last row of bin ph;
 //                       [18..24] first column of the compact window of bin pw; [25] window width of the ROI: 2, 3, 4, 6, 8
-//                       (kNXMax + 1 = use the dense column tables); [26] image index (-1: invalid -> zero output)
+//                       (kNXMax + 1 = use the dense column tables); [26] image index (-1: invalid -> zero output); [27] ROI index
 //   floats [32..87] Bc[pw*kNXMax + j]: weight of column lim[18+pw] + j for bin pw (the nonzero run of B's row pw)
 //   floats [96..96+8H) Ad[y*8 + ph], ph < 7; word y*8 + 7 holds (first bin fed by row y) | (number of such bins << 8)
 // so that the persistent forward CTAs prefetch it with cp.async while they work on the previous ROI instead of spending
 // ~20 % of their life in a latency-bound prologue (ROI load from DRAM, table build by 14 threads, two barriers).
 constexpr int kNXMax = 8;                  // widest per-bin column window handled by the compact (sparse-in-x) forward
+constexpr int kCostClasses = 16;           // ROI cost classes of the L2 forward's longest-processing-time-first order
 constexpr int kRecHead = 96;               // 32 ints + 7 x 8 compact weights, padded
 __host__ __device__ inline int sep_rec_floats(int H) { return kRecHead + 8 * H; }
 
 __global__ void __launch_bounds__(128) roi_sep_tables_kernel(const float *__restrict__ rois, int R, int N, int H, int W, float scale,
                                                              int sampling_ratio, int aligned, float *__restrict__ recs,
-                                                             unsigned *__restrict__ counter) {
+                                                             int *__restrict__ bcnt, int *__restrict__ bucket) {
   extern __shared__ __align__(16) float tb_smem[];
   const int rec = sep_rec_floats(H);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + warp;
   pdl_launch_dependents();   // the forward kernel may start its prologue; it waits (griddepcontrol.wait) before touching recs
-  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;   // work counter of the forward kernel that follows in stream order
   if (r >= R) return;
   float *my = tb_smem + (size_t)warp * rec;
   int *lim = reinterpret_cast<int *>(my);
@@ -310,7 +310,14 @@ __global__ void __launch_bounds__(128) roi_sep_tables_kernel(const float *__rest
   }
   ymn = __reduce_min_sync(0xFFFFFFFFu, ymn); ymx = __reduce_max_sync(0xFFFFFFFFu, ymx);
   xmn = __reduce_min_sync(0xFFFFFFFFu, xmn); xmx = __reduce_max_sync(0xFFFFFFFFu, xmx);
-  if (lane == 0) { lim[0] = ymn; lim[1] = ymx; lim[2] = xmn; lim[3] = xmx; lim[25] = nx; lim[26] = valid ? g.n : -1; }
+  if (lane == 0) {
+    lim[0] = ymn; lim[1] = ymx; lim[2] = xmn; lim[3] = xmx; lim[25] = nx; lim[26] = valid ? g.n : -1; lim[27] = r;
+    if (bucket) {   // cost class = log2 of the window area: the L2 forward pulls the most expensive ROIs first (LPT order)
+      const int area = (ymx >= ymn && xmx >= xmn) ? (ymx - ymn + 1) * (xmx - xmn + 1) : 0;
+      const int cls = area > 0 ? min(kCostClasses - 1, 32 - __clz(area)) : 0;
+      bucket[(size_t)cls * R + atomicAdd(&bcnt[cls], 1)] = r;
+    }
+  }
   __syncwarp();
   for (int y = lane; y < H; y += 32) {   // bins fed by row y form a run [first, first + count): packed into the row's padding word
     int first = kPH, last = -1;
@@ -523,7 +530,8 @@ template <int kC>
 __global__ void __launch_bounds__(kSepThreads, 3) roi_align_fwd_sep_kernel(const float *__restrict__ feat /* NHWC */,
                                                                            const float *__restrict__ rois,
                                                                            const float *__restrict__ recs,
-                                                                           unsigned *__restrict__ counter, int N, int C, int H,
+                                                                           unsigned *__restrict__ counter, const int *__restrict__ bcnt,
+                                                                           const int *__restrict__ bucket, int N, int C, int H,
                                                                            int W, int R, float scale, int sampling_ratio,
                                                                            int aligned, float *__restrict__ output) {
   extern __shared__ __align__(128) float sep_smem[];
@@ -537,8 +545,24 @@ __global__ void __launch_bounds__(kSepThreads, 3) roi_align_fwd_sep_kernel(const
   if (cur >= nitems) return;
   unsigned long long l2_stream;   // the output stream must not evict the feature map from L2
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_stream));
+  // Items are pulled in order of DECREASING ROI cost (window area classes filled by the table kernel): with a few hundred
+  // items per CTA and ROI costs spanning two orders of magnitude (2 x 2 ... 38 x 75 cells), arrival order leaves the tail of
+  // the launch to whichever CTA drew a map-sized ROI last.
+  __shared__ int s_pref[kCostClasses + 1];
+  if (tid == 0 && bucket) {
+    int acc = 0;
+    for (int k = 0; k < kCostClasses; ++k) { s_pref[k] = acc; acc += bcnt[kCostClasses - 1 - k]; }
+    s_pref[kCostClasses] = acc;
+  }
+  __syncthreads();
+  auto roi_of = [&](int i) -> int {   // i-th ROI in decreasing-cost order (arrival order when no cost classes were built)
+    if (!bucket) return i;
+    int k = 0;
+    while (k + 1 < kCostClasses && i >= s_pref[k + 1]) ++k;
+    return bucket[(size_t)(kCostClasses - 1 - k) * R + (i - s_pref[k])];
+  };
   auto fetch = [&](int item, int b) {
-    const float4 *src = reinterpret_cast<const float4 *>(recs + (size_t)(item / nslab) * rec);
+    const float4 *src = reinterpret_cast<const float4 *>(recs + (size_t)roi_of(item / nslab) * rec);
     const unsigned dst = (unsigned)__cvta_generic_to_shared(tab + b * rec);
     for (int i = tid; i < rec / 4; i += kSepThreads)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + i) : "memory");
@@ -557,10 +581,11 @@ __global__ void __launch_bounds__(kSepThreads, 3) roi_align_fwd_sep_kernel(const
     if (nxt < nitems) fetch(nxt, buf ^ 1);
     int after = 0;
     if (tid == 0) after = (int)(gridDim.x + atomicAdd(counter, 1u));
-    const int r = cur / nslab, cbase = (cur - r * nslab) * kCT;
+    const int cbase = (cur % nslab) * kCT;
     SepSmem s;
     s.tile = tile; s.lim = reinterpret_cast<int *>(tab + buf * rec); s.Bc = tab + buf * rec + 32; s.Ad = tab + buf * rec + kRecHead;
     s.Bd = Bd;
+    const int r = s.lim[27];   // the record carries its ROI index (items arrive in cost order, not in ROI order)
     const int n = s.lim[26];
     const bool empty = n < 0 || s.lim[1] < s.lim[0] || s.lim[3] < s.lim[2];
     const bool active = cbase + 2 * tid < C;
@@ -1049,7 +1074,8 @@ SFOD_API size_t sfod_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, i
   // kernel also needs one table record per ROI and its work counter
   const bool need = exact ? (layout == SFOD_NHWC) : (layout == SFOD_NCHW);
   size_t bytes = need ? sfod_align_up((size_t)N * C * H * W * sizeof(float), 256) : 0;
-  if (!exact) bytes += 256 + sfod_align_up((size_t)(R > 0 ? R : 0) * sep_rec_floats(H) * sizeof(float), 256);
+  if (!exact) bytes += 256 + sfod_align_up((size_t)(R > 0 ? R : 0) * sep_rec_floats(H) * sizeof(float), 256) +
+                       sfod_align_up((size_t)(R > 0 ? R : 0) * kCostClasses * sizeof(int), 256);
   return bytes ? bytes : 256;
 }
 
@@ -1075,10 +1101,13 @@ SFOD_API int sfod_roi_align_fwd(const float *input, int layout, const float *roi
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     const size_t rec_bytes = (size_t)sep_rec_floats(H) * sizeof(float);
     const size_t feat_ws = layout == SFOD_NCHW ? sfod_align_up(fbytes, 256) : 0;   // transposed copy (only some paths use it)
-    if (!workspace || workspace_bytes < feat_ws + 256 + (size_t)R * rec_bytes) return SFOD_ERR_WORKSPACE_TOO_SMALL;
+    const size_t rec_ws = sfod_align_up((size_t)R * rec_bytes, 256);
+    if (!workspace || workspace_bytes < feat_ws + 256 + rec_ws + (size_t)R * kCostClasses * sizeof(int)) return SFOD_ERR_WORKSPACE_TOO_SMALL;
     if (!sfod_aligned16(ws + feat_ws) || !sfod_aligned16(input)) return SFOD_ERR_ALIGNMENT;
-    unsigned *counter = reinterpret_cast<unsigned *>(ws + feat_ws);
+    unsigned *counter = reinterpret_cast<unsigned *>(ws + feat_ws);          // [0]: work counter; [16 .. 31]: cost-class counts
+    int *bcnt = reinterpret_cast<int *>(ws + feat_ws) + 16;
     float *recs = reinterpret_cast<float *>(ws + feat_ws + 256);
+    int *bucket = reinterpret_cast<int *>(ws + feat_ws + 256 + rec_ws);
     int sms = 0, cur_dev = 0, max_optin = 0;
     SFOD_CUDA_TRY(cudaGetDevice(&cur_dev));
     SFOD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev));
@@ -1096,7 +1125,15 @@ SFOD_API int sfod_roi_align_fwd(const float *input, int layout, const float *roi
       if (rc) return rc;
       feat = static_cast<const float *>(workspace);
     }
-    roi_sep_tables_kernel<<<(R + 3) / 4, 128, 4 * rec_bytes, st>>>(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, recs, counter);
+    const bool l2_path = !slab_warps;
+    // Cost-ordered items pay off when a CTA sees few of them (1 image: 18 items per CTA, 296 -> 211 us on R101-C4); with
+    // hundreds per CTA the tail is small and arrival (image-major) order keeps one image's map hot in L2 (8 images: 1 494 us in
+    // arrival order, 1 595 us in cost order).
+    const long long l2_items = (long long)R * ((C + kCT - 1) / kCT);
+    const bool lpt = l2_path && l2_items < 64LL * 3 * sms;
+    if (l2_path) SFOD_CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
+    if (!lpt) { bcnt = nullptr; bucket = nullptr; }
+    roi_sep_tables_kernel<<<(R + 3) / 4, 128, 4 * rec_bytes, st>>>(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, recs, bcnt, bucket);
     SFOD_LAUNCH_CHECK();
     if (slab_warps) {
       // launched with programmatic stream serialization: its prologue overlaps the table kernel (griddepcontrol.wait inside)
@@ -1127,7 +1164,7 @@ SFOD_API int sfod_roi_align_fwd(const float *input, int layout, const float *roi
       SFOD_CUDA_TRY(cudaFuncSetAttribute(roi_align_fwd_sep_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       const int grid = sep_fwd_grid(reinterpret_cast<const void *>(roi_align_fwd_sep_kernel<KC>), smem, items);             \
       if (grid < 1) return SFOD_ERR_UNSUPPORTED;                                                                                   \
-      roi_align_fwd_sep_kernel<KC><<<grid, kSepThreads, smem, st>>>(feat, rois, recs, counter, N, C, H, W, R, spatial_scale, \
+      roi_align_fwd_sep_kernel<KC><<<grid, kSepThreads, smem, st>>>(feat, rois, recs, counter, bcnt, bucket, N, C, H, W, R, spatial_scale, \
                                                                     sampling_ratio, aligned, output);                        \
     } while (0)
     switch (C) {
