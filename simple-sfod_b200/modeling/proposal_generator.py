@@ -227,8 +227,7 @@ class RPN(nn.Module):
         """Device-side result of ``predict_proposals`` without the host read of the counts:
         (boxes (N, P, 4), logits (N, P), src_index (N, P), count (N) int32, invalid (N) int32)."""
         if len(pred_objectness_logits) != 1:
-            raise NotImplementedError("multi-level RPN selection: every shipped config is single-level "
-                                      "(RPN.IN_FEATURES ['vgg4'] / ['res4'], SURVEY.md 8a-a3)")
+            return self._select_proposals_multilevel(pred_objectness_logits, pred_anchor_deltas, image_sizes, feat_hw, anchors)
         ag = self.anchor_generator
         kw = {}
         if feat_hw is not None and isinstance(ag, DefaultAnchorGenerator) and ag.num_anchors[0] <= 64:
@@ -240,6 +239,45 @@ class RPN(nn.Module):
                               weights=self.box2box_transform.weights, scale_clamp=self.box2box_transform.scale_clamp,
                               pre_nms_topk=self.pre_nms_topk[self.training], post_nms_topk=self.post_nms_topk[self.training],
                               nms_thresh=self.nms_thresh, min_box_size=self.min_box_size, **kw)
+
+    def _select_proposals_multilevel(self, pred_objectness_logits, pred_anchor_deltas, image_sizes, feat_hw, anchors):
+        """detectron2 ``find_top_rpn_proposals`` for several feature levels (FPN-style ``RPN.IN_FEATURES``; the reference registers
+        ``build_vgg_fpn_backbone``, daod/modeling/meta_arch/vgg.py:121-143, although no shipped YAML selects it).  Functional, not
+        fused: per level the single-level kernel chain decodes, filters and takes the level's top ``pre_nms_topk`` with suppression
+        switched off; the levels are then concatenated per image and go through ``batched_nms`` with the level as the category
+        (one host read of the per-level counts + one per image for the keep count, like torchvision's own GPU path)."""
+        ag = self.anchor_generator
+        N = pred_objectness_logits[0].shape[0]
+        pre, post = self.pre_nms_topk[self.training], self.post_nms_topk[self.training]
+        per_level = []
+        for l, (lg, dl) in enumerate(zip(pred_objectness_logits, pred_anchor_deltas)):
+            if feat_hw is not None and isinstance(ag, DefaultAnchorGenerator) and ag.num_anchors[l] <= 64:
+                kw = dict(cell_anchors=ag.host_cell_anchors[l], feat_hw=feat_hw[l], stride=ag.strides[l], anchor_offset=ag.offset)
+            else:
+                kw = dict(anchors=anchors[l].tensor)
+            k = min(int(lg.shape[1]), pre)
+            per_level.append(ops.rpn_select(lg, dl, image_sizes, weights=self.box2box_transform.weights,
+                                            scale_clamp=self.box2box_transform.scale_clamp, pre_nms_topk=pre, post_nms_topk=k,
+                                            nms_thresh=2.0, min_box_size=self.min_box_size, **kw))      # IoU never exceeds 2: keep all
+        counts = torch.stack([torch.stack([r[3], r[4]]) for r in per_level]).cpu().tolist()           # [level][count|invalid][image]
+        dev = pred_objectness_logits[0].device
+        out_b = torch.zeros((N, post, 4), dtype=torch.float32, device=dev)
+        out_l = torch.zeros((N, post), dtype=torch.float32, device=dev)
+        out_s = torch.full((N, post), -1, dtype=torch.int64, device=dev)
+        kept, invalid, base = [], [], [0]
+        for lg in pred_objectness_logits:
+            base.append(base[-1] + int(lg.shape[1]))
+        for n in range(N):
+            bx = torch.cat([r[0][n, :counts[l][0][n]] for l, r in enumerate(per_level)])
+            sc = torch.cat([r[1][n, :counts[l][0][n]] for l, r in enumerate(per_level)])
+            src = torch.cat([r[2][n, :counts[l][0][n]] + base[l] for l, r in enumerate(per_level)])
+            lvl = torch.cat([torch.full((counts[l][0][n],), l, dtype=torch.int64, device=dev) for l in range(len(per_level))])
+            keep = ops.batched_nms(bx, sc, lvl, self.nms_thresh)[:post]
+            k = int(keep.numel())
+            out_b[n, :k], out_l[n, :k], out_s[n, :k] = bx[keep], sc[keep], src[keep]
+            kept.append(k)
+            invalid.append(sum(int(counts[l][1][n]) for l in range(len(per_level))))
+        return out_b, out_l, out_s, torch.tensor(kept, dtype=torch.int32, device=dev), torch.tensor(invalid, dtype=torch.int32, device=dev)
 
     def _closed_form_anchors(self) -> bool:
         ag = self.anchor_generator

@@ -687,3 +687,33 @@ def test_label_and_sample_batched_equals_oracle_with_kernel_permutation(cfg, cud
                                                     randperm=randperm_for(raw, 0))
     for a, b, c, d in zip(labels, want_l, boxes, want_b):
         assert torch.equal(a.cpu().to(torch.int64), b.to(torch.int64)) and torch.equal(c.cpu(), d)
+
+
+def test_multilevel_rpn_selection_matches_oracle(cuda_device):
+    """detectron2 find_top_rpn_proposals over three feature levels (FPN-style RPN.IN_FEATURES; registered but unused by the shipped
+    YAMLs): per-level top-k, per-level NMS via batched_nms, top post_nms_topk across levels -- proposal indices (flat, level-
+    concatenated), boxes and logits equal to the oracle's restatement."""
+    from sfod_b200.modeling.anchor_generator import DefaultAnchorGenerator
+    from sfod_b200.modeling.box_regression import Box2BoxTransform
+    strides, hw = [8, 16, 32], [(40, 60), (20, 30), (10, 15)]
+    ag = DefaultAnchorGenerator(sizes=[[32], [64], [128]], aspect_ratios=[[0.5, 1.0, 2.0]], strides=strides, offset=0.0)
+    rpn = modeling.RPN(in_features=["p3", "p4", "p5"], head=torch.nn.Identity(), anchor_generator=ag,
+                       box2box_transform=Box2BoxTransform(weights=(1.0, 1.0, 1.0, 1.0)), pre_nms_topk=(2000, 1000), post_nms_topk=(1000, 300))
+    rpn.eval()
+    g = torch.Generator().manual_seed(77)
+    N = 2
+    sizes = [(320, 480), (300, 470)]
+    logits = [synth.tie_free(torch.randn(N, h * w * 3, generator=g)) for (h, w) in hw]
+    deltas = [torch.randn(N, h * w * 3, 4, generator=g) * 0.4 for (h, w) in hw]
+    anchors = [o.grid_anchors(s, st, o.generate_cell_anchors((sz,), (0.5, 1.0, 2.0))) for s, st, sz in zip(hw, strides, (32, 64, 128))]
+    ref = o.rpn_predict_proposals(anchors, logits, deltas, sizes, 0.7, 1000, 300, 0.0, False, exp=o.exp_correctly_rounded)
+    for kw in (dict(feat_hw=hw), dict()):      # closed-form anchors per level, and explicit anchor tensors
+        got = rpn.predict_proposals([Boxes(a.to(cuda_device)) for a in anchors], [t.to(cuda_device) for t in logits],
+                                    [t.to(cuda_device) for t in deltas], sizes, **kw)
+        for a, b in zip(got, ref):
+            assert len(a) == len(b["proposal_boxes"]) and 50 < len(a) <= 300
+            assert torch.equal(a.proposal_boxes.tensor.cpu(), b["proposal_boxes"]) and torch.equal(a.objectness_logits.cpu(), b["objectness_logits"])
+    b, l, src, cnt, inv = rpn.select_proposals([t.to(cuda_device) for t in logits], [t.to(cuda_device) for t in deltas], sizes, hw,
+                                               [Boxes(a.to(cuda_device)) for a in anchors])
+    for n in range(N):
+        assert torch.equal(src[n, :int(cnt[n])].cpu(), ref[n]["src_index"]) and int(inv[n]) == 0
