@@ -175,6 +175,21 @@ mean, var = finalize_stats_host(payload, 5, total)
 ref_mean = full.mean(dim=(0, 2, 3)); ref_var = full.var(dim=(0, 2, 3), unbiased=False)
 assert total == 6 * 7 * 9, total
 assert torch.allclose(mean, ref_mean, rtol=1e-12, atol=1e-12) and torch.allclose(var, ref_var, rtol=1e-10), (mean, ref_mean)
+# the sync-free variant (round 2): the global count stays inside the payload, where phase 2 of the kernels reads it
+from sfod_b200.engine.adabn_dist import allreduce_bn_stats_device
+payload2 = torch.cat([stats, torch.tensor([float(mine.numel() // 5)], dtype=torch.float64)])
+assert allreduce_bn_stats_device(payload2, 5) is None
+assert torch.equal(payload2, payload) and payload2[10].item() == 6 * 7 * 9
+# the shim's detectron2.utils.comm is rank-aware (ADVICE r1): one main process, gather / all_gather of picklable objects
+from sfod_b200 import d2shim
+d2shim.install(force=True)
+import detectron2.utils.comm as comm
+assert comm.get_world_size() == world and comm.get_rank() == rank and comm.is_main_process() == (rank == 0)
+got = comm.gather({"rank": rank}, dst=0)
+assert (got == [{"rank": 0}, {"rank": 1}]) if rank == 0 else (got == [])
+assert comm.all_gather(rank * 10) == [0, 10]
+comm.synchronize()
+d2shim.uninstall()
 dist.barrier()
 if rank == 0:
     print("GLOO_OK")
