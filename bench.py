@@ -722,28 +722,99 @@ def adabn_record(teacher, dev_batches, B, world, rank, dev, timed, steps, cfg):
     from sfod_b200.engine import adabn as adabn_mod
     adabn_mod.recursive_traversal(bb); adabn_mod.recursive_traversal(bb)
     layers = [m for m in bb.modules() if isinstance(m, SfodBatchNorm2d)]
-    for m in layers:
-        m.process_group = True if world > 1 else None
     bb.train()
     x_norm = [teacher.preprocess_batch(b).tensor for b in dev_batches]
 
     def step(i):
         with torch.no_grad():
             return bb(x_norm[i % len(x_norm)])
-    for i in range(3):
-        step(i)
-    n = max(3, min(steps, 10))
-    ms, launches, _, _ = timed(step, n)
+
+    def run(group):
+        for m in layers:
+            m.process_group = group
+        for i in range(3):
+            step(i)
+        n_ = max(3, min(steps, 10))
+        ms_, launches_, _, _ = timed(step, n_)
+        return ms_, launches_, n_
+
+    # Product path at N > 1: the statistic all-reduce fused into the finalize kernel over NVLink peer memory
+    # (sfod_bn_exchange_finalize_apply); baseline beside it: one ncclAllReduce launch per BN layer.
+    peer, peer_err, nccl_ms = None, None, None
+    if world > 1:
+        ms_b, _, n_b = run(True)
+        nccl_ms = ms_b / n_b
+        try:
+            from sfod_b200.engine.p2p import PeerStatExchange
+            peer = PeerStatExchange.from_process_group(device=dev)
+        except Exception as e:   # no peer access / IPC on this box: the NCCL path is reported, and said so
+            peer_err = f"{type(e).__name__}: {e}"[:200]
+        ok = torch.tensor([0 if peer is None else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and peer is not None:
+            peer.close(); peer = None; peer_err = peer_err or "a peer rank could not map the inboxes"
+    group = peer if peer is not None else (True if world > 1 else None)
+    variants = None
+    if peer is not None:   # delivery by the statistics kernel's last CTA (default) vs by the finalize kernel
+        from sfod_b200 import ops as _ops
+        default_tail = _ops.BN_P2P_TAIL_PUSH
+        _ops.BN_P2P_TAIL_PUSH = 1 - default_tail
+        ms_o, _, n_o = run(group)
+        _ops.BN_P2P_TAIL_PUSH = default_tail
+        variants = {("payload_delivered_by_statistics_kernel_tail" if not default_tail else "payload_delivered_by_finalize_kernel"): round(ms_o / n_o, 3)}
+    ms, launches, n = run(group)
+    if variants is not None:
+        variants[("payload_delivered_by_statistics_kernel_tail" if default_tail else "payload_delivered_by_finalize_kernel") + " (default, = ms_per_step)"] = round(ms / n, 3)
     payload = sum(2 * m.num_features + 1 for m in layers) * 8
+    if world == 1:
+        coll = None
+    elif peer is not None:
+        coll = (f"one-shot all-reduce over NVLink peer memory fused into the finalize kernel of each of the {len(layers)} BN layers "
+                f"(P2P stores of self-validating 16-byte (value, tag) elements, fp64 (sum, sum^2, count) payloads, {2 * payload} B per rank and peer and step, no fence, no flag, no collective launch, no host read)")
+    else:
+        coll = (f"{len(layers)} ncclAllReduce per step (one per BN layer, fp64 (sum, sum^2, count) payloads, {payload} B per rank and step in total), "
+                f"enqueued without any host read; peer-memory path unavailable: {peer_err}")
     rec = {"metric": "adabn_images_per_s", "value": round(world * B * n / (ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms / n, 3), "steps": n,
-           "bn_layers": len(layers), "gpu_launches": int(launches),
-           "collective": None if world == 1 else f"{len(layers)} ncclAllReduce per step (one per BN layer, fp64 (sum, sum^2, count) payloads, "
-                                                 f"{payload} B per rank and step in total), enqueued without any host read",
+           "bn_layers": len(layers), "gpu_launches": int(launches), "collective": coll,
            "what": "configs[3] AdaBN step: backbone forward in train() mode under no_grad, running statistics of the concatenated batch"}
+    if nccl_ms is not None:
+        rec["nccl_allreduce_baseline_ms_per_step"] = round(nccl_ms, 3)
+    if variants is not None:
+        rec["peer_memory_variants_ms_per_step"] = variants
+    if world > 1:
+        # The step above is dominated by the convolutions and by the skew between the ranks; the cost of the collective itself
+        # is isolated here: one 512-channel BN layer on a tiny activation, 200 forwards back to back, microseconds per layer.
+        from sfod_b200 import ops as _ops
+
+        def layer_us(grp):
+            bn_ = SfodBatchNorm2d(512, process_group=grp).to(dev).train()
+            xs_ = torch.randn(2, 512, 8, 8, device=dev)
+            saved = _ops.BN_FUSED_MAX_BYTES
+            _ops.BN_FUSED_MAX_BYTES = 0      # two-phase path for the no-collective line as well
+            try:
+                with torch.no_grad():
+                    for _ in range(20):
+                        bn_(xs_)
+                    dist.barrier(); torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(200):
+                        bn_(xs_)
+                    e1.record(); torch.cuda.synchronize()
+            finally:
+                _ops.BN_FUSED_MAX_BYTES = saved
+            t_ = torch.tensor([e0.elapsed_time(e1) * 1e3 / 200], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return round(float(t_.item()), 2)
+        lat = {"no_collective": layer_us(None), "nccl_allreduce": layer_us(True)}
+        if peer is not None:
+            lat["peer_memory_fused"] = layer_us(peer)
+        lat["what"] = "us per 512-channel BN layer forward (statistics + [collective] + finalize + apply) on a 2x512x8x8 activation, max over ranks"
+        rec["collective_latency_us_per_layer"] = lat
     if world > 1:   # self-check of the multi-GPU statistics against a single-device computation on the concatenated batch
         g = torch.Generator().manual_seed(77)
         xs = [torch.randn(2, 8, 24, 40, generator=g) * (r + 1) + r for r in range(world)]
-        bn = SfodBatchNorm2d(8, process_group=True).to(dev).train()
+        bn = SfodBatchNorm2d(8, process_group=group).to(dev).train()
         with torch.no_grad():
             bn(xs[rank].to(dev))
         ref = torch.nn.BatchNorm2d(8).train()
@@ -754,6 +825,13 @@ def adabn_record(teacher, dev_batches, B, world, rank, dev, timed, steps, cfg):
         t = torch.tensor([err], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         rec["selfcheck_vs_cpu_batchnorm_on_concatenated_batch"] = {"max_rel_err": float(t.item()), "tolerance": 1e-5, "ok": bool(t.item() <= 1e-5)}
+        if peer is not None:
+            ex, to = peer.status()
+            tt = torch.tensor([to], dtype=torch.int64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            rec["peer_exchanges"] = {"completed_on_rank0": ex, "timeouts_max_over_ranks": int(tt.item())}
+            dist.barrier()
+            peer.close()
     return rec
 
 

@@ -320,6 +320,49 @@ int sfod_bn_frozen_apply(const float *x, const float *residual, float *y, int la
                          double eps, int fuse_relu, void *scratch, sfod_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU AdaBN statistics over NVLink peer memory (collective (2)): the all-reduce of the per-layer
+ * (sum x, sum x^2, count) payload that makes every rank normalise with the statistics of the concatenated batch when
+ * test_refinement (reference daod/engine/trainers/base.py:270-337) or the teacher forward
+ * (source_free_adaptive_teacher.py:385-390) runs data-parallel.  Instead of a collective launch per layer (NCCL
+ * all-reduce of 2C+1 doubles: the baseline, see simple-sfod_b200/engine/adabn_dist.py) the exchange is fused into phase 2:
+ * one kernel stores the local payload into every peer's inbox with P2P stores, raises a flag per peer, waits for the
+ * peers' flags, adds the payloads in rank order (bit-identical totals on every rank) and computes the coefficients.
+ *
+ * An inbox is sfod_p2p_inbox_bytes() of device memory allocated by sfod_p2p_alloc (cudaMalloc + zero fill), which also
+ * returns its 64-byte CUDA IPC handle; the caller ships the handle to the other processes of the node (any host channel:
+ * torch.distributed.all_gather_object in simple-sfod_b200/engine/p2p.py) and maps theirs with sfod_p2p_open.  Ranks sharing
+ * one process (tests) put each other's inbox pointers into the comm directly.  All ranks must issue the same sequence of
+ * exchanges.  A peer that never arrives is abandoned after ~3 s (sfod_p2p_status reports the number of such timeouts; the
+ * results of a timed-out exchange are invalid) -- the GPU is never left spinning. */
+#define SFOD_P2P_MAX_RANKS 8
+#define SFOD_P2P_HANDLE_BYTES 64
+typedef struct sfod_p2p_comm {
+  int32_t rank, world;                 /* world <= SFOD_P2P_MAX_RANKS */
+  void *inbox[SFOD_P2P_MAX_RANKS];     /* inbox[r]: rank r's inbox as mapped into THIS process (inbox[rank] = own allocation) */
+} sfod_p2p_comm_t;
+size_t sfod_p2p_inbox_bytes(void);
+int sfod_p2p_max_channels(void);       /* largest C one exchange carries (2051: covers the 2048-channel res5 of the reference backbones) */
+int sfod_p2p_alloc(void **inbox, unsigned char *handle /* SFOD_P2P_HANDLE_BYTES, may be NULL */);
+int sfod_p2p_open(const unsigned char *handle, void **peer_inbox);
+int sfod_p2p_close(void *peer_inbox);
+int sfod_p2p_free(void *inbox);
+/* Synchronous read of the own inbox header: exchanges completed, exchanges abandoned on a timeout. */
+int sfod_p2p_status(const sfod_p2p_comm_t *comm, uint64_t *exchanges, uint32_t *timeouts);
+/* sfod_bn_partial_stats for a rank of `comm`: same result in stats_dev; in addition the CTA of the statistics kernel that
+ * finishes last delivers the payload to the peers' inboxes (NCHW layers covered by one launch; otherwise phase 2 delivers it),
+ * so the NVLink transfer overlaps the launch gap between the two phases.  Must be followed by
+ * sfod_bn_exchange_finalize_apply on the same stream, comm and stats_dev. */
+int sfod_bn_partial_stats_p2p(const float *x, const float *pre_bias, int layout, int N, int C, int64_t HW, double *stats_dev,
+                              const sfod_p2p_comm_t *comm, sfod_stream_t stream);
+/* sfod_bn_finalize_apply_v2 with the cross-rank exchange in front of it: stats_dev holds this rank's phase-1 result
+ * ((C,2) totals and the local element count at [2C]) on entry and the totals of the concatenated batch on return. */
+int sfod_bn_exchange_finalize_apply(const float *x, const float *pre_bias, const float *residual, float *y, int layout, int N,
+                                    int C, int H, int W, double *stats_dev, const sfod_p2p_comm_t *comm, const float *weight,
+                                    const float *bias, float *running_mean, float *running_var, int64_t *num_batches_tracked,
+                                    double momentum, double eps, int fuse_relu, int fuse_maxpool2, float *save_mean,
+                                    float *save_invstd, sfod_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------
  * Strong augmentation of the student's input on the device.  Replaces the PIL / torchvision CPU
  * pipeline of reference daod/data/detection_utils.py:7-37, applied per image at
  * daod/data/mappers/two_crop_augmentation_mapper.py:141-157: RandomApply(ColorJitter(0.4, 0.4, 0.4, 0.1), 0.8),

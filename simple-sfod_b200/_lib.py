@@ -46,6 +46,14 @@ class FrcnnParams(C.Structure):
                 ("coord_trick_max_n", C.c_int64), ("rows_stride", C.c_int)]
 
 
+P2P_MAX_RANKS = 8
+P2P_HANDLE_BYTES = 64
+
+
+class P2PComm(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("inbox", C.c_void_p * P2P_MAX_RANKS)]
+
+
 # name -> (restype, argtypes); every symbol include/sfod_b200.h declares
 SIGNATURES = {
     "sfod_abi_version": (C.c_int, []),
@@ -94,6 +102,17 @@ SIGNATURES = {
     "sfod_bn_frozen_scratch_bytes": (C.c_size_t, [C.c_int]),
     "sfod_bn_frozen_apply": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                                        C.c_double, C.c_int, c_ptr, c_ptr]),
+    "sfod_p2p_inbox_bytes": (C.c_size_t, []),
+    "sfod_p2p_max_channels": (C.c_int, []),
+    "sfod_p2p_alloc": (C.c_int, [C.POINTER(C.c_void_p), c_ptr]),
+    "sfod_p2p_open": (C.c_int, [c_ptr, C.POINTER(C.c_void_p)]),
+    "sfod_p2p_close": (C.c_int, [c_ptr]),
+    "sfod_p2p_free": (C.c_int, [c_ptr]),
+    "sfod_p2p_status": (C.c_int, [C.POINTER(P2PComm), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "sfod_bn_partial_stats_p2p": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int64, c_ptr, C.POINTER(P2PComm), c_ptr]),
+    "sfod_bn_exchange_finalize_apply": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr,
+                                                  C.POINTER(P2PComm), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_double, C.c_double, C.c_int,
+                                                  C.c_int, c_ptr, c_ptr, c_ptr]),
     "sfod_bn_finalize_apply_v2": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.c_double, C.c_int,
                                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_double, C.c_double, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
 }

@@ -9,6 +9,7 @@
 // that (warp, block, grid, and the E[x^2]-E[x]^2 combination) is fp64.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <string.h>
 
 namespace {
 
@@ -28,15 +29,54 @@ __device__ __forceinline__ void flush_channel(double *stats, int c, double sd, d
   atomicAdd(stats + 2 * c + 1, sd2 + 2.0 * K * sd + m * K * K);
 }
 
-__global__ void __launch_bounds__(kThreads) bn_stats_nchw_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
-                                                                 int C, long long HW, double *__restrict__ stats, double local_count) {
+// ---- NVLink peer-memory exchange of the statistics: inbox layout and the delivery step (described at the end of this file)
+constexpr int kP2PMaxPayload = 4104;                   // 2 * 2048 + 1 doubles, rounded up to a multiple of 8
+constexpr size_t kP2PHeaderBytes = 256;
+constexpr int kP2PThreads = 1024;
+constexpr long long kP2PSpinLimit = 6000000000ll;      // ~3 s of SM clocks: a missing peer must not hang the GPU
+
+// One payload element on the wire: the two 32-bit halves of the double, each next to a copy of the exchange's 32-bit tag.
+// An aligned 8-byte store is single-copy atomic, so each (half, tag) pair validates itself: the receiver needs neither a
+// separate flag nor a fence between payload and flag -- one NVLink one-way latency per exchange (the "LL" idea of NCCL).
+__device__ __forceinline__ uint4 *p2p_slot(char *inbox, int par, int src) {
+  return reinterpret_cast<uint4 *>(inbox + kP2PHeaderBytes) + ((size_t)par * SFOD_P2P_MAX_RANKS + src) * kP2PMaxPayload;
+}
+__device__ __forceinline__ unsigned p2p_tag(unsigned long long epoch) { return (unsigned)(epoch & 0x7FFFFFFFull) | 0x80000000u; }   // never 0
+__device__ __forceinline__ void p2p_store(uint4 *p, double v, unsigned tag) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)u), "r"(tag), "r"((unsigned)(u >> 32)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ bool p2p_load(const uint4 *p, unsigned tag, double &v) {
+  uint4 e;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "l"(p) : "memory");
+  v = __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
+  return e.y == tag && e.w == tag;
+}
+
+// Delivery step, called by all threads of one CTA: element i of `src` goes to slot [epoch & 1][rank] of every PEER's inbox.
+__device__ __forceinline__ void p2p_push(const double *__restrict__ src, int n, const sfod_p2p_comm_t &comm, unsigned long long epoch) {
+  const int par = (int)(epoch & 1ull);
+  const unsigned tag = p2p_tag(epoch);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = __ldcg(src + i);
+    for (int p = 0; p < comm.world; ++p)
+      if (p != comm.rank) p2p_store(p2p_slot(static_cast<char *>(comm.inbox[p]), par, comm.rank) + i, v, tag);
+  }
+}
+constexpr unsigned long long kP2PPushed = ~0ull;   // value of the ticket word stats[2C + 1] once the statistics kernel has delivered the payload
+
+template <bool kPush>
+__global__ void __launch_bounds__(kThreads, kPush ? 8 : 1) bn_stats_nchw_kernel(const float *__restrict__ x, const float *__restrict__ pre_bias,
+                                                                 int C, long long HW, double *__restrict__ stats, double local_count,
+                                                                 sfod_p2p_comm_t comm) {
   __shared__ double red[2][kThreads / 32];
   const int plane = blockIdx.y;          // n * C + c
   if (local_count > 0.0 && blockIdx.x == 0 && plane == 0 && threadIdx.x == 0) stats[2 * C] = local_count;   // third part of the all-reduce payload
   const int c = plane % C;
   const long long start = (long long)blockIdx.x * kChunk;
   const long long len = min((long long)kChunk, HW - start);
-  if (len <= 0) return;
+  if (len <= 0 && !kPush) return;
+  if (len > 0) {
   const float *p = x + (size_t)plane * HW + start;
   // The statistics are those of v = fl(x + pre_bias[c]) (the conv bias the reference adds before BatchNorm, fused here);
   // the pivot is expressed in x-space: (x + b) - (x0 + b) is evaluated as fl(fl(x + b) - K) with K = fl(x0 + b).
@@ -67,6 +107,25 @@ __global__ void __launch_bounds__(kThreads) bn_stats_nchw_kernel(const float *__
     ds2 = lane < kThreads / 32 ? red[1][lane] : 0.0;
     ds = warp_sum(ds); ds2 = warp_sum(ds2);
     if (lane == 0) flush_channel(stats, c, ds, ds2, (double)len, (double)K);
+  }
+  }
+  if constexpr (kPush) {
+    // Multi-GPU: the CTA that finishes last (ticket word stats[2C + 1], zeroed with the totals) delivers the rank's 2C+1 payload
+    // to every peer's inbox right here, so the NVLink latency overlaps the launch gap before the finalize kernel, which then
+    // only polls for the peers' elements.
+    __shared__ int s_last;
+    unsigned long long *ticket = reinterpret_cast<unsigned long long *>(stats + 2 * C + 1);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x * gridDim.y - 1ull;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const unsigned long long epoch = *reinterpret_cast<const unsigned long long *>(comm.inbox[comm.rank]) + 1ull;
+      p2p_push(stats, 2 * C + 1, comm, epoch);
+      if (threadIdx.x == 0) *ticket = kP2PPushed;
+    }
   }
 }
 
@@ -166,18 +225,14 @@ __global__ void __launch_bounds__(kThreads) bn_stats_nhwc_scalar_kernel(const fl
   }
 }
 
-// One thread per channel: ATen batch_norm_cpu_update_stats arithmetic in fp64.
-__global__ void bn_finalize_kernel(const double *__restrict__ stats, int C, double n_host, int count_on_device, const float *__restrict__ weight,
-                                   const float *__restrict__ bias, float *__restrict__ running_mean,
-                                   float *__restrict__ running_var, long long *__restrict__ nbt, double momentum, double eps,
-                                   float *__restrict__ save_mean, float *__restrict__ save_invstd, float *__restrict__ scale,
-                                   float *__restrict__ shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt) *nbt += 1;
-  if (c >= C) return;
-  const double n = count_on_device ? stats[2 * C] : n_host;   // all-reduced element count: no host read between the phases
-  const double mean = stats[2 * c] / n;
-  double var = stats[2 * c + 1] / n - mean * mean;
+// One channel: ATen batch_norm_cpu_update_stats arithmetic in fp64 on the channel's (sum x, sum x^2) and the element count n.
+__device__ __forceinline__ void bn_finalize_channel(int c, double sum, double sumsq, double n, const float *__restrict__ weight,
+                                                    const float *__restrict__ bias, float *__restrict__ running_mean,
+                                                    float *__restrict__ running_var, double momentum, double eps,
+                                                    float *__restrict__ save_mean, float *__restrict__ save_invstd,
+                                                    float *__restrict__ scale, float *__restrict__ shift) {
+  const double mean = sum / n;
+  double var = sumsq / n - mean * mean;
   if (var < 0.0) var = 0.0;
   const double invstd = 1.0 / sqrt(var + eps);
   const float mean_f = (float)mean;
@@ -191,6 +246,20 @@ __global__ void bn_finalize_kernel(const double *__restrict__ stats, int C, doub
   const double w = weight ? (double)weight[c] : 1.0, b = bias ? (double)bias[c] : 0.0;
   scale[c] = (float)(w * invstd);
   shift[c] = (float)(b - mean * w * invstd);
+}
+
+// One thread per channel.
+__global__ void bn_finalize_kernel(const double *__restrict__ stats, int C, double n_host, int count_on_device, const float *__restrict__ weight,
+                                   const float *__restrict__ bias, float *__restrict__ running_mean,
+                                   float *__restrict__ running_var, long long *__restrict__ nbt, double momentum, double eps,
+                                   float *__restrict__ save_mean, float *__restrict__ save_invstd, float *__restrict__ scale,
+                                   float *__restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  const double n = count_on_device ? stats[2 * C] : n_host;   // all-reduced element count: no host read between the phases
+  bn_finalize_channel(c, stats[2 * c], stats[2 * c + 1], n, weight, bias, running_mean, running_var, momentum, eps, save_mean,
+                      save_invstd, scale, shift);
 }
 
 template <bool kRelu>
@@ -481,20 +550,45 @@ SFOD_API size_t sfod_bn_stats_bytes(int C) {
   return C > 0 ? sfod_align_up((size_t)C * (4 + 2 * kStatReplicas) * sizeof(double), 256) : 256;
 }
 
+static bool p2p_comm_ok(const sfod_p2p_comm_t *comm) {
+  if (!comm || comm->world < 1 || comm->world > SFOD_P2P_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world) return false;
+  for (int r = 0; r < comm->world; ++r)
+    if (!comm->inbox[r]) return false;
+  return true;
+}
+
+static int bn_partial_stats_impl(const float *x, const float *pre_bias, int layout, int N, int C, int64_t HW, double *stats_dev,
+                                 const sfod_p2p_comm_t *comm, sfod_stream_t stream);
+
 SFOD_API int sfod_bn_partial_stats(const float *x, const float *pre_bias, int layout, int N, int C, int64_t HW, double *stats_dev,
                                    sfod_stream_t stream) {
+  return bn_partial_stats_impl(x, pre_bias, layout, N, C, HW, stats_dev, nullptr, stream);
+}
+
+SFOD_API int sfod_bn_partial_stats_p2p(const float *x, const float *pre_bias, int layout, int N, int C, int64_t HW, double *stats_dev,
+                                       const sfod_p2p_comm_t *comm, sfod_stream_t stream) {
+  if (!p2p_comm_ok(comm)) return SFOD_ERR_INVALID_ARG;
+  if (2 * C + 1 > kP2PMaxPayload) return SFOD_ERR_UNSUPPORTED;
+  return bn_partial_stats_impl(x, pre_bias, layout, N, C, HW, stats_dev, comm, stream);
+}
+
+static int bn_partial_stats_impl(const float *x, const float *pre_bias, int layout, int N, int C, int64_t HW, double *stats_dev,
+                                 const sfod_p2p_comm_t *comm, sfod_stream_t stream) {
   if (!x || !stats_dev || N <= 0 || C <= 0 || HW <= 0) return SFOD_ERR_INVALID_ARG;
   if (layout != SFOD_NCHW && layout != SFOD_NHWC) return SFOD_ERR_INVALID_ARG;
   cudaStream_t st = sfod_cu(stream);
-  SFOD_CUDA_TRY(cudaMemsetAsync(stats_dev, 0, (size_t)C * 2 * sizeof(double), st));
+  SFOD_CUDA_TRY(cudaMemsetAsync(stats_dev, 0, ((size_t)C * 2 + 2) * sizeof(double), st));   // totals, count, ticket word
   if (layout == SFOD_NCHW) {
     const long long planes = (long long)N * C;
     const long long step = 65535 / C * (long long)C;  // grid.y limit; multiples of C keep channel = plane % C
     if (step == 0) return SFOD_ERR_UNSUPPORTED;
+    const bool push = comm != nullptr && planes <= step;   // one launch covers the layer: its last CTA delivers the payload
     for (long long p0 = 0; p0 < planes; p0 += step) {
       const long long np = planes - p0 < step ? planes - p0 : step;
       dim3 grid((unsigned)((HW + kChunk - 1) / kChunk), (unsigned)np);
-      bn_stats_nchw_kernel<<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, pre_bias, C, HW, stats_dev, p0 == 0 ? (double)N * (double)HW : 0.0);
+      const double cnt = p0 == 0 ? (double)N * (double)HW : 0.0;
+      if (push) bn_stats_nchw_kernel<true><<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, pre_bias, C, HW, stats_dev, cnt, *comm);
+      else bn_stats_nchw_kernel<false><<<grid, kThreads, 0, st>>>(x + (size_t)p0 * HW, pre_bias, C, HW, stats_dev, cnt, sfod_p2p_comm_t{});
       SFOD_LAUNCH_CHECK();
     }
     return SFOD_OK;
@@ -703,4 +797,168 @@ SFOD_API int sfod_bn_train_fused(const float *x, const float *pre_bias, const fl
   SFOD_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(kThreads), args, 0, st));
   sfod_count_launch();
   return SFOD_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// Multi-GPU statistics: one-shot all-reduce of the (sum x, sum x^2, count) payload over NVLink peer memory, fused into the
+// finalize kernel (SURVEY.md 8e collective (2); reference daod/engine/trainers/base.py:270-337 run on several ranks).
+//
+// Every rank owns an INBOX (cudaMalloc'ed, exported with cudaIpcGetMemHandle and mapped by every peer):
+//   [0]    uint64 counter  -- exchanges this rank has completed (the epoch of the next one is counter + 1; kept on the device so
+//                             that a captured CUDA graph replays correctly)
+//   [8]    uint32 timeouts -- exchanges abandoned because a peer's payload did not arrive (diagnostic; results are then invalid)
+//   [256]  uint4 slot[2][8][kP2PMaxPayload]   slot[parity][src][i] = (lo32, tag, hi32, tag) of rank src's i-th payload double
+// One exchange, executed by ONE CTA on every rank after its statistics pass: (1) store the local 2C+1 doubles into slot
+// [epoch & 1][rank] of every PEER's inbox as 16-byte (value, tag) elements (NVLink P2P stores, coalesced; no fence, no flag:
+// every 8-byte half carries the tag of this exchange); (2) every thread polls its element of each peer's slot in the own inbox
+// until both tags match, and adds the contributions in rank order -- the same order on every rank, so all ranks obtain
+// bit-identical totals; (3) the per-channel coefficients and running statistics are computed from the totals in the same kernel.
+// 16 KB per rank and 512-channel layer cross NVLink once, with one one-way latency on the critical path; there is no separate
+// collective launch and no host involvement.  Step (1) can also be taken by the statistics kernel itself (its last CTA, see
+// bn_stats_nchw_kernel<true>), which hides the transfer behind the launch gap between the two phases.  Slot reuse is safe
+// without a handshake: a rank that writes epoch e + 2 has completed exchange e + 1, for which every peer had delivered its
+// epoch-(e+1) payload, which a peer does only after its own exchange e -- the last reader of the slot -- has finished
+// (stream order); and a reader accepts an element only with the tag of its own epoch.
+namespace {
+__global__ void __launch_bounds__(kP2PThreads) bn_exchange_finalize_kernel(double *__restrict__ stats, int C, sfod_p2p_comm_t comm,
+                                                                            const float *__restrict__ weight, const float *__restrict__ bias,
+                                                                            float *__restrict__ running_mean, float *__restrict__ running_var,
+                                                                            long long *__restrict__ nbt, double momentum, double eps,
+                                                                            float *__restrict__ save_mean, float *__restrict__ save_invstd,
+                                                                            float *__restrict__ scale, float *__restrict__ shift) {
+  __shared__ double tot[kP2PMaxPayload];
+  __shared__ int s_timeout;
+  char *mine = static_cast<char *>(comm.inbox[comm.rank]);
+  unsigned long long *counter = reinterpret_cast<unsigned long long *>(mine);
+  const unsigned long long epoch = *counter + 1ull;
+  const int par = (int)(epoch & 1ull);
+  const unsigned tag = p2p_tag(epoch);
+  const int n = 2 * C + 1;
+  if (threadIdx.x == 0) s_timeout = 0;
+  // the statistics kernel's last CTA may already have delivered the payload (ticket word == kP2PPushed)
+  const bool pushed = *reinterpret_cast<const unsigned long long *>(stats + 2 * C + 1) == kP2PPushed;   // CTA-uniform
+  if (!pushed) p2p_push(stats, n, comm, epoch);
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double t = 0.0;
+    for (int r = 0; r < comm.world; ++r) {   // rank order: the same sum on every rank
+      double v;
+      if (r == comm.rank) v = __ldcg(stats + i);   // own contribution straight from phase 1
+      else {
+        const uint4 *e = p2p_slot(mine, par, r) + i;
+        while (!p2p_load(e, tag, v)) {
+          if (clock64() - t0 > kP2PSpinLimit) { s_timeout = 1; v = 0.0; break; }
+          __nanosleep(20);
+        }
+      }
+      t += v;
+    }
+    tot[i] = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) stats[i] = tot[i];   // the totals of the concatenated batch, as the NCCL path leaves them
+  const double cnt = tot[2 * C];
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    bn_finalize_channel(c, tot[2 * c], tot[2 * c + 1], cnt, weight, bias, running_mean, running_var, momentum, eps, save_mean, save_invstd,
+                        scale, shift);
+  if (threadIdx.x == 0) {
+    if (nbt) *nbt += 1;
+    if (s_timeout) atomicAdd(reinterpret_cast<unsigned *>(mine + 8), 1u);
+    *counter = epoch;
+  }
+}
+}  // namespace
+
+SFOD_API size_t sfod_p2p_inbox_bytes(void) {
+  return kP2PHeaderBytes + 2 * (size_t)SFOD_P2P_MAX_RANKS * kP2PMaxPayload * sizeof(uint4);
+}
+SFOD_API int sfod_p2p_max_channels(void) { return (kP2PMaxPayload - 1) / 2; }
+
+// With CUDA's lazy module loading the FIRST launch of a kernel may synchronise the context.  Ranks that share one process
+// (and one GPU: tests) would deadlock if that happened while a peer's finalize kernel is already polling for this rank's
+// payload, so every kernel a BatchNorm layer can launch is loaded up front.
+static int p2p_preload_kernels() {
+  const void *kernels[] = {
+      (const void *)bn_stats_nchw_kernel<true>, (const void *)bn_stats_nchw_kernel<false>, (const void *)bn_stats_nhwc_kernel,
+      (const void *)bn_fold_replicas_kernel, (const void *)bn_stats_nhwc_scalar_kernel, (const void *)bn_exchange_finalize_kernel,
+      (const void *)bn_finalize_kernel,
+      (const void *)bn_apply_nchw_kernel<true, true>, (const void *)bn_apply_nchw_kernel<true, false>,
+      (const void *)bn_apply_nchw_kernel<false, true>, (const void *)bn_apply_nchw_kernel<false, false>,
+      (const void *)bn_apply_pool_nchw_kernel<true, true>, (const void *)bn_apply_pool_nchw_kernel<true, false>,
+      (const void *)bn_apply_pool_nchw_kernel<false, true>, (const void *)bn_apply_pool_nchw_kernel<false, false>,
+      (const void *)bn_apply_nhwc_kernel<true, true>, (const void *)bn_apply_nhwc_kernel<true, false>,
+      (const void *)bn_apply_nhwc_kernel<false, true>, (const void *)bn_apply_nhwc_kernel<false, false>,
+      (const void *)bn_apply_pool_nhwc_kernel<true>, (const void *)bn_apply_pool_nhwc_kernel<false>,
+      (const void *)bn_apply_nhwc_scalar_kernel<true>, (const void *)bn_apply_nhwc_scalar_kernel<false>};
+  for (const void *k : kernels) {
+    cudaFuncAttributes attr;
+    SFOD_CUDA_TRY(cudaFuncGetAttributes(&attr, k));
+  }
+  return SFOD_OK;
+}
+
+SFOD_API int sfod_p2p_alloc(void **inbox, unsigned char *handle) {
+  if (!inbox) return SFOD_ERR_INVALID_ARG;
+  if (int rc = p2p_preload_kernels()) return rc;
+  void *p = nullptr;
+  SFOD_CUDA_TRY(cudaMalloc(&p, sfod_p2p_inbox_bytes()));
+  cudaError_t e = cudaMemset(p, 0, sfod_p2p_inbox_bytes());
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess && handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == SFOD_P2P_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e == cudaSuccess) memcpy(handle, &h, sizeof(h));
+  }
+  if (e != cudaSuccess) { cudaFree(p); return SFOD_ERR_CUDA_BASE + (int)e; }
+  *inbox = p;
+  return SFOD_OK;
+}
+SFOD_API int sfod_p2p_open(const unsigned char *handle, void **peer_inbox) {
+  if (!handle || !peer_inbox) return SFOD_ERR_INVALID_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  SFOD_CUDA_TRY(cudaIpcOpenMemHandle(peer_inbox, h, cudaIpcMemLazyEnablePeerAccess));
+  return SFOD_OK;
+}
+SFOD_API int sfod_p2p_close(void *peer_inbox) {
+  if (!peer_inbox) return SFOD_ERR_INVALID_ARG;
+  SFOD_CUDA_TRY(cudaIpcCloseMemHandle(peer_inbox));
+  return SFOD_OK;
+}
+SFOD_API int sfod_p2p_free(void *inbox) {
+  if (!inbox) return SFOD_ERR_INVALID_ARG;
+  SFOD_CUDA_TRY(cudaFree(inbox));
+  return SFOD_OK;
+}
+SFOD_API int sfod_p2p_status(const sfod_p2p_comm_t *comm, uint64_t *exchanges, uint32_t *timeouts) {
+  if (!comm || comm->world < 1 || comm->world > SFOD_P2P_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world) return SFOD_ERR_INVALID_ARG;
+  unsigned long long head[2] = {0, 0};
+  SFOD_CUDA_TRY(cudaMemcpy(head, comm->inbox[comm->rank], sizeof(head), cudaMemcpyDeviceToHost));   // synchronises with the stream's work
+  if (exchanges) *exchanges = head[0];
+  if (timeouts) *timeouts = (uint32_t)(head[1] & 0xFFFFFFFFull);
+  return SFOD_OK;
+}
+
+SFOD_API int sfod_bn_exchange_finalize_apply(const float *x, const float *pre_bias, const float *residual, float *y, int layout, int N,
+                                             int C, int H, int W, double *stats_dev, const sfod_p2p_comm_t *comm, const float *weight,
+                                             const float *bias, float *running_mean, float *running_var, int64_t *num_batches_tracked,
+                                             double momentum, double eps, int fuse_relu, int fuse_maxpool2, float *save_mean,
+                                             float *save_invstd, sfod_stream_t stream) {
+  if (!stats_dev || !comm || N <= 0 || C <= 0 || H <= 0 || W <= 0) return SFOD_ERR_INVALID_ARG;
+  if (!p2p_comm_ok(comm)) return SFOD_ERR_INVALID_ARG;
+  if (2 * C + 1 > kP2PMaxPayload) return SFOD_ERR_UNSUPPORTED;
+  if (layout != SFOD_NCHW && layout != SFOD_NHWC) return SFOD_ERR_INVALID_ARG;
+  if (residual && fuse_maxpool2) return SFOD_ERR_INVALID_ARG;
+  if (residual && x && ((reinterpret_cast<uintptr_t>(residual) ^ reinterpret_cast<uintptr_t>(x)) & 15u)) return SFOD_ERR_ALIGNMENT;
+  cudaStream_t st = sfod_cu(stream);
+  float *scale = reinterpret_cast<float *>(stats_dev + 2 * (size_t)C + 2);
+  float *shift = scale + sfod_align_up((size_t)C, 4);
+  bn_exchange_finalize_kernel<<<1, kP2PThreads, 0, st>>>(stats_dev, C, *comm, weight, bias, running_mean, running_var,
+                                                         reinterpret_cast<long long *>(num_batches_tracked), momentum, eps, save_mean,
+                                                         save_invstd, scale, shift);
+  SFOD_LAUNCH_CHECK();
+  if (!x || !y) return SFOD_OK;
+  return launch_bn_apply(x, pre_bias, residual, y, layout, N, C, H, W, scale, shift, fuse_relu, fuse_maxpool2, st);
 }

@@ -1,0 +1,100 @@
+"""NVLink peer-memory exchange of the AdaBN statistics (collective (2)).
+
+``PeerStatExchange`` owns one inbox per rank (``sfod_p2p_alloc``), ships its CUDA IPC handle to the other processes of the
+node through ``torch.distributed`` (host plumbing only) and maps theirs; ``ops.bn_train_forward(group=<PeerStatExchange>)``
+then runs ``sfod_bn_exchange_finalize_apply``: the all-reduce of the (sum x, sum x^2, count) payload happens INSIDE the
+finalize kernel with P2P stores and flags (csrc/bn.cu), instead of one NCCL all-reduce launch per BN layer
+(``engine/adabn_dist.py``, the baseline it is measured against in ``bench.py``'s ``adabn`` record).
+
+Reference: the train-mode forwards of daod/engine/trainers/base.py:270-337 (AdaBN) and
+daod/engine/trainers/source_free_adaptive_teacher.py:385-390 (teacher) executed data-parallel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+from .. import _lib
+
+
+class PeerStatExchange:
+    """One rank's endpoint of the exchange.  Build it with ``PeerStatExchange.from_process_group()`` (one process per GPU) or
+    ``PeerStatExchange.local_ring()`` (several ranks inside one process, e.g. on separate streams of one GPU: tests)."""
+
+    def __init__(self, rank: int, world: int, inboxes: List[int], device: torch.device, owned: Optional[int], opened: List[int]):
+        if not (1 <= world <= _lib.P2P_MAX_RANKS and 0 <= rank < world and len(inboxes) == world):
+            raise ValueError("PeerStatExchange: 1 <= world <= 8 ranks, one inbox pointer per rank")
+        self.rank, self.world, self.device = rank, world, device
+        self.comm = _lib.P2PComm()
+        self.comm.rank, self.comm.world = rank, world
+        for r, p in enumerate(inboxes):
+            self.comm.inbox[r] = p
+        self._owned, self._opened = owned, list(opened)
+        self.max_channels = int(_lib.lib().sfod_p2p_max_channels())
+
+    # ------------------------------------------------------------------------------------------------ construction
+    @staticmethod
+    def _alloc(device: torch.device, want_handle: bool) -> Tuple[int, bytes]:
+        L = _lib.lib()
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * _lib.P2P_HANDLE_BYTES)()
+        with torch.cuda.device(device):
+            _lib.check(L.sfod_p2p_alloc(C.byref(ptr), handle if want_handle else None), "sfod_p2p_alloc")
+        return int(ptr.value), bytes(handle)
+
+    @classmethod
+    def from_process_group(cls, group=None, device: Optional[torch.device] = None) -> "PeerStatExchange":
+        """Collective over ``group`` (default group when None): every rank allocates its inbox, the IPC handles travel through
+        ``all_gather_object`` and every rank maps its peers' inboxes.  All ranks must live on GPUs of one node with peer access."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerStatExchange.from_process_group needs an initialised torch.distributed process group")
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if world > _lib.P2P_MAX_RANKS:
+            raise ValueError(f"PeerStatExchange supports up to {_lib.P2P_MAX_RANKS} ranks (one NVSwitch node)")
+        own, handle = cls._alloc(device, True)
+        gathered: List[Optional[bytes]] = [None] * world
+        dist.all_gather_object(gathered, handle, group=group)
+        L = _lib.lib()
+        inboxes, opened = [], []
+        with torch.cuda.device(device):
+            for r in range(world):
+                if r == rank:
+                    inboxes.append(own)
+                    continue
+                buf = (C.c_ubyte * _lib.P2P_HANDLE_BYTES).from_buffer_copy(gathered[r])
+                p = C.c_void_p()
+                _lib.check(L.sfod_p2p_open(buf, C.byref(p)), f"sfod_p2p_open(rank {r})")
+                inboxes.append(int(p.value))
+                opened.append(int(p.value))
+        dist.barrier(group=group)   # nobody starts exchanging before every mapping exists
+        return cls(rank, world, inboxes, device, own, opened)
+
+    @classmethod
+    def local_ring(cls, world: int, device: Optional[torch.device] = None) -> List["PeerStatExchange"]:
+        """``world`` endpoints inside this process whose inboxes are plain allocations on ``device``: each endpoint must be
+        driven from its own stream (the exchange kernels of all ranks have to be resident at the same time)."""
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        ptrs = [cls._alloc(device, False)[0] for _ in range(world)]
+        return [cls(r, world, ptrs, device, ptrs[r], []) for r in range(world)]
+
+    # ------------------------------------------------------------------------------------------------ use
+    def status(self) -> Tuple[int, int]:
+        """(exchanges completed, exchanges abandoned on a timeout) -- synchronises the device."""
+        ex, to = C.c_uint64(0), C.c_uint32(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().sfod_p2p_status(C.byref(self.comm), C.byref(ex), C.byref(to)), "sfod_p2p_status")
+        return int(ex.value), int(to.value)
+
+    def close(self) -> None:
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                L.sfod_p2p_close(p)
+            self._opened = []
+            if self._owned is not None:
+                L.sfod_p2p_free(self._owned)
+                self._owned = None

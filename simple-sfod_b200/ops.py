@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -666,6 +667,12 @@ class EmaPlan:
 
 
 # ----------------------------------------------------------------------------------------------- BatchNorm (AdaBN)
+# Multi-GPU statistics over peer memory: 0 = the payload is delivered by the finalize kernel itself (default), 1 = by the last CTA
+# of the statistics kernel (overlapping the launch gap before the finalize kernel, at the price of a ticket atomic per CTA).  Both
+# are correct and tested; bench.py measures both (no difference beyond noise in the AdaBN step at 2 GPUs: DESIGN.md section 7).
+BN_P2P_TAIL_PUSH = int(os.environ.get("SFOD_P2P_TAIL_PUSH", "0"))
+
+
 def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], running_mean: Optional[Tensor],
                      running_var: Optional[Tensor], num_batches_tracked: Optional[Tensor], momentum: float = 0.1,
                      eps: float = 1e-5, fuse_relu: bool = False, inplace: bool = False, group=None,
@@ -716,14 +723,26 @@ def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor]
                 return y
             if rc != 3:   # SFOD_ERR_UNSUPPORTED: no cooperative grid -> the two-phase path below
                 check(rc, "sfod_bn_train_fused")
+        peer = None
+        if group is not None:
+            from .engine.p2p import PeerStatExchange
+            if isinstance(group, PeerStatExchange):
+                peer = group   # the all-reduce happens inside the statistics / finalize kernels, over NVLink peer memory
+                if Cc > peer.max_channels:
+                    raise ValueError(f"PeerStatExchange carries at most {peer.max_channels} channels per layer")
         with _timed("bn_partial_stats"):
-            check(L.sfod_bn_partial_stats(xin.data_ptr(), pb.data_ptr() if pb is not None else None, layout, N, Cc, H * W,
-                                          stats.data_ptr(), _stream(dev)), "sfod_bn_partial_stats")
+            if peer is not None and BN_P2P_TAIL_PUSH:
+                check(L.sfod_bn_partial_stats_p2p(xin.data_ptr(), pb.data_ptr() if pb is not None else None, layout, N, Cc, H * W,
+                                                  stats.data_ptr(), C.byref(peer.comm), _stream(dev)), "sfod_bn_partial_stats_p2p")
+            else:
+                check(L.sfod_bn_partial_stats(xin.data_ptr(), pb.data_ptr() if pb is not None else None, layout, N, Cc, H * W,
+                                              stats.data_ptr(), _stream(dev)), "sfod_bn_partial_stats")
         on_device = 0
         if group is not None:
-            from .engine.adabn_dist import allreduce_bn_stats_device
-            allreduce_bn_stats_device(stats, Cc, group=group if group is not True else None)   # payload [0, 2C] incl. the count
-            on_device = 1
+            if peer is None:
+                from .engine.adabn_dist import allreduce_bn_stats_device
+                allreduce_bn_stats_device(stats, Cc, group=group if group is not True else None)   # payload [0, 2C] incl. the count
+                on_device = 1
         y = None
         if compute_output:
             if fuse_maxpool:
@@ -731,6 +750,20 @@ def bn_train_forward(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor]
                 y = torch.empty((N, Cc, H // 2, W // 2), dtype=torch.float32, device=dev, memory_format=fmt)
             else:
                 y = xin if inplace else torch.empty_like(xin)
+        if peer is not None:
+            with _timed("bn_exchange_finalize_apply"):
+                check(L.sfod_bn_exchange_finalize_apply(xin.data_ptr() if compute_output else None, pb.data_ptr() if pb is not None else None,
+                                                        res.data_ptr() if (res is not None and compute_output) else None,
+                                                        y.data_ptr() if y is not None else None, layout, N, Cc, H, W, stats.data_ptr(),
+                                                        C.byref(peer.comm),
+                                                        weight.data_ptr() if weight is not None else None,
+                                                        bias.data_ptr() if bias is not None else None,
+                                                        running_mean.data_ptr() if running_mean is not None else None,
+                                                        running_var.data_ptr() if running_var is not None else None,
+                                                        num_batches_tracked.data_ptr() if num_batches_tracked is not None else None,
+                                                        float(momentum), float(eps), int(fuse_relu), int(fuse_maxpool), None, None,
+                                                        _stream(dev)), "sfod_bn_exchange_finalize_apply")
+            return y
         with _timed("bn_finalize_apply_pool" if fuse_maxpool else ("bn_finalize_apply_res" if res is not None else "bn_finalize_apply")):
             check(L.sfod_bn_finalize_apply_v2(xin.data_ptr() if compute_output else None, pb.data_ptr() if pb is not None else None,
                                               res.data_ptr() if (res is not None and compute_output) else None,

@@ -197,3 +197,89 @@ def test_adabn_statistic_allreduce_nccl_two_gpus(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "NCCL_BN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_peer_statistic_exchange_local_ring_matches_concatenated_batch(cuda_device):
+    """The NVLink peer-memory all-reduce of the BN statistics (sfod_bn_exchange_finalize_apply), with the ranks emulated as
+    streams of ONE GPU (their inboxes are plain allocations in this process): every rank must end with the running statistics
+    and the normalised output of nn.BatchNorm2d on the concatenated batch, the exchanged totals must be bit-identical on all
+    ranks, and repeated exchanges (slot parity, device-side epoch counter) must keep working without a host reset."""
+    from sfod_b200 import modeling
+    from sfod_b200.engine.p2p import PeerStatExchange
+    from sfod_b200 import ops
+    world, C_ = 4, 48
+    tail_default = ops.BN_P2P_TAIL_PUSH
+    peers = PeerStatExchange.local_ring(world, cuda_device)
+    try:
+        g = torch.Generator().manual_seed(11)
+        streams = [torch.cuda.Stream(cuda_device) for _ in range(world)]
+        bns = [modeling.SfodBatchNorm2d(C_, process_group=peers[r]).to(cuda_device).train() for r in range(world)]
+        ref = torch.nn.BatchNorm2d(C_).train()
+        for it in range(5):                                               # odd and even epochs
+            ops.BN_P2P_TAIL_PUSH = int(it not in (2, 3))                  # payload delivered by the statistics kernel / by the finalize kernel
+            parts = [torch.randn(2 + (r == 1), C_, 20, 28, generator=g) * (r + 1) + 0.5 * r for r in range(world)]   # ragged shards
+            dparts = [p.to(cuda_device) for p in parts]
+            if it == 4:                                                   # channels-last statistics pass (delivery always by the finalize kernel)
+                dparts = [p.contiguous(memory_format=torch.channels_last) for p in dparts]
+            torch.cuda.synchronize()
+            ys = [None] * world
+            for r in range(world):
+                with torch.cuda.stream(streams[r]), torch.no_grad():
+                    ys[r] = bns[r](dparts[r], fuse_relu=(it % 2 == 1))
+            torch.cuda.synchronize()
+            with torch.no_grad():
+                yref = ref(torch.cat(parts))
+                if it % 2 == 1:
+                    yref = torch.relu(yref)
+            o = 0
+            for r in range(world):
+                n = parts[r].shape[0]
+                assert torch.allclose(ys[r].cpu(), yref[o:o + n], rtol=1e-5, atol=1e-5), (it, r)
+                o += n
+                assert torch.allclose(bns[r].running_mean.cpu(), ref.running_mean, rtol=1e-5, atol=1e-6)
+                assert torch.allclose(bns[r].running_var.cpu(), ref.running_var, rtol=1e-5)
+                assert torch.equal(bns[r].running_mean, bns[0].running_mean) and torch.equal(bns[r].running_var, bns[0].running_var)
+                assert int(bns[r].num_batches_tracked) == it + 1
+        for r in range(world):
+            assert peers[r].status() == (5, 0)                            # 5 exchanges, no timeout
+    finally:
+        ops.BN_P2P_TAIL_PUSH = tail_default
+        for p in peers:
+            p.close()
+
+
+def test_peer_statistic_exchange_single_rank_equals_plain_path(cuda_device):
+    """world = 1 degenerates to the plain two-phase BatchNorm (bit for bit)."""
+    from sfod_b200 import modeling
+    from sfod_b200.engine.p2p import PeerStatExchange
+    (peer,) = PeerStatExchange.local_ring(1, cuda_device)
+    try:
+        x = torch.randn(3, 16, 33, 41, device=cuda_device) * 2 + 1
+        a = modeling.SfodBatchNorm2d(16, process_group=peer).to(cuda_device).train()
+        b = modeling.SfodBatchNorm2d(16, process_group=True).to(cuda_device).train()   # no process group initialised: local statistics, two-phase path
+        with torch.no_grad():
+            ya, yb = a(x), b(x)
+        assert torch.equal(ya, yb) and torch.equal(a.running_mean, b.running_mean) and torch.equal(a.running_var, b.running_var)
+    finally:
+        peer.close()
+
+
+_P2P_WORKER = _NCCL_WORKER.replace("bn = modeling.SfodBatchNorm2d(32, process_group=True).cuda().train()",
+                                   "from sfod_b200.engine.p2p import PeerStatExchange\n"
+                                   "peer = PeerStatExchange.from_process_group()\n"
+                                   "bn = modeling.SfodBatchNorm2d(32, process_group=peer).cuda().train()") \
+    .replace('    print("NCCL_BN_OK")', '    print("NCCL_BN_OK")\nassert peer.status() == (1, 0)\npeer.close()')
+
+
+def test_adabn_statistic_exchange_peer_memory_two_gpus(tmp_path):
+    """The same contract as the NCCL test above for the product path: IPC-mapped inboxes of two processes on two GPUs."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_P2P_WORKER)
+    env = dict(os.environ, SFOD_ROOT=root, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29534", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "NCCL_BN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

@@ -50,6 +50,20 @@ def test_host_only_entry_points():
     assert 16000 * rec <= L.sfod_roi_align_fwd_workspace_bytes(8, 512, 18, 37, 16000, 1, 0) <= 16000 * rec + cls + 1024
     assert L.sfod_roi_align_fwd_workspace_bytes(8, 512, 18, 37, 16000, 0, 1) == 256                 # exact kernel reads NCHW directly
     assert L.sfod_bn_stats_bytes(512) >= 512 * 4 * 8
+    # peer-memory statistic exchange: inbox = header + 2 parities x 8 ranks x (2 * 2048 + 1 rounded up) 16-byte (value, tag) elements; argument checks
+    # happen before any CUDA call
+    assert L.sfod_p2p_max_channels() == 2051 and L.sfod_p2p_inbox_bytes() == 256 + 2 * 8 * 4104 * 16
+    comm = _lib.P2PComm(); comm.rank, comm.world = 0, 2
+    comm.inbox[0] = 0x1000                                                                                # inbox[1] missing
+    a = [None] * 4 + [0, 8, 64, 20, 20, 0x2000]
+    tail = [None] * 5 + [0.1, 1e-5, 0, 0, None, None, None]
+    assert L.sfod_bn_exchange_finalize_apply(*a, C.byref(comm), *tail) == 1
+    comm.inbox[1] = 0x3000; comm.world = 9
+    assert L.sfod_bn_exchange_finalize_apply(*a, C.byref(comm), *tail) == 1
+    comm.world = 2
+    a[6] = 2052                                                                                           # C beyond the payload slot
+    assert L.sfod_bn_exchange_finalize_apply(*a, C.byref(comm), *tail) == 3
+    assert L.sfod_p2p_status(C.byref(_lib.P2PComm()), None, None) == 1 and L.sfod_p2p_open(None, None) == 1
     p = _lib.RpnParams(); p.N, p.HWA, p.pre_nms_topk, p.post_nms_topk = 8, 9990, 12000, 2000
     assert L.sfod_rpn_select_workspace_bytes(C.byref(p)) > 8 * 9990 * 157 * 8
     # EMA plan: 16384-element chunks, built on the host
