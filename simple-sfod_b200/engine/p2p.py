@@ -45,9 +45,10 @@ class PeerStatExchange:
         return int(ptr.value), bytes(handle)
 
     @classmethod
-    def from_process_group(cls, group=None, device: Optional[torch.device] = None) -> "PeerStatExchange":
+    def from_process_group(cls, group=None, device: Optional[torch.device] = None, probe: bool = True) -> "PeerStatExchange":
         """Collective over ``group`` (default group when None): every rank allocates its inbox, the IPC handles travel through
-        ``all_gather_object`` and every rank maps its peers' inboxes.  All ranks must live on GPUs of one node with peer access."""
+        ``all_gather_object`` and every rank maps its peers' inboxes.  All ranks must live on GPUs of one node with peer access;
+        ``probe`` verifies that with one exchange of a known payload and raises on every rank if it does not come through."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PeerStatExchange.from_process_group needs an initialised torch.distributed process group")
@@ -71,7 +72,28 @@ class PeerStatExchange:
                 inboxes.append(int(p.value))
                 opened.append(int(p.value))
         dist.barrier(group=group)   # nobody starts exchanging before every mapping exists
-        return cls(rank, world, inboxes, device, own, opened)
+        self = cls(rank, world, inboxes, device, own, opened)
+        if probe:
+            self._probe(group)
+        return self
+
+    def _probe(self, group) -> None:
+        """One exchange of a known payload: every rank must see the sum over all ranks and no timeout, otherwise ALL ranks raise
+        (a node whose peer stores do not arrive would otherwise cost ~3 s per BN layer before anybody noticed)."""
+        import torch.distributed as dist
+        from .. import ops
+        x = torch.full((1, 4, 2, 2), float(self.rank + 1), device=self.device)
+        rm, rv = torch.zeros(4, device=self.device), torch.ones(4, device=self.device)
+        ops.bn_train_forward(x, None, None, rm, rv, None, momentum=1.0, group=self, compute_output=False)
+        _, timeouts = self.status()
+        want = (self.world + 1) / 2.0                                   # mean of 1..world
+        ok = timeouts == 0 and bool(torch.allclose(rm.cpu(), torch.full((4,), want), rtol=1e-6))
+        flag = torch.tensor([1 if ok else 0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self.close()
+            raise RuntimeError(f"PeerStatExchange: probe exchange failed on some rank (this rank: timeouts={timeouts}, "
+                               f"running_mean={rm.tolist()}, expected {want}); peer access between the GPUs of this node is not usable")
 
     @classmethod
     def local_ring(cls, world: int, device: Optional[torch.device] = None) -> List["PeerStatExchange"]:

@@ -268,7 +268,7 @@ _P2P_WORKER = _NCCL_WORKER.replace("bn = modeling.SfodBatchNorm2d(32, process_gr
                                    "from sfod_b200.engine.p2p import PeerStatExchange\n"
                                    "peer = PeerStatExchange.from_process_group()\n"
                                    "bn = modeling.SfodBatchNorm2d(32, process_group=peer).cuda().train()") \
-    .replace('    print("NCCL_BN_OK")', '    print("NCCL_BN_OK")\nassert peer.status() == (1, 0)\npeer.close()')
+    .replace('    print("NCCL_BN_OK")', '    print("NCCL_BN_OK")\nassert peer.status() == (2, 0)\npeer.close()')
 
 
 def test_adabn_statistic_exchange_peer_memory_two_gpus(tmp_path):
