@@ -56,22 +56,43 @@ class PeerStatExchange:
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         if world > _lib.P2P_MAX_RANKS:
             raise ValueError(f"PeerStatExchange supports up to {_lib.P2P_MAX_RANKS} ranks (one NVSwitch node)")
-        own, handle = cls._alloc(device, True)
-        gathered: List[Optional[bytes]] = [None] * world
-        dist.all_gather_object(gathered, handle, group=group)
+        # Every step that can fail locally is followed by a collective agreement, so that either ALL ranks obtain an endpoint or
+        # ALL ranks raise -- a rank that bailed out alone would leave its peers polling for a payload that never comes.
         L = _lib.lib()
+        own, handle, err = None, None, None
+        try:
+            own, handle = cls._alloc(device, True)
+        except Exception as e:   # noqa: BLE001 - reported to every rank below
+            err = f"rank {rank}: {type(e).__name__}: {e}"
+        gathered: List[Optional[tuple]] = [None] * world
+        dist.all_gather_object(gathered, (handle, err), group=group)
+        errors = [g[1] for g in gathered if g[1] is not None]
         inboxes, opened = [], []
-        with torch.cuda.device(device):
-            for r in range(world):
-                if r == rank:
-                    inboxes.append(own)
-                    continue
-                buf = (C.c_ubyte * _lib.P2P_HANDLE_BYTES).from_buffer_copy(gathered[r])
-                p = C.c_void_p()
-                _lib.check(L.sfod_p2p_open(buf, C.byref(p)), f"sfod_p2p_open(rank {r})")
-                inboxes.append(int(p.value))
-                opened.append(int(p.value))
-        dist.barrier(group=group)   # nobody starts exchanging before every mapping exists
+        if not errors:
+            try:
+                with torch.cuda.device(device):
+                    for r in range(world):
+                        if r == rank:
+                            inboxes.append(own)
+                            continue
+                        buf = (C.c_ubyte * _lib.P2P_HANDLE_BYTES).from_buffer_copy(gathered[r][0])
+                        p = C.c_void_p()
+                        _lib.check(L.sfod_p2p_open(buf, C.byref(p)), f"sfod_p2p_open(rank {r})")
+                        inboxes.append(int(p.value))
+                        opened.append(int(p.value))
+            except Exception as e:   # noqa: BLE001
+                err = f"rank {rank}: {type(e).__name__}: {e}"
+            gathered2: List[Optional[str]] = [None] * world
+            dist.all_gather_object(gathered2, err, group=group)   # also the barrier: nobody exchanges before every mapping exists
+            errors = [g for g in gathered2 if g is not None]
+        if errors:
+            if opened or own is not None:
+                with torch.cuda.device(device):
+                    for p in opened:
+                        L.sfod_p2p_close(p)
+                    if own is not None:
+                        L.sfod_p2p_free(own)
+            raise RuntimeError("PeerStatExchange: peer memory is not usable on this node: " + "; ".join(errors)[:500])
         self = cls(rank, world, inboxes, device, own, opened)
         if probe:
             self._probe(group)

@@ -205,6 +205,15 @@ assert (got == [{"rank": 0}, {"rank": 1}]) if rank == 0 else (got == [])
 assert comm.all_gather(rank * 10) == [0, 10]
 comm.synchronize()
 d2shim.uninstall()
+# the peer-memory exchange cannot exist without GPUs: construction must fail on EVERY rank with the same collective sequence
+# (no rank may be left waiting in a collective or, on a GPU box, polling for a payload that never comes)
+from sfod_b200.engine.p2p import PeerStatExchange
+if not torch.cuda.is_available():
+    try:
+        PeerStatExchange.from_process_group(device="cuda:0")
+        raise SystemExit("PeerStatExchange must not come up without a GPU")
+    except RuntimeError as e:
+        assert "peer memory is not usable" in str(e) and "rank 0" in str(e) and "rank 1" in str(e), str(e)
 dist.barrier()
 if rank == 0:
     print("GLOO_OK")
