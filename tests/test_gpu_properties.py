@@ -199,7 +199,8 @@ def test_adabn_statistic_allreduce_nccl_two_gpus(tmp_path):
     assert r.returncode == 0 and "NCCL_BN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
-def test_peer_statistic_exchange_local_ring_matches_concatenated_batch(cuda_device):
+@pytest.mark.parametrize("world", [3, 6])   # all 8 slots are exercised by the 8-process bench self-check (profiles/r2s_*)
+def test_peer_statistic_exchange_local_ring_matches_concatenated_batch(cuda_device, world):
     """The NVLink peer-memory all-reduce of the BN statistics (sfod_bn_exchange_finalize_apply), with the ranks emulated as
     streams of ONE GPU (their inboxes are plain allocations in this process): every rank must end with the running statistics
     and the normalised output of nn.BatchNorm2d on the concatenated batch, the exchanged totals must be bit-identical on all
@@ -207,7 +208,7 @@ def test_peer_statistic_exchange_local_ring_matches_concatenated_batch(cuda_devi
     from sfod_b200 import modeling
     from sfod_b200.engine.p2p import PeerStatExchange
     from sfod_b200 import ops
-    world, C_ = 4, 48
+    C_ = 48
     tail_default = ops.BN_P2P_TAIL_PUSH
     peers = PeerStatExchange.local_ring(world, cuda_device)
     try:
