@@ -92,7 +92,30 @@ def bench_roi(cfg, N, R_per, tv=True):
     xg = xcl.clone().requires_grad_(True)
     y = ops.roi_align(xg, rb, (7, 7), sc, 0, True)
     m, mn = time_fn(lambda: torch.autograd.grad(y, xg, g, retain_graph=True))
-    report(f"roi_align_bwd sep NHWC {cfg['name']} N={N} R={Rb}", m, mn, algb)
+    report(f"roi_align_bwd sep NHWC {cfg['name']} N={N} R={Rb}", m, mn, algb,
+           note="through torch.autograd.grad with a synchronize per iteration: includes the host's launch latency (host-bound below ~100 us)")
+    # the same C-ABI call enqueued back to back (flush, event, call, event; no synchronize in between): device time only
+    from sfod_b200 import _lib
+    L = _lib.lib()
+    gin = torch.empty((N, C, H, W), device=dev).contiguous(memory_format=torch.channels_last)
+    ws = torch.empty(L.sfod_roi_align_bwd_workspace_bytes(N, C, H, W, 1), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def call():
+        _lib.check(L.sfod_roi_align_bwd(g.data_ptr(), rb.data_ptr(), N, C, H, W, Rb, 7, 7, sc, 0, 1, gin.data_ptr(), 1, ws.data_ptr(), ws.numel(), st))
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(10):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); call(); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
+    report(f"roi_align_bwd C-ABI queued NHWC {cfg['name']} N={N} R={Rb}", ts[len(ts) // 2], ts[0], algb,
+           note="device time: flush, event, C-ABI call (memset + kernel), event enqueued back to back, no synchronize in between")
     if tv:
         xg2 = x.clone().requires_grad_(True)
         y2 = torchvision.ops.roi_align(xg2, rb, (7, 7), sc, 0, True)
