@@ -212,19 +212,25 @@ def flush_l2(dev):
 
 
 def event_time_us(fn, dev, iters=7, warmup=3):
-    """Median device time of ``fn`` in microseconds: CUDA events on the launching stream, L2 flushed before every timed call."""
+    """Median device time of ``fn`` in microseconds: CUDA events on the launching stream, L2 flushed before every timed call.
+    All iterations are enqueued behind a ~2 ms spin kernel without a synchronize in between, so the host runs ahead of the
+    device and the interval between the two events of a call holds device time only -- with a synchronize per iteration a
+    call of a few tens of microseconds is dominated by the host's launch latency (ROIAlign backward through autograd: 46 us
+    measured that way, 34 us on the device).  A ``fn`` that synchronizes internally (``ops.nms`` returns a host-sized tensor)
+    simply drains the queue and is timed as before."""
     import torch
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize(dev)
-    ts = []
+    torch.cuda._sleep(4_000_000)
+    evs = []
     for _ in range(iters):
         flush_l2(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record()
-        torch.cuda.synchronize(dev)
-        ts.append(e0.elapsed_time(e1) * 1e3)
-    ts.sort()
+        evs.append((e0, e1))
+    torch.cuda.synchronize(dev)
+    ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
     return ts[len(ts) // 2]
 
 
@@ -282,7 +288,8 @@ def named_kernel_rooflines(dev, peak, ema_plan):
         us = event_time_us(lambda: ema_plan.step(0.9996), dev)
         out["ema_multi_tensor"] = {"us": round(us, 1), "elements": int(ema_plan.numel), "alg_MB": round(12.0 * ema_plan.numel / 1e6, 1),
                                    "GBps": round(12.0 * ema_plan.numel / us / 1e3, 1), "frac": round(12.0 * ema_plan.numel / us / 1e3 / peak, 3)}
-        out["how"] = "each call timed alone: CUDA events on the launching stream, median of 7 after 3 warm-ups, 256 MB L2 flush before each"
+        out["how"] = ("each call timed alone: CUDA events on the launching stream, median of 7 after 3 warm-ups, 256 MB L2 flush before each; the 7 "
+                      "iterations are enqueued back to back behind a 2 ms spin kernel (no synchronize in between), i.e. device time without the host's launch latency")
     except Exception as e:   # a report, never a reason to lose the headline
         out["error"] = repr(e)[:300]
     return out
