@@ -384,6 +384,13 @@ int sfod_color_jitter(const uint8_t *images, int N, int H, int W, const sfod_jit
  * taps[n][0 .. 2*radius[n]]; radius_dev[n] = 0 copies the image (RandomApply miss); max_radius = max over n (<= 15). */
 int sfod_gaussian_blur(const uint8_t *images, int N, int H, int W, const float *taps_dev, const int32_t *radius_dev,
                        int max_radius, uint8_t *out, sfod_stream_t stream);
+/* Pillow's ImageFilter.GaussianBlur bit for bit -- the filter the reference actually applies (reference
+ * daod/data/transforms/augmentations.py:18-21): three extended-box-blur passes per axis in 8.24 fixed point, each rounded to
+ * uint8, edges replicated (Pillow src/libImaging/BoxBlur.c).  Per image: radius_dev[n] = integer box radius (-1: copy the image,
+ * i.e. a RandomApply miss), ww_dev[n] / fw_dev[n] = the fixed-point weights of the inner / outermost taps; the host derives all
+ * three from sigma exactly as Pillow does (simple-sfod_b200/ops.py::pil_blur_params).  max_radius = max over n (<= 9). */
+int sfod_gaussian_blur_pil(const uint8_t *images, int N, int H, int W, const int32_t *radius_dev, const uint32_t *ww_dev,
+                           const uint32_t *fw_dev, int max_radius, uint8_t *out, sfod_stream_t stream);
 typedef struct sfod_erase_params {
   int32_t n_rects;        /* 0..4 rectangles, applied in order (a later one overwrites an earlier one) */
   int32_t rect[4][4];     /* (top, left, height, width) */

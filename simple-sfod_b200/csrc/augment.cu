@@ -196,6 +196,80 @@ __global__ void __launch_bounds__(256) gauss_blur_kernel(const unsigned char *__
   }
 }
 
+// ---- PIL's ImageFilter.GaussianBlur, bit for bit.  The reference blurs with Pillow (reference daod/data/transforms/augmentations.py:18-21:
+// x.filter(ImageFilter.GaussianBlur(radius=sigma))), which is NOT a Gaussian convolution: libImaging/BoxBlur.c approximates it with
+// three passes of an "extended box blur" per axis (rows first, then columns), each pass in 8.24 fixed point and rounded to uint8:
+//   out[x] = (ww * sum_{|d| <= r} in[c(x + d)] + fw * (in[c(x - r - 1)] + in[c(x + r + 1)]) + 2^23) >> 24,   c = clamp to the line,
+// r = int(R), ww = uint32(2^24 / (2 R + 1)), fw = (2^24 - (2 r + 1) ww) / 2, R = the fractional box radius derived from sigma (host,
+// ops.pil_blur_params).  All six passes run on one shared-memory tile: 32 x 32 outputs plus a halo of 3 (r + 1) pixels per side;
+// every pass clamps in IMAGE coordinates, exactly as the line-by-line C code does, so borders are identical too.
+constexpr int kPilMaxRadius = 9;   // box radius; sigma <= ~10
+
+__global__ void __launch_bounds__(256) pil_blur_kernel(const unsigned char *__restrict__ img, const int *__restrict__ radius,
+                                                       const unsigned *__restrict__ wws, const unsigned *__restrict__ fws, int H, int W,
+                                                       unsigned char *__restrict__ out) {
+  extern __shared__ unsigned char pb_smem[];
+  const int plane = blockIdx.z;          // n * 3 + c
+  const int n = plane / 3;
+  const int r = radius[n];
+  const unsigned char *src = img + (size_t)plane * H * W;
+  unsigned char *dst = out + (size_t)plane * H * W;
+  const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+  if (r < 0) {                            // not blurred: copy
+    for (int t = threadIdx.x; t < kTile * kTile; t += 256) {
+      const int y = y0 + t / kTile, x = x0 + t % kTile;
+      if (y < H && x < W) dst[(size_t)y * W + x] = src[(size_t)y * W + x];
+    }
+    return;
+  }
+  const unsigned ww = wws[n], fw = fws[n];
+  const int h = 3 * (r + 1), TW = kTile + 2 * h;
+  unsigned char *A = pb_smem, *B = pb_smem + TW * TW;
+  const int ox = x0 - h, oy = y0 - h;     // image coordinates of tile cell (0, 0)
+  for (int t = threadIdx.x; t < TW * TW; t += 256) {
+    const int ty = t / TW, tx = t - ty * TW;
+    const int y = min(max(oy + ty, 0), H - 1), x = min(max(ox + tx, 0), W - 1);
+    A[t] = src[(size_t)y * W + x];
+  }
+  __syncthreads();
+  // three horizontal passes over every row of the tile that lies inside the image
+  for (int p = 1; p <= 3; ++p) {
+    const int lo = p * (r + 1), wid = TW - 2 * lo;
+    for (int t = threadIdx.x; t < TW * wid; t += 256) {
+      const int ty = t / wid, tx = lo + (t - ty * wid);
+      const int yi = oy + ty, xi = ox + tx;
+      if (yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
+      const unsigned char *row = A + ty * TW;
+      unsigned acc = 0;
+      for (int d = -r; d <= r; ++d) acc += row[min(max(xi + d, 0), W - 1) - ox];
+      const unsigned far = (unsigned)row[min(max(xi - r - 1, 0), W - 1) - ox] + (unsigned)row[min(max(xi + r + 1, 0), W - 1) - ox];
+      B[ty * TW + tx] = (unsigned char)((acc * ww + far * fw + (1u << 23)) >> 24);
+    }
+    __syncthreads();
+    unsigned char *tmp = A; A = B; B = tmp;
+  }
+  // three vertical passes over the output columns
+  for (int p = 1; p <= 3; ++p) {
+    const int lo = p * (r + 1), hgt = TW - 2 * lo;
+    for (int t = threadIdx.x; t < hgt * kTile; t += 256) {
+      const int ty = lo + t / kTile, tx = h + t % kTile;
+      const int yi = oy + ty, xi = ox + tx;
+      if (yi < 0 || yi >= H || xi >= W) continue;
+      unsigned acc = 0;
+      for (int d = -r; d <= r; ++d) acc += A[(min(max(yi + d, 0), H - 1) - oy) * TW + tx];
+      const unsigned far = (unsigned)A[(min(max(yi - r - 1, 0), H - 1) - oy) * TW + tx] + (unsigned)A[(min(max(yi + r + 1, 0), H - 1) - oy) * TW + tx];
+      B[ty * TW + tx] = (unsigned char)((acc * ww + far * fw + (1u << 23)) >> 24);
+    }
+    __syncthreads();
+    unsigned char *tmp = A; A = B; B = tmp;
+  }
+  for (int t = threadIdx.x; t < kTile * kTile; t += 256) {
+    const int ty = t / kTile, tx = t - ty * kTile;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y < H && x < W) dst[(size_t)y * W + x] = A[(h + ty) * TW + h + tx];
+  }
+}
+
 // ---- RandomErasing(value="random"): up to kMaxRects rectangles per image, applied in order
 constexpr int kMaxRects = 4;
 struct EraseRec { int n_rects; int rect[kMaxRects][4]; };   // (i, j, h, w) = top, left, height, width
@@ -272,6 +346,20 @@ SFOD_API int sfod_gaussian_blur(const uint8_t *images, int N, int H, int W, cons
   SFOD_CUDA_TRY(cudaFuncSetAttribute(gauss_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, N * 3);
   gauss_blur_kernel<<<grid, 256, smem, sfod_cu(stream)>>>(images, taps_dev, radius_dev, H, W, out);
+  SFOD_LAUNCH_CHECK();
+  return SFOD_OK;
+}
+
+SFOD_API int sfod_gaussian_blur_pil(const uint8_t *images, int N, int H, int W, const int32_t *radius_dev, const uint32_t *ww_dev,
+                                    const uint32_t *fw_dev, int max_radius, uint8_t *out, sfod_stream_t stream) {
+  if (N < 0 || H <= 0 || W <= 0 || max_radius < 0 || max_radius > kPilMaxRadius) return SFOD_ERR_INVALID_ARG;
+  if (N == 0) return SFOD_OK;
+  if (!images || !radius_dev || !ww_dev || !fw_dev || !out || images == out) return SFOD_ERR_INVALID_ARG;
+  const int TW = kTile + 6 * (max_radius + 1);
+  const size_t smem = 2 * (size_t)TW * TW;
+  SFOD_CUDA_TRY(cudaFuncSetAttribute(pil_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, N * 3);
+  pil_blur_kernel<<<grid, 256, smem, sfod_cu(stream)>>>(images, radius_dev, ww_dev, fw_dev, H, W, out);
   SFOD_LAUNCH_CHECK();
   return SFOD_OK;
 }

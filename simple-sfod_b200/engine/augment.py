@@ -8,7 +8,7 @@ The reference builds, per image and on the CPU (PIL), reference daod/data/detect
 
 and applies it in the data mapper (daod/data/mappers/two_crop_augmentation_mapper.py:141-157).  Here the random DECISIONS are
 drawn on the host with the same distributions and in the same order as torchvision draws them (``draw_params``), and the
-pixel work runs on the batch in HBM (``ops.color_jitter`` / ``ops.gaussian_blur`` / ``ops.random_erase_``: 4 launches per batch
+pixel work runs on the batch in HBM (``ops.color_jitter`` / ``ops.gaussian_blur_pil`` / ``ops.random_erase_``: 4 launches per batch
 instead of ~10 PIL passes per image on one CPU core).  Images are RGB uint8 (N, 3, H, W), as the mapper's PIL images are.
 """
 from __future__ import annotations
@@ -73,14 +73,20 @@ def draw_params(N: int, H: int, W: int, generator: Optional[torch.Generator] = N
 
 
 def strong_augment(images: Tensor, params: Optional[List[Dict]] = None, generator: Optional[torch.Generator] = None,
-                   noise: Optional[Tensor] = None, seed: Optional[int] = None) -> Tensor:
-    """(N, 3, H, W) uint8 RGB CUDA batch -> strongly augmented uint8 batch (a new tensor)."""
+                   noise: Optional[Tensor] = None, seed: Optional[int] = None, blur: str = "pil") -> Tensor:
+    """(N, 3, H, W) uint8 RGB CUDA batch -> strongly augmented uint8 batch (a new tensor).
+
+    ``blur="pil"`` (default) is the reference's filter, ``PIL.ImageFilter.GaussianBlur(radius=sigma)`` (reference
+    daod/data/transforms/augmentations.py:18-21) reproduced bit for bit (``ops.gaussian_blur_pil``: Pillow's three extended
+    box-blur passes per axis); ``blur="gaussian"`` is a true Gaussian convolution with torchvision's taps (``ops.gaussian_blur``)."""
+    if blur not in ("pil", "gaussian"):
+        raise ValueError("blur must be 'pil' or 'gaussian'")
     N, _, H, W = images.shape
     if params is None:
         params = draw_params(N, H, W, generator)
     x = ops.color_jitter(images, params)
     if any(p["sigma"] is not None for p in params):
-        x = ops.gaussian_blur(x, [p["sigma"] for p in params])
+        x = (ops.gaussian_blur_pil if blur == "pil" else ops.gaussian_blur)(x, [p["sigma"] for p in params])
     if any(p["rects"] for p in params):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator if generator is not None else torch.default_generator))

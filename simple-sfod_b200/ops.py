@@ -882,6 +882,51 @@ def gaussian_blur(images: Tensor, sigmas: Sequence[Optional[float]], kernel_size
     return out
 
 
+def pil_blur_params(sigma: float, passes: int = 3) -> Tuple[int, int, int]:
+    """(box radius, ww, fw) of Pillow's GaussianBlur(radius=sigma): the float32 arithmetic of ``_gaussian_blur_radius`` and
+    ``ImagingHorizontalBoxBlur`` (Pillow src/libImaging/BoxBlur.c), operation by operation."""
+    import numpy as np
+    f = np.float32
+    rad = f(sigma)
+    sigma2 = f(rad * rad / f(passes))
+    L = f(np.sqrt(12.0 * float(sigma2) + 1.0))
+    l = f(np.floor((float(L) - 1.0) / 2.0))
+    a = f(f(f(2) * l + f(1)) * f(f(l * f(l + f(1))) - f(f(3) * sigma2)))
+    a = f(a / f(f(6) * f(sigma2 - f(f(l + f(1)) * f(l + f(1))))))
+    fr = f(l + a)
+    r = int(fr)
+    ww = int(f(16777216.0) / f(fr * f(2) + f(1)))
+    fw = ((1 << 24) - (r * 2 + 1) * ww) // 2
+    return r, ww, fw
+
+
+def gaussian_blur_pil(images: Tensor, sigmas: Sequence[Optional[float]]) -> Tensor:
+    """``PIL.ImageFilter.GaussianBlur(radius=sigma)`` on a uint8 batch, bit for bit -- the blur of the reference's strong augmentation
+    (reference daod/data/transforms/augmentations.py:18-21).  ``sigmas[n] is None`` (or 0) leaves image n untouched."""
+    x, dev = _u8_batch(images)
+    N, _, H, W = x.shape
+    if len(sigmas) != N:
+        raise ValueError("one sigma (or None) per image")
+    radius, wws, fws = [-1] * N, [0] * N, [0] * N
+    for n, sg in enumerate(sigmas):
+        if sg is None or float(sg) == 0.0:
+            continue
+        if float(sg) < 0:
+            raise ValueError("sigma must be >= 0")
+        radius[n], wws[n], fws[n] = pil_blur_params(float(sg))
+        if radius[n] > 9:
+            raise ValueError("sigma too large for the fused tile kernel (box radius <= 9, sigma <= ~10)")
+    out = torch.empty_like(x)
+    if N == 0:
+        return out
+    with torch.cuda.device(dev), _timed("gaussian_blur_pil"):
+        r_dev = _small_i32(dev, radius)
+        w_dev = _small_i32(dev, wws + fws)     # both weights are < 2^24: int32 and uint32 share the bit pattern
+        check(_lib.lib().sfod_gaussian_blur_pil(x.data_ptr(), N, H, W, r_dev.data_ptr(), w_dev.data_ptr(), w_dev.data_ptr() + 4 * N,
+                                                max(max(radius), 0), out.data_ptr(), _stream(dev)), "sfod_gaussian_blur_pil")
+    return out
+
+
 def random_erase_(images: Tensor, rects: Sequence[Sequence[Tuple[int, int, int, int]]], noise: Optional[Tensor] = None, seed: int = 0) -> Tensor:
     """In place RandomErasing(value="random") on a uint8 batch: ``rects[n]`` = up to four (top, left, height, width) rectangles
     applied in order; the fill is ``byte(255 * v)`` with v ~ N(0, 1) (device generator keyed by ``seed``), or

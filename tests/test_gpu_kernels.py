@@ -918,6 +918,38 @@ def test_gaussian_blur_vs_torchvision_and_pil(ops, cuda_device):
     assert torch.equal(same[0], x[0]) and torch.equal(same[2], x[2]) and not torch.equal(same[1], x[1])
 
 
+def test_gaussian_blur_pil_bit_exact(ops, cuda_device):
+    """ops.gaussian_blur_pil == PIL.ImageFilter.GaussianBlur(radius=sigma), bit for bit: the blur of the reference's strong
+    augmentation (reference daod/data/transforms/augmentations.py:18-21).  Image sizes that are not multiples of the 32-pixel tile,
+    images narrower than the halo, the reference's sigma range and beyond, RandomApply misses; also against the CPU restatement
+    (oracle/pil_cpu.py) and through engine.strong_augment (default blur)."""
+    from PIL import Image, ImageFilter
+    from oracle import pil_cpu
+    g = torch.Generator().manual_seed(17)
+    for (H, W), sigmas in (((97, 131), [0.1, 0.77, 2.0, None, 1.3]), ((600, 1200), [1.9, None]), ((5, 7), [2.0, 0.4]), ((33, 4), [5.5, 9.7]),
+                           ((1, 40), [1.0]), ((64, 64), [0.0, 3.3])):
+        x = torch.randint(0, 256, (len(sigmas), 3, H, W), dtype=torch.uint8, generator=g)
+        got = ops.gaussian_blur_pil(x.to(cuda_device), sigmas).cpu()
+        for n, sg in enumerate(sigmas):
+            if sg is None or sg == 0.0:
+                assert torch.equal(got[n], x[n])
+                continue
+            hwc = x[n].permute(1, 2, 0).contiguous().numpy()
+            want = torch.from_numpy(np.array(Image.fromarray(hwc, "RGB").filter(ImageFilter.GaussianBlur(radius=sg)))).permute(2, 0, 1)
+            assert torch.equal(got[n], want), ((H, W), sg, int((got[n].int() - want.int()).abs().max()), int((got[n] != want).sum()))
+            if H * W <= 20000:
+                assert np.array_equal(pil_cpu.gaussian_blur(hwc, sg), want.permute(1, 2, 0).numpy())
+    with pytest.raises(ValueError):
+        ops.gaussian_blur_pil(torch.zeros(1, 3, 8, 8, dtype=torch.uint8, device=cuda_device), [40.0])
+    # the strong augmentation uses it by default
+    from sfod_b200 import engine
+    x = torch.randint(0, 256, (2, 3, 60, 90), dtype=torch.uint8, generator=g)
+    params = [{"order": [], "factors": [], "grayscale": False, "sigma": 1.25, "rects": []}, {"order": [], "factors": [], "grayscale": False, "sigma": None, "rects": []}]
+    aug = engine.strong_augment(x.to(cuda_device), params=params).cpu()
+    want = torch.from_numpy(np.array(Image.fromarray(x[0].permute(1, 2, 0).contiguous().numpy(), "RGB").filter(ImageFilter.GaussianBlur(radius=1.25)))).permute(2, 0, 1)
+    assert torch.equal(aug[0], want) and torch.equal(aug[1], x[1])
+
+
 def test_random_erase_equals_totensor_erase_topil(ops, cuda_device):
     """3 x RandomErasing(value="random") between ToTensor and ToPILImage (reference daod/data/detection_utils.py:18-33) with the
     SAME noise: bit-exact, including the wrap-around of byte(255 * v) for v outside [0, 1] and overlapping rectangles; with the
