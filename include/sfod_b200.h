@@ -380,6 +380,13 @@ typedef struct sfod_jitter_params {
  * rgb_to_grayscale), operation by operation.  workspace: N * 8 bytes.  out may alias images. */
 int sfod_color_jitter(const uint8_t *images, int N, int H, int W, const sfod_jitter_params *params_dev, void *workspace,
                       size_t workspace_bytes, uint8_t *out, sfod_stream_t stream);
+/* The same ops in PILLOW's arithmetic -- what the reference executes, because its data mapper hands PIL images to the transforms
+ * (daod/data/mappers/two_crop_augmentation_mapper.py:141-157): Image.blend against a black / mean-gray / gray degenerate image
+ * (ImageEnhance.Brightness / Contrast / Color), convert("L") = (19595 R + 38470 G + 7471 B + 0x8000) >> 16, adjust_hue through
+ * convert("HSV") with the shift byte uint8(int32(255 * hue)).  Same record layout; for a hue op `one_minus[k]` carries the shift byte
+ * (as a float), `factor[k]` is the blend alpha of the other ops.  Bit-exact against torchvision's PIL path (tests). */
+int sfod_color_jitter_pil(const uint8_t *images, int N, int H, int W, const sfod_jitter_params *params_dev, void *workspace,
+                          size_t workspace_bytes, uint8_t *out, sfod_stream_t stream);
 /* Separable Gaussian blur with reflect padding and round-half-even to uint8.  taps_dev: (N, 31) floats, image n uses
  * taps[n][0 .. 2*radius[n]]; radius_dev[n] = 0 copies the image (RandomApply miss); max_radius = max over n (<= 15). */
 int sfod_gaussian_blur(const uint8_t *images, int N, int H, int W, const float *taps_dev, const int32_t *radius_dev,

@@ -13,9 +13,11 @@
 //     _hsv2rgb :303-321, adjust_hue :196-221) operation by operation -- bit-exact, except that the image mean of the contrast
 //     op is the exact integer sum / n here and a float32 cascade sum in ATen (differs in the last ulp: a pixel can move by one
 //     level when its blend lands within 1e-5 of an integer);
-//   * Gaussian blur is a true separable Gaussian with the taps torchvision's gaussian_blur would use for the kernel size the
-//     host chooses, reflect padding, round-half-to-even to uint8 (the reference's PIL filter is a 3-pass box approximation of the
-//     same Gaussian: agreement is statistical, not bitwise; tests state both tolerances);
+//   * ... and, by default, the SAME ops in Pillow's arithmetic (jitter_pixel<true>): the reference's mapper hands PIL images to the
+//     transforms, so torchvision's PIL path (ImageEnhance / Image.convert) is what the reference executes -- bit-exact;
+//   * Gaussian blur: pil_blur_kernel reproduces Pillow's ImageFilter.GaussianBlur (three extended-box passes per axis in 8.24
+//     fixed point) bit for bit -- the reference's filter; gauss_blur_kernel is a true separable Gaussian with torchvision's taps,
+//     reflect padding, round-half-to-even to uint8 (optional);
 //   * erasing writes byte(255 * v) (v ~ N(0, 1) from a counter-based generator, or a caller-provided noise tensor) into the
 //     rectangles, which is what ToTensor -> erase(value="random") -> ToPILImage (`pic.mul(255).byte()`) leaves there.
 #include "common.cuh"
@@ -86,15 +88,88 @@ __device__ __forceinline__ void hue_shift(unsigned char &R, unsigned char &G, un
   B = (unsigned char)(int)__fmul_rn(bo, 255.999f);
 }
 
+// ---- the same ops in PILLOW's arithmetic: the reference hands PIL images to torchvision's transforms
+// (daod/data/mappers/two_crop_augmentation_mapper.py:141-157), whose PIL path is ImageEnhance / Image.convert, not the tensor
+// code above.  Restated from Pillow's libImaging (Blend.c, Convert.c) and torchvision/transforms/_functional_pil.py and pinned
+// against the installed Pillow (oracle/pil_cpu.py, tests): bit-exact.
+//   convert("L"):   L = (19595 R + 38470 G + 7471 B + 0x8000) >> 16
+//   Image.blend(degenerate, image, alpha): (UINT8)(float)(deg + alpha * (img - deg)), clipped to [0, 255] when alpha is outside [0, 1]
+//   Brightness: degenerate = 0;  Contrast: degenerate = int(mean(L) + 0.5);  Color (saturation): degenerate = L
+//   adjust_hue: convert("HSV") (colorsys in float / double, see below), h += uint8(int32(255 hue)) mod 256, convert back
+__device__ __forceinline__ unsigned char pil_L(unsigned char r, unsigned char g, unsigned char b) {
+  return (unsigned char)((r * 19595u + g * 38470u + b * 7471u + 0x8000u) >> 16);
+}
+__device__ __forceinline__ unsigned char pil_blend(int deg, unsigned char img, float alpha) {
+  const float t = __fadd_rn((float)deg, __fmul_rn(alpha, (float)((int)img - deg)));
+  if (alpha >= 0.0f && alpha <= 1.0f) return (unsigned char)(int)t;
+  return t <= 0.0f ? (unsigned char)0 : t >= 255.0f ? (unsigned char)255 : (unsigned char)(int)t;
+}
+__device__ __forceinline__ int clip8(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+__device__ __forceinline__ void pil_hue_shift(unsigned char &R, unsigned char &G, unsigned char &B, int shift) {
+  // rgb2hsv_row (Convert.c): float h, s, rc, gc, bc, cr; the literals 2.0 / 4.0 / 6.0 / 255.0 are doubles
+  const int r = R, g = G, b = B;
+  const int maxc = max(r, max(g, b)), minc = min(r, min(g, b));
+  int uh = 0, us = 0;
+  const int uv = maxc;
+  if (minc != maxc) {
+    const float cr = (float)(maxc - minc);
+    const float s = __fdiv_rn(cr, (float)maxc);
+    const float rc = __fdiv_rn((float)(maxc - r), cr), gc = __fdiv_rn((float)(maxc - g), cr), bc = __fdiv_rn((float)(maxc - b), cr);
+    float h;
+    if (r == maxc) h = __fsub_rn(bc, gc);
+    else if (g == maxc) h = (float)(__dsub_rn(__dadd_rn(2.0, (double)rc), (double)bc));
+    else h = (float)(__dsub_rn(__dadd_rn(4.0, (double)gc), (double)rc));
+    const double hd = __dadd_rn(__ddiv_rn((double)h, 6.0), 1.0);
+    h = (float)(hd - floor(hd));                                   // fmod(x, 1.0) for x in (0, 2): exact
+    uh = clip8((int)__dmul_rn((double)h, 255.0));
+    us = clip8((int)__dmul_rn((double)s, 255.0));
+  }
+  uh = (uh + shift) & 255;
+  // hsv2rgb (Convert.c)
+  if (us == 0) { R = G = B = (unsigned char)uv; return; }
+  const double h6 = __ddiv_rn(__dmul_rn((double)(float)uh, 6.0), 255.0);
+  const int i = (int)floor(h6);
+  const float f = (float)__dsub_rn(h6, (double)(float)i);
+  const float fs = (float)__ddiv_rn((double)(float)us, 255.0);
+  const double v = (double)(float)uv;
+  const int pp = clip8((int)round(__dmul_rn(v, __dsub_rn(1.0, (double)fs))));
+  const int qq = clip8((int)round(__dmul_rn(v, __dsub_rn(1.0, __dmul_rn((double)fs, (double)f)))));
+  const int tt = clip8((int)round(__dmul_rn(v, __dsub_rn(1.0, __dmul_rn((double)fs, __dsub_rn(1.0, (double)f))))));
+  int ro, go, bo;
+  switch (i % 6) {
+    case 0: ro = uv; go = tt; bo = pp; break;
+    case 1: ro = qq; go = uv; bo = pp; break;
+    case 2: ro = pp; go = uv; bo = tt; break;
+    case 3: ro = pp; go = qq; bo = uv; break;
+    case 4: ro = tt; go = pp; bo = uv; break;
+    default: ro = uv; go = pp; bo = qq; break;
+  }
+  R = (unsigned char)ro; G = (unsigned char)go; B = (unsigned char)bo;
+}
+
+template <bool kPil>
+__device__ __forceinline__ unsigned char gray_of(unsigned char r, unsigned char g, unsigned char b) { return kPil ? pil_L(r, g, b) : gray_u8(r, g, b); }
+
 // applies ops [0, upto) of the record to one pixel; `mean` = gray mean of the image at the point where contrast is applied
+// (kPil: the integer int(mean + 0.5); the hue record carries the shift byte in one_minus)
+template <bool kPil>
 __device__ __forceinline__ void jitter_pixel(const JitterRec &p, int upto, float mean, unsigned char &r, unsigned char &g, unsigned char &b) {
   for (int k = 0; k < upto; ++k) {
     const float f = p.factor[k], om = p.one_minus[k];
-    switch (p.op[k]) {
-      case kOpBrightness: r = blend_u8(r, 0.0f, f, om); g = blend_u8(g, 0.0f, f, om); b = blend_u8(b, 0.0f, f, om); break;
-      case kOpContrast: r = blend_u8(r, mean, f, om); g = blend_u8(g, mean, f, om); b = blend_u8(b, mean, f, om); break;
-      case kOpSaturation: { const float l = u8f(gray_u8(r, g, b)); r = blend_u8(r, l, f, om); g = blend_u8(g, l, f, om); b = blend_u8(b, l, f, om); break; }
-      default: hue_shift(r, g, b, f); break;
+    if (kPil) {
+      switch (p.op[k]) {
+        case kOpBrightness: r = pil_blend(0, r, f); g = pil_blend(0, g, f); b = pil_blend(0, b, f); break;
+        case kOpContrast: { const int m = (int)mean; r = pil_blend(m, r, f); g = pil_blend(m, g, f); b = pil_blend(m, b, f); break; }
+        case kOpSaturation: { const int l = pil_L(r, g, b); r = pil_blend(l, r, f); g = pil_blend(l, g, f); b = pil_blend(l, b, f); break; }
+        default: pil_hue_shift(r, g, b, (int)om); break;
+      }
+    } else {
+      switch (p.op[k]) {
+        case kOpBrightness: r = blend_u8(r, 0.0f, f, om); g = blend_u8(g, 0.0f, f, om); b = blend_u8(b, 0.0f, f, om); break;
+        case kOpContrast: r = blend_u8(r, mean, f, om); g = blend_u8(g, mean, f, om); b = blend_u8(b, mean, f, om); break;
+        case kOpSaturation: { const float l = u8f(gray_u8(r, g, b)); r = blend_u8(r, l, f, om); g = blend_u8(g, l, f, om); b = blend_u8(b, l, f, om); break; }
+        default: hue_shift(r, g, b, f); break;
+      }
     }
   }
 }
@@ -105,6 +180,7 @@ __device__ __forceinline__ int contrast_pos(const JitterRec &p) {
 }
 
 // pass A: sum of the gray levels of every image at the point where its contrast op applies (exact integer sum)
+template <bool kPil>
 __global__ void __launch_bounds__(kJThreads) jitter_gray_sum_kernel(const unsigned char *__restrict__ img, const JitterRec *__restrict__ recs,
                                                                     int HW, unsigned long long *__restrict__ sums) {
   const int n = blockIdx.y;
@@ -115,27 +191,30 @@ __global__ void __launch_bounds__(kJThreads) jitter_gray_sum_kernel(const unsign
   unsigned int local = 0;
   for (int i = blockIdx.x * kJThreads + threadIdx.x; i < HW; i += gridDim.x * kJThreads) {
     unsigned char r = R[i], g = G[i], b = B[i];
-    jitter_pixel(p, cp, 0.0f, r, g, b);
-    local += gray_u8(r, g, b);
+    jitter_pixel<kPil>(p, cp, 0.0f, r, g, b);
+    local += gray_of<kPil>(r, g, b);
   }
   local = __reduce_add_sync(0xFFFFFFFFu, local);
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(sums + n, (unsigned long long)local);
 }
 
 // pass B: the whole op sequence (+ RandomGrayscale) per pixel
+template <bool kPil>
 __global__ void __launch_bounds__(kJThreads) jitter_apply_kernel(const unsigned char *__restrict__ img, const JitterRec *__restrict__ recs,
                                                                  const unsigned long long *__restrict__ sums, int HW,
                                                                  unsigned char *__restrict__ out) {
   const int n = blockIdx.y;
   const JitterRec p = recs[n];
   // torch.mean of the float32 gray image; here: exact sum / n rounded once
-  const float mean = contrast_pos(p) >= 0 ? (float)((double)sums[n] / (double)HW) : 0.0f;
+  // (kPil: ImageStat mean = sum / count as a Python float, then int(mean + 0.5))
+  const double dmean = contrast_pos(p) >= 0 ? (double)sums[n] / (double)HW : 0.0;
+  const float mean = kPil ? (float)(int)(dmean + 0.5) : (float)dmean;
   const unsigned char *R = img + (size_t)n * 3 * HW, *G = R + HW, *B = G + HW;
   unsigned char *Ro = out + (size_t)n * 3 * HW, *Go = Ro + HW, *Bo = Go + HW;
   for (int i = blockIdx.x * kJThreads + threadIdx.x; i < HW; i += gridDim.x * kJThreads) {
     unsigned char r = R[i], g = G[i], b = B[i];
-    jitter_pixel(p, p.n_ops, mean, r, g, b);
-    if (p.grayscale) { const unsigned char l = gray_u8(r, g, b); r = g = b = l; }
+    jitter_pixel<kPil>(p, p.n_ops, mean, r, g, b);
+    if (p.grayscale) { const unsigned char l = gray_of<kPil>(r, g, b); r = g = b = l; }
     Ro[i] = r; Go[i] = g; Bo[i] = b;
   }
 }
@@ -315,8 +394,8 @@ __global__ void __launch_bounds__(256) erase_kernel(unsigned char *__restrict__ 
 }  // namespace
 
 // =========================================================================== C ABI
-SFOD_API int sfod_color_jitter(const uint8_t *images, int N, int H, int W, const sfod_jitter_params *params_dev, void *workspace,
-                               size_t workspace_bytes, uint8_t *out, sfod_stream_t stream) {
+static int color_jitter_impl(bool pil, const uint8_t *images, int N, int H, int W, const sfod_jitter_params *params_dev, void *workspace,
+                             size_t workspace_bytes, uint8_t *out, sfod_stream_t stream) {
   static_assert(sizeof(sfod_jitter_params) == sizeof(JitterRec), "parameter record layout");
   if (N < 0 || H <= 0 || W <= 0) return SFOD_ERR_INVALID_ARG;
   if (N == 0) return SFOD_OK;
@@ -328,11 +407,23 @@ SFOD_API int sfod_color_jitter(const uint8_t *images, int N, int H, int W, const
   const int HW = H * W;
   const unsigned gx = (unsigned)min(SFOD_NUM_SMS * 2, (HW + kJThreads - 1) / kJThreads);
   const JitterRec *recs = reinterpret_cast<const JitterRec *>(params_dev);
-  jitter_gray_sum_kernel<<<dim3(gx, N), kJThreads, 0, st>>>(images, recs, HW, sums);
+  if (pil) jitter_gray_sum_kernel<true><<<dim3(gx, N), kJThreads, 0, st>>>(images, recs, HW, sums);
+  else jitter_gray_sum_kernel<false><<<dim3(gx, N), kJThreads, 0, st>>>(images, recs, HW, sums);
   SFOD_LAUNCH_CHECK();
-  jitter_apply_kernel<<<dim3(gx, N), kJThreads, 0, st>>>(images, recs, sums, HW, out);
+  if (pil) jitter_apply_kernel<true><<<dim3(gx, N), kJThreads, 0, st>>>(images, recs, sums, HW, out);
+  else jitter_apply_kernel<false><<<dim3(gx, N), kJThreads, 0, st>>>(images, recs, sums, HW, out);
   SFOD_LAUNCH_CHECK();
   return SFOD_OK;
+}
+
+SFOD_API int sfod_color_jitter(const uint8_t *images, int N, int H, int W, const sfod_jitter_params *params_dev, void *workspace,
+                               size_t workspace_bytes, uint8_t *out, sfod_stream_t stream) {
+  return color_jitter_impl(false, images, N, H, W, params_dev, workspace, workspace_bytes, out, stream);
+}
+
+SFOD_API int sfod_color_jitter_pil(const uint8_t *images, int N, int H, int W, const sfod_jitter_params *params_dev, void *workspace,
+                                   size_t workspace_bytes, uint8_t *out, sfod_stream_t stream) {
+  return color_jitter_impl(true, images, N, H, W, params_dev, workspace, workspace_bytes, out, stream);
 }
 
 SFOD_API int sfod_gaussian_blur(const uint8_t *images, int N, int H, int W, const float *taps_dev, const int32_t *radius_dev,

@@ -73,8 +73,12 @@ def draw_params(N: int, H: int, W: int, generator: Optional[torch.Generator] = N
 
 
 def strong_augment(images: Tensor, params: Optional[List[Dict]] = None, generator: Optional[torch.Generator] = None,
-                   noise: Optional[Tensor] = None, seed: Optional[int] = None, blur: str = "pil") -> Tensor:
+                   noise: Optional[Tensor] = None, seed: Optional[int] = None, blur: str = "pil", arithmetic: str = "pil") -> Tensor:
     """(N, 3, H, W) uint8 RGB CUDA batch -> strongly augmented uint8 batch (a new tensor).
+
+    ``arithmetic="pil"`` (default): ColorJitter / RandomGrayscale in Pillow's arithmetic (torchvision's PIL path, which the
+    reference's mapper takes: daod/data/mappers/two_crop_augmentation_mapper.py:141-157), bit for bit; ``"tensor"``: torchvision's
+    uint8-tensor arithmetic.
 
     ``blur="pil"`` (default) is the reference's filter, ``PIL.ImageFilter.GaussianBlur(radius=sigma)`` (reference
     daod/data/transforms/augmentations.py:18-21) reproduced bit for bit (``ops.gaussian_blur_pil``: Pillow's three extended
@@ -84,7 +88,7 @@ def strong_augment(images: Tensor, params: Optional[List[Dict]] = None, generato
     N, _, H, W = images.shape
     if params is None:
         params = draw_params(N, H, W, generator)
-    x = ops.color_jitter(images, params)
+    x = ops.color_jitter(images, params, arithmetic=arithmetic)
     if any(p["sigma"] is not None for p in params):
         x = (ops.gaussian_blur_pil if blur == "pil" else ops.gaussian_blur)(x, [p["sigma"] for p in params])
     if any(p["rects"] for p in params):

@@ -819,10 +819,15 @@ def _struct_array_to_device(arr, dev: torch.device) -> Tensor:
     return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
 
 
-def color_jitter(images: Tensor, params: Sequence[dict]) -> Tensor:
+def color_jitter(images: Tensor, params: Sequence[dict], arithmetic: str = "tensor") -> Tensor:
     """torchvision ColorJitter (+ RandomGrayscale) on a uint8 batch with per-image decisions ``params[n] = dict(order=[...],
     factors=[...], grayscale=bool)``: ``order`` lists op codes (0 brightness, 1 contrast, 2 saturation, 3 hue) in application
-    order with their ``factors`` (Python floats); an empty order = jitter not applied."""
+    order with their ``factors`` (Python floats); an empty order = jitter not applied.  ``arithmetic="tensor"`` follows
+    torchvision's uint8-tensor code, ``"pil"`` follows its PIL path (ImageEnhance / Image.convert: what the reference runs, since its
+    mapper feeds PIL images) -- both bit for bit."""
+    if arithmetic not in ("tensor", "pil"):
+        raise ValueError("arithmetic must be 'tensor' or 'pil'")
+    pil = arithmetic == "pil"
     x, dev = _u8_batch(images)
     N, _, H, W = x.shape
     if len(params) != N:
@@ -835,6 +840,10 @@ def color_jitter(images: Tensor, params: Sequence[dict]) -> Tensor:
         arr[n].n_ops = len(order)
         for k, (o, f) in enumerate(zip(order, fac)):
             arr[n].op[k], arr[n].factor[k], arr[n].one_minus[k] = int(o), float(f), 1.0 - float(f)
+            if pil and int(o) == 3:
+                if not -0.5 <= float(f) <= 0.5:
+                    raise ValueError("hue factor must lie in [-0.5, 0.5]")
+                arr[n].one_minus[k] = float(int(float(f) * 255) & 0xFF)   # np.int32(hue * 255).astype(np.uint8) of torchvision's PIL path
         arr[n].grayscale = int(bool(p.get("grayscale", False)))
     out = torch.empty_like(x)
     if N == 0:
@@ -842,8 +851,8 @@ def color_jitter(images: Tensor, params: Sequence[dict]) -> Tensor:
     with torch.cuda.device(dev), _timed("color_jitter"):
         rec = _struct_array_to_device(arr, dev)
         ws = _workspace(dev, "jitter", 8 * N)
-        check(_lib.lib().sfod_color_jitter(x.data_ptr(), N, H, W, rec.data_ptr(), ws.data_ptr(), ws.numel(), out.data_ptr(), _stream(dev)),
-              "sfod_color_jitter")
+        fn = _lib.lib().sfod_color_jitter_pil if pil else _lib.lib().sfod_color_jitter
+        check(fn(x.data_ptr(), N, H, W, rec.data_ptr(), ws.data_ptr(), ws.numel(), out.data_ptr(), _stream(dev)), "sfod_color_jitter")
     return out
 
 

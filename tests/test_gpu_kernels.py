@@ -889,6 +889,38 @@ def test_color_jitter_equals_torchvision_tensor_ops(ops, cuda_device):
                 assert diff.max() == 0, (p, int(diff.max()), int((diff > 0).sum()))
 
 
+def test_color_jitter_pil_arithmetic_bit_exact(ops, cuda_device):
+    """The same decisions through torchvision's PIL path -- what the reference executes, because its mapper hands PIL images to
+    the transforms (reference daod/data/mappers/two_crop_augmentation_mapper.py:141-157): ImageEnhance.Brightness / Contrast /
+    Color (Image.blend), convert("L"), convert("HSV").  ops.color_jitter(arithmetic="pil") is bit-equal, for every op alone at the
+    extreme factors (incl. hue +-0.5 and factors outside [0, 1], where Image.blend clips) and for full random sequences with
+    RandomGrayscale; also bit-equal to the CPU restatement (oracle/pil_cpu.py)."""
+    from PIL import Image
+    from oracle import pil_cpu
+    x = _aug_images(3, 97, 131, 21)
+    x[2] = (x[2] // 12 + 100)                                     # low-contrast image: contrast / saturation extrapolation clips
+    g = torch.Generator().manual_seed(4)
+    recs = []
+    for o in range(4):
+        lo, hi = [(0.6, 1.4), (0.6, 1.4), (0.6, 1.4), (-0.1, 0.1)][o]
+        for f in (lo, hi, (lo + hi) / 2 + 0.0123) + ((0.0, 1.0, 2.5) if o < 3 else (-0.5, 0.5, 0.0)):
+            recs.append(dict(order=[o], factors=[f]))
+    for _ in range(15):
+        order = torch.randperm(4, generator=g).tolist()
+        vals = [float(torch.empty(1).uniform_(0.6, 1.4, generator=g)) for _ in range(3)] + [float(torch.empty(1).uniform_(-0.1, 0.1, generator=g))]
+        recs.append(dict(order=order, factors=[vals[k] for k in order], grayscale=bool(torch.rand(1, generator=g) < 0.3)))
+    recs += [dict(order=[], factors=[], grayscale=True), dict(order=[], factors=[])]
+    for r0 in range(0, len(recs), 3):
+        batch = recs[r0:r0 + 3]
+        imgs = x[:len(batch)]
+        got = ops.color_jitter(imgs.to(cuda_device), batch, arithmetic="pil").cpu()
+        for n, p in enumerate(batch):
+            hwc = imgs[n].permute(1, 2, 0).contiguous().numpy()
+            want = torch.from_numpy(np.array(_tv_jitter(Image.fromarray(hwc, "RGB"), p))).permute(2, 0, 1)
+            assert torch.equal(got[n], want), (p, int((got[n].int() - want.int()).abs().max()), int((got[n] != want).sum()))
+            assert np.array_equal(pil_cpu.color_jitter(hwc, p["order"], p["factors"], bool(p.get("grayscale"))), want.permute(1, 2, 0).numpy())
+
+
 def test_gaussian_blur_vs_torchvision_and_pil(ops, cuda_device):
     """GaussianBlur((0.1, 2.0)) of reference daod/data/transforms/augmentations.py:6-21 (PIL ImageFilter.GaussianBlur(radius=sigma)).
     Parity definition: (a) against torchvision's tensor gaussian_blur with the same kernel size and sigma (a true Gaussian, reflect
@@ -977,6 +1009,35 @@ def test_random_erase_equals_totensor_erase_topil(ops, cuda_device):
     assert abs(fill.mean().item() - 127.5) < 4 and 65 < fill.std().item() < 82             # ~uniform bytes
     again = ops.random_erase_(x.clone().to(cuda_device), rects, seed=1234).cpu()
     assert torch.equal(again, dev)                                                           # counter-based: reproducible
+
+
+def test_strong_augment_equals_the_reference_chain_on_pil_images(cuda_device):
+    """The WHOLE strong augmentation of reference daod/data/detection_utils.py:7-37 as its mapper runs it
+    (two_crop_augmentation_mapper.py:141-157: PIL image in, PIL image out) -- ColorJitter ops in the drawn order and
+    RandomGrayscale on the PIL image, PIL GaussianBlur(radius=sigma), ToTensor, the RandomErasing rectangles filled with the
+    drawn noise, ToPILImage -- against engine.strong_augment with the SAME decisions and noise: bit-equal for every image of a
+    batch drawn with the reference's probabilities (seeded until every branch occurs)."""
+    import torchvision.transforms.functional as TF
+    from PIL import Image, ImageFilter
+    from sfod_b200 import engine
+    N, H, W = 12, 96, 160
+    x = _aug_images(N, H, W, 31)
+    g = torch.Generator().manual_seed(2025)
+    params = engine.draw_strong_augmentation_params(N, H, W, g)
+    assert any(p["order"] for p in params) and any(p["grayscale"] for p in params) and any(p["sigma"] is not None for p in params)
+    assert any(len(p["rects"]) >= 2 for p in params) and any(not p["order"] for p in params)
+    noise = torch.randn(N, 4, 3, H, W, generator=g)
+    got = engine.strong_augment(x.to(cuda_device), params=params, noise=noise.to(cuda_device)).cpu()
+    for n, p in enumerate(params):
+        img = Image.fromarray(x[n].permute(1, 2, 0).contiguous().numpy(), "RGB")
+        img = _tv_jitter(img, p)                                                             # ColorJitter + RandomGrayscale (PIL path)
+        if p["sigma"] is not None:
+            img = img.filter(ImageFilter.GaussianBlur(radius=p["sigma"]))                   # reference augmentations.py:18-21
+        t = TF.to_tensor(img)
+        for k, (i, j, h, w) in enumerate(p["rects"]):
+            t = TF.erase(t, i, j, h, w, noise[n, k, :, i:i + h, j:j + w])
+        want = torch.from_numpy(np.array(TF.to_pil_image(t))).permute(2, 0, 1)
+        assert torch.equal(got[n], want), (n, p, int((got[n] != want).sum()))
 
 
 def test_strong_augment_pipeline(cuda_device):
