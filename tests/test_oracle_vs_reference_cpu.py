@@ -329,3 +329,36 @@ def test_oracle_reproduces_reference_executed_fixture(gold):
     dets = [dict(scores=t(f"frcnn_{i}_out_scores"), pred_classes=t(f"frcnn_{i}_out_pred_classes")) for i in range(n_img)]
     assert torch.equal(o.count_label_prediction(dets, 8, 0.8), t("reserve_count"))
     assert torch.equal(o.update_adaptive_threshold(t("reserve_matrix").clone()), t("classwise_acc_new"))
+
+
+@needs_reference
+def test_prediction_to_gt_equals_the_reference_script_executed(tmp_path):
+    """the reference converts detections into the fixed-pseudo-label annotation file with a SCRIPT
+    (cityscapes-to-coco-conversion/prediction_to_gt.py).  The script's own text is executed here with its three hard-coded paths
+    redirected to temporary files (nothing is copied), and the json it writes must equal engine.prediction_to_gt's, entry by
+    entry -- including the `score < 0.7` boundary, the running ids and the untouched rest of the dataset dict."""
+    import json
+    import re
+    from sfod_b200 import engine
+    src_path = os.path.join(ref_exec.REF_ROOT if hasattr(ref_exec, "REF_ROOT") else "/root/reference", "cityscapes-to-coco-conversion", "prediction_to_gt.py")
+    src = open(src_path).read()
+    rng = np.random.default_rng(5)
+    preds = [{"image_id": int(rng.integers(1, 40)), "bbox": [float(v) for v in rng.uniform(0, 500, 4).round(2)],
+              "category_id": int(rng.integers(1, 9)), "score": float(s)}
+             for s in list(rng.uniform(0.05, 1.0, 300)) + [0.7, 0.7000000001, 0.6999999999]]
+    dataset = {"images": [{"id": i, "file_name": f"{i}.png", "height": 600, "width": 1200} for i in range(1, 40)],
+               "categories": [{"id": k, "name": f"c{k}"} for k in range(1, 9)], "annotations": [{"id": 99, "old": True}], "info": {"x": 1}}
+    p_in, d_in, out = tmp_path / "preds.json", tmp_path / "dataset.json", tmp_path / "out.json"
+    p_in.write_text(json.dumps(preds)); d_in.write_text(json.dumps(dataset))
+    # the uncommented open() calls, in order: predictions (read), dataset (read), output (write)
+    paths = iter([str(p_in), str(d_in), str(out)])
+    lines = []
+    for line in src.splitlines():
+        if not line.lstrip().startswith("#") and "open(" in line:
+            line = re.sub(r"open\('[^']*'", lambda m: "open(%r" % next(paths), line, count=1)
+        lines.append(line)
+    exec(compile("\n".join(lines), src_path, "exec"), {"__name__": "__ref_script__"})
+    want = json.loads(out.read_text())
+    got = engine.prediction_to_gt(preds, dataset, 0.7)
+    assert got == want and len(want["annotations"]) == sum(p["score"] >= 0.7 for p in preds) and want["annotations"][0]["id"] == 1
+    assert want["images"] == dataset["images"] and want["info"] == dataset["info"]
