@@ -129,7 +129,10 @@ int sfod_nms(const float *boxes, const float *scores, const int64_t *idxs, int64
  *   drop non-finite (counted in invalid_count_dev; d2 raises in training), clip to (h,w),
  *   drop boxes with w <= min_box_size or h <= min_box_size; greedy NMS (iou_threshold);
  *   first post_nms_topk survivors.
- * logits (N,HWA) and deltas (N,HWA,4) are the flattened head outputs of rpn.py:28-41.
+ * head_layout 0: logits (N,HWA) and deltas (N,HWA,4) are the flattened head outputs of rpn.py:28-41.
+ * head_layout 1: logits (N,A,Hf,Wf) and deltas (N,4A,Hf,Wf) are the RPN head's convolution outputs AS THEY LIE (what
+ *   rpn.py:28-41 permutes and copies): the flatten is folded into the key build and the top-k gather, indices
+ *   (out_src_index, anchors) keep the flattened (Hf,Wf,A) numbering.  Needs A, Hf, Wf (also with an anchor tensor).
  * anchors: (HWA,4) device tensor, or NULL to recompute d2's DefaultAnchorGenerator grid in
  * closed form from cell_anchors (A,4) host floats, feature size (Hf,Wf), stride and offset.
  * image_hw_dev: (N,2) int32 device [h, w].
@@ -144,6 +147,7 @@ typedef struct sfod_rpn_params {
   float min_box_size;
   double nms_thresh;
   float cell_anchors[64 * 4]; /* up to 64 cell anchors, used when anchors == NULL */
+  int head_layout;            /* 0: flattened (N,HWA) / (N,HWA,4); 1: head outputs (N,A,Hf,Wf) / (N,4A,Hf,Wf) */
 } sfod_rpn_params;
 
 size_t sfod_rpn_select_workspace_bytes(const sfod_rpn_params *p);

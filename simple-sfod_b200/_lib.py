@@ -36,7 +36,7 @@ class RpnParams(C.Structure):
     _fields_ = [("N", C.c_int), ("HWA", C.c_int), ("A", C.c_int), ("Hf", C.c_int), ("Wf", C.c_int), ("stride", C.c_int),
                 ("anchor_offset", C.c_float), ("weights", C.c_float * 4), ("scale_clamp", C.c_float),
                 ("pre_nms_topk", C.c_int), ("post_nms_topk", C.c_int), ("min_box_size", C.c_float),
-                ("nms_thresh", C.c_double), ("cell_anchors", C.c_float * 256)]
+                ("nms_thresh", C.c_double), ("cell_anchors", C.c_float * 256), ("head_layout", C.c_int)]
 
 
 class FrcnnParams(C.Structure):

@@ -140,7 +140,10 @@ SFOD_API int sfod_rpn_select(const sfod_rpn_params *p, const float *logits, cons
   if (p->N <= 0 || p->HWA <= 0 || p->pre_nms_topk <= 0 || p->post_nms_topk <= 0) return SFOD_ERR_INVALID_ARG;
   if (!anchors && (p->A <= 0 || p->A > 64 || p->Hf <= 0 || p->Wf <= 0 || p->Hf * p->Wf * p->A != p->HWA))
     return SFOD_ERR_INVALID_ARG;
-  if (!sfod_aligned16(deltas) || !sfod_aligned16(out_boxes) || (anchors && !sfod_aligned16(anchors))) return SFOD_ERR_ALIGNMENT;
+  const bool native = p->head_layout == 1;
+  if (p->head_layout != 0 && p->head_layout != 1) return SFOD_ERR_INVALID_ARG;
+  if (native && (p->A <= 0 || p->Hf <= 0 || p->Wf <= 0 || (long long)p->Hf * p->Wf * p->A != p->HWA)) return SFOD_ERR_INVALID_ARG;
+  if ((!native && !sfod_aligned16(deltas)) || !sfod_aligned16(out_boxes) || (anchors && !sfod_aligned16(anchors))) return SFOD_ERR_ALIGNMENT;
   cudaStream_t st = sfod_cu(stream);
   SfodWs ws(workspace, workspace_bytes); rpnk::Plan pl; rpnk::Buffers b;
   rpnk::carve(ws, p, pl, &b);
@@ -148,16 +151,18 @@ SFOD_API int sfod_rpn_select(const sfod_rpn_params *p, const float *logits, cons
   const int N = p->N;
   {
     dim3 grid((pl.P + 255) / 256, N);
-    rpnk::rpn_make_keys_kernel<<<grid, 256, 0, st>>>(logits, p->HWA, pl.P, b.keys);
+    if (native) rpnk::rpn_make_keys_kernel<true><<<grid, 256, 0, st>>>(logits, p->HWA, pl.P, p->A, p->Hf * p->Wf, b.keys);
+    else rpnk::rpn_make_keys_kernel<false><<<grid, 256, 0, st>>>(logits, p->HWA, pl.P, 1, p->HWA, b.keys);
     SFOD_LAUNCH_CHECK();
   }
   int rc = bsort::segmented_sort(b.keys, N, pl.P, st);
   if (rc) return rc;
   rpnk::CellAnchors cell;
   for (int i = 0; i < 64 * 4; ++i) cell.v[i] = p->cell_anchors[i];
-  rpnk::rpn_decode_compact_kernel<<<N, rpnk::kDecodeThreads, 0, st>>>(
-      b.keys, pl.P, logits, reinterpret_cast<const float4 *>(deltas), reinterpret_cast<const float4 *>(anchors), cell,
-      p->HWA, p->A, p->Wf, p->stride, p->anchor_offset, p->weights[0], p->weights[1], p->weights[2], p->weights[3],
+  auto decode = native ? rpnk::rpn_decode_compact_kernel<true> : rpnk::rpn_decode_compact_kernel<false>;
+  decode<<<N, rpnk::kDecodeThreads, 0, st>>>(
+      b.keys, pl.P, logits, deltas, reinterpret_cast<const float4 *>(anchors), cell,
+      p->HWA, p->A, p->Wf, p->Hf * p->Wf, p->stride, p->anchor_offset, p->weights[0], p->weights[1], p->weights[2], p->weights[3],
       p->scale_clamp, pl.topk, p->min_box_size, image_hw_dev, b.sboxes, b.sscores, b.ssrc, b.segs, invalid_count_dev);
   SFOD_LAUNCH_CHECK();
   rc = nmsk::run_segmented(b.sboxes, nullptr, b.segs, N, pl.topk, pl.topk, pl.wstride, p->nms_thresh, p->post_nms_topk,

@@ -12,7 +12,11 @@ namespace rpnk {
 struct CellAnchors { float v[64 * 4]; };
 
 // key = (~score_key << 32) | flat_anchor_index : ascending key order == score descending, index ascending.
-__global__ void __launch_bounds__(256) rpn_make_keys_kernel(const float *__restrict__ logits, int HWA, int P,
+// kNative: the logits lie as the head wrote them, (N, A, Hf*Wf); slot j = a * HW + pos is read coalesced and carries the
+// FLATTENED index pos * A + a in its key (the sort does not care where a key starts), so the permute copy of
+// reference rpn.py:28-33 is never made.
+template <bool kNative>
+__global__ void __launch_bounds__(256) rpn_make_keys_kernel(const float *__restrict__ logits, int HWA, int P, int A, int HW,
                                                             unsigned long long *__restrict__ keys) {
   const int n = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -20,7 +24,8 @@ __global__ void __launch_bounds__(256) rpn_make_keys_kernel(const float *__restr
   unsigned long long k = bsort::kSentinel;
   if (i < HWA) {
     const float s = logits[(size_t)n * HWA + i];
-    k = ((unsigned long long)(~sfod_score_key(s)) << 32) | (unsigned)i;
+    const unsigned flat = kNative ? (unsigned)((i % HW) * A + i / HW) : (unsigned)i;
+    k = ((unsigned long long)(~sfod_score_key(s)) << 32) | flat;
   }
   keys[(size_t)n * P + i] = k;
 }
@@ -31,9 +36,12 @@ __global__ void __launch_bounds__(256) rpn_make_keys_kernel(const float *__restr
 // the whole round come from one warp-level scan of the kDecodeE x 32 ballot counts (3 barriers per 4096 ranks).
 constexpr int kDecodeThreads = 1024;
 constexpr int kDecodeE = 4;
+// kNative: logits (N, A, HW) and deltas (N, 4A, HW) as the head wrote them -- the (N, HWA, 4) copy of reference
+// rpn.py:34-41 is replaced by four 4-byte gathers per selected anchor.
+template <bool kNative>
 __global__ void __launch_bounds__(kDecodeThreads) rpn_decode_compact_kernel(
     const unsigned long long *__restrict__ keys, int P, const float *__restrict__ logits,
-    const float4 *__restrict__ deltas, const float4 *__restrict__ anchors, CellAnchors cell, int HWA, int A, int Wf,
+    const float *__restrict__ deltas, const float4 *__restrict__ anchors, CellAnchors cell, int HWA, int A, int Wf, int HW,
     int stride, float anchor_offset, float wx, float wy, float ww, float wh, float scale_clamp, int topk,
     float min_box_size, const int *__restrict__ image_hw, float4 *__restrict__ sboxes, float *__restrict__ sscores,
     int *__restrict__ ssrc, nmsk::Seg *__restrict__ segs, int *__restrict__ invalid_count) {
@@ -59,8 +67,15 @@ __global__ void __launch_bounds__(kDecodeThreads) rpn_decode_compact_kernel(
       const int j = base + e * kDecodeThreads + tid;
       idx[e] = (int)(unsigned)(key[e] & 0xFFFFFFFFull);
       if (j >= topk) idx[e] = 0;
-      score[e] = logits[(size_t)n * HWA + idx[e]];
-      dl[e] = deltas[(size_t)n * HWA + idx[e]];
+      if (kNative) {
+        const int ai = idx[e] % A, cellpos = idx[e] / A;
+        score[e] = logits[(size_t)n * HWA + (size_t)ai * HW + cellpos];
+        const float *d = deltas + ((size_t)n * HWA + (size_t)ai * HW) * 4 + cellpos;
+        dl[e] = make_float4(d[0], d[HW], d[2 * (size_t)HW], d[3 * (size_t)HW]);
+      } else {
+        score[e] = logits[(size_t)n * HWA + idx[e]];
+        dl[e] = reinterpret_cast<const float4 *>(deltas)[(size_t)n * HWA + idx[e]];
+      }
       if (anchors) an[e] = anchors[idx[e]];
     }
     bool keep[kDecodeE]; float4 box[kDecodeE]; unsigned bal[kDecodeE];

@@ -225,8 +225,12 @@ class RPN(nn.Module):
     def select_proposals(self, pred_objectness_logits: List[Tensor], pred_anchor_deltas: List[Tensor], image_sizes,
                          feat_hw: Optional[List[Tuple[int, int]]] = None, anchors: Optional[List[Boxes]] = None):
         """Device-side result of ``predict_proposals`` without the host read of the counts:
-        (boxes (N, P, 4), logits (N, P), src_index (N, P), count (N) int32, invalid (N) int32)."""
+        (boxes (N, P, 4), logits (N, P), src_index (N, P), count (N) int32, invalid (N) int32).
+        The head outputs may be passed flattened (reference rpn.py:28-41) or as they lie ((N, A, H, W) / (N, 4A, H, W)): the
+        single-level kernel chain reads the latter directly, so the teacher's forward makes no permute copy."""
         if len(pred_objectness_logits) != 1:
+            if pred_objectness_logits[0].dim() == 4:
+                pred_objectness_logits, pred_anchor_deltas = self._flatten_head_outputs(pred_objectness_logits, pred_anchor_deltas)
             return self._select_proposals_multilevel(pred_objectness_logits, pred_anchor_deltas, image_sizes, feat_hw, anchors)
         ag = self.anchor_generator
         kw = {}
@@ -297,8 +301,8 @@ class RPN(nn.Module):
         anchors = self.anchor_generator(feats)
         pred_objectness_logits, pred_anchor_deltas = self.rpn_head(feats)
         feat_hw = [tuple(f.shape[-2:]) for f in feats]
-        pred_objectness_logits, pred_anchor_deltas = self._flatten_head_outputs(pred_objectness_logits, pred_anchor_deltas)
         if self.training:
+            pred_objectness_logits, pred_anchor_deltas = self._flatten_head_outputs(pred_objectness_logits, pred_anchor_deltas)
             gt_labels, gt_boxes = self.label_and_sample_anchors(anchors, gt_instances)
             losses = self.losses(anchors, pred_objectness_logits, gt_labels, pred_anchor_deltas, gt_boxes)
         else:
@@ -320,8 +324,8 @@ class PseudoLabRPN(RPN):
         anchors = self.anchor_generator(feats) if (need_loss or not self._closed_form_anchors()) else None
         pred_objectness_logits, pred_anchor_deltas = self.rpn_head(feats)
         feat_hw = [tuple(f.shape[-2:]) for f in feats]
-        pred_objectness_logits, pred_anchor_deltas = self._flatten_head_outputs(pred_objectness_logits, pred_anchor_deltas)
-        if need_loss:
+        if need_loss:   # the flattened copies of rpn.py:28-41 are made for the losses only; the selection reads the head outputs as they lie
+            pred_objectness_logits, pred_anchor_deltas = self._flatten_head_outputs(pred_objectness_logits, pred_anchor_deltas)
             gt_labels, gt_boxes = self.label_and_sample_anchors(anchors, gt_instances)
             losses = self.losses(anchors, pred_objectness_logits, gt_labels, pred_anchor_deltas, gt_boxes)
             losses = {k: v * self.loss_weight.get(k, 1.0) for k, v in losses.items()}
@@ -341,8 +345,8 @@ class DARPN(RPN):
         anchors = self.anchor_generator(feats)
         pred_objectness_logits, pred_anchor_deltas = self.rpn_head(feats)
         feat_hw = [tuple(f.shape[-2:]) for f in feats]
-        pred_objectness_logits, pred_anchor_deltas = self._flatten_head_outputs(pred_objectness_logits, pred_anchor_deltas)
         if self.training and gt_instances is not None:
+            pred_objectness_logits, pred_anchor_deltas = self._flatten_head_outputs(pred_objectness_logits, pred_anchor_deltas)
             gt_labels, gt_boxes = self.label_and_sample_anchors(anchors, gt_instances)
             losses = self.losses(anchors, pred_objectness_logits, gt_labels, pred_anchor_deltas, gt_boxes)
         else:

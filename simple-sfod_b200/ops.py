@@ -498,14 +498,25 @@ def rpn_select(logits: Tensor, deltas: Tensor, image_sizes: Sequence[Tuple[int, 
                cell_anchors: Optional[Tensor] = None, feat_hw: Optional[Tuple[int, int]] = None, stride: int = 0,
                anchor_offset: float = 0.0, weights: Sequence[float] = (1.0, 1.0, 1.0, 1.0), scale_clamp: float = SCALE_CLAMP,
                pre_nms_topk: int = 12000, post_nms_topk: int = 2000, nms_thresh: float = 0.7, min_box_size: float = 0.0):
-    """Single-level RPN.predict_proposals for all images: logits (N, HWA), deltas (N, HWA, 4).
+    """Single-level RPN.predict_proposals for all images: logits (N, HWA), deltas (N, HWA, 4) -- or the RPN head's outputs as they
+    lie, logits (N, A, Hf, Wf) and deltas (N, 4A, Hf, Wf): the flatten of reference rpn.py:28-41 is then folded into the kernels
+    (no permute copy); indices keep the flattened (Hf, Wf, A) numbering either way.
     Either ``anchors`` (HWA, 4) or (``cell_anchors`` (A, 4), ``feat_hw``, ``stride``) must be given.
     Returns (boxes (N, P, 4), logits (N, P), src_index (N, P) int64, count (N) int32, invalid (N) int32)."""
     dev = _require_cuda(logits, deltas, anchors)
     lg, dl = _f32c(logits), _f32c(deltas)
-    N, HWA = lg.shape
-    if dl.shape != (N, HWA, 4):
-        raise ValueError(f"deltas must be (N, HWA, 4) = {(N, HWA, 4)}, got {tuple(dl.shape)}")
+    native = lg.dim() == 4
+    if native:
+        N, A_head, Hh, Wh = lg.shape
+        HWA = A_head * Hh * Wh
+        if dl.shape != (N, 4 * A_head, Hh, Wh):
+            raise ValueError(f"deltas must be (N, 4A, Hf, Wf) = {(N, 4 * A_head, Hh, Wh)}, got {tuple(dl.shape)}")
+        if feat_hw is not None and (int(feat_hw[0]), int(feat_hw[1])) != (Hh, Wh):
+            raise ValueError("feat_hw does not match the head outputs")
+    else:
+        N, HWA = lg.shape
+        if dl.shape != (N, HWA, 4):
+            raise ValueError(f"deltas must be (N, HWA, 4) = {(N, HWA, 4)}, got {tuple(dl.shape)}")
     if len(image_sizes) != N:
         raise ValueError("one image size per image is required")
     p = RpnParams()
@@ -521,7 +532,7 @@ def rpn_select(logits: Tensor, deltas: Tensor, image_sizes: Sequence[Tuple[int, 
         anc = _f32c(anchors)
         if anc.shape != (HWA, 4):
             raise ValueError("anchors must be (HWA, 4)")
-        p.A, p.Hf, p.Wf = 0, 0, 0
+        p.A, p.Hf, p.Wf = (A_head, Hh, Wh) if native else (0, 0, 0)
     else:
         if cell_anchors is None or feat_hw is None or stride <= 0:
             raise ValueError("need anchors or (cell_anchors, feat_hw, stride)")
@@ -529,9 +540,12 @@ def rpn_select(logits: Tensor, deltas: Tensor, image_sizes: Sequence[Tuple[int, 
         A = len(ca) // 4
         if A > 64:
             raise ValueError("at most 64 cell anchors are supported in closed form; pass `anchors`")
+        if native and A != A_head:
+            raise ValueError(f"{A} cell anchors for head outputs with {A_head} anchors per cell")
         p.A, p.Hf, p.Wf = A, int(feat_hw[0]), int(feat_hw[1])
         for i, v in enumerate(ca):
             p.cell_anchors[i] = v
+    p.head_layout = 1 if native else 0
     P = int(post_nms_topk)
     L = _lib.lib()
     with torch.cuda.device(dev):

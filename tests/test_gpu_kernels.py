@@ -310,12 +310,21 @@ def test_apply_deltas_and_softmax_defined_arithmetic(ops, cuda_device):
 
 
 # ------------------------------------------------------------------------------------------------ RPN selection
-def _rpn_case(ops, dev, cfg, N, seed, pre, post, image_sizes, use_anchor_tensor=False, delta_std=0.5):
+def _head_layout(cfg, logits, deltas):
+    """Undo the flatten of reference rpn.py:28-41: (N, HWA) -> (N, A, H, W), (N, HWA, 4) -> (N, 4A, H, W) as the head writes them."""
+    N, H, W = logits.shape[0], cfg["H"], cfg["W"]
+    A = logits.shape[1] // (H * W)
+    return (logits.view(N, H, W, A).permute(0, 3, 1, 2).contiguous(),
+            deltas.view(N, H, W, A, 4).permute(0, 3, 4, 1, 2).reshape(N, 4 * A, H, W).contiguous())
+
+
+def _rpn_case(ops, dev, cfg, N, seed, pre, post, image_sizes, use_anchor_tensor=False, delta_std=0.5, native=False):
     logits, deltas, cell, anchors = synth.rpn_head_outputs(cfg, N, seed, delta_std)
     ref = o.rpn_predict_proposals([anchors], [logits], [deltas], image_sizes, 0.7, pre, post, 0.0, False,
                                   exp=o.exp_correctly_rounded)
     kw = dict(anchors=anchors.to(dev)) if use_anchor_tensor else dict(cell_anchors=cell, feat_hw=(cfg["H"], cfg["W"]), stride=cfg["stride"])
-    boxes, lg, src, cnt, invalid = ops.rpn_select(logits.to(dev), deltas.to(dev), image_sizes, pre_nms_topk=pre,
+    lg_in, dl_in = _head_layout(cfg, logits, deltas) if native else (logits, deltas)
+    boxes, lg, src, cnt, invalid = ops.rpn_select(lg_in.to(dev), dl_in.to(dev), image_sizes, pre_nms_topk=pre,
                                                   post_nms_topk=post, nms_thresh=0.7, **kw)
     cnt = cnt.cpu().tolist()
     assert invalid.cpu().tolist() == [0] * N
@@ -342,6 +351,26 @@ def test_rpn_select_explicit_anchor_tensor(ops, cuda_device):
 
 def test_rpn_select_r101_topk_12000_of_34200(ops, cuda_device):
     _rpn_case(ops, cuda_device, synth.R101, 1, 1237, 12000, 2000, [(600, 1200)])
+
+
+@pytest.mark.parametrize("cfg_name,use_anchor_tensor", [("V", False), ("V", True), ("R101", False)])
+def test_rpn_select_reads_the_head_outputs_as_they_lie(ops, cuda_device, cfg_name, use_anchor_tensor):
+    """head_layout 1: (N, A, H, W) logits / (N, 4A, H, W) deltas straight from the RPN head's convolutions -- the permute
+    copies of reference rpn.py:28-41 are folded into the key build and the top-k gather.  Same oracle, same bits; ragged
+    image sizes; non-finite entries are counted at the same flattened positions."""
+    cfg = getattr(synth, cfg_name)
+    _rpn_case(ops, cuda_device, cfg, 3, 1241, 12000, 2000, [(600, 1200), (576, 1100), (300, 400)],
+              use_anchor_tensor=use_anchor_tensor, native=True)
+    logits, deltas, cell, anchors = synth.rpn_head_outputs(cfg, 1, 78)
+    deltas[0, 5, 0] = float("inf"); logits[0, 9] = float("nan")
+    kw = dict(cell_anchors=cell, feat_hw=(cfg["H"], cfg["W"]), stride=cfg["stride"], pre_nms_topk=12000, post_nms_topk=2000)
+    flat = ops.rpn_select(logits.to(cuda_device), deltas.to(cuda_device), [(600, 1200)], **kw)
+    lg4, dl4 = _head_layout(cfg, logits, deltas)
+    nat = ops.rpn_select(lg4.to(cuda_device), dl4.to(cuda_device), [(600, 1200)], **kw)
+    for a, b in zip(flat, nat):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        ops.rpn_select(lg4.to(cuda_device), dl4[:, :-4].contiguous().to(cuda_device), [(600, 1200)], **kw)
 
 
 def test_rpn_select_high_suppression_and_reference_exp(ops, cuda_device):
