@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--workload", default="vgg", choices=sorted(WORKLOADS),
                     help="vgg = BASELINE configs[2] (headline, the driver's default); r101 = configs[4] (ResNet-101-C4 teacher)")
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step (configs[2]: 8)")
+    ap.add_argument("--num-classes", type=int, default=8,
+                    help="foreground classes K of the ROI heads (8 = Cityscapes, every shipped YAML; 1 = the 'Sim10k-shaped 1-class "
+                         "variant' BASELINE.json names with configs[4] -- a benchmark variant, SURVEY.md section 8(d))")
     ap.add_argument("--extras", type=int, default=1,
                     help="1 = after the headline measurement also report: the named kernels' rooflines (NMS / ROIAlign / EMA at the bench "
                          "and the N=1 config-[1] shapes), the PyTorch-default (TF32) library-math record, the AdaBN step with its "
@@ -126,7 +129,14 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
 def build_cfg(workload: str):
     from sfod_b200 import config
-    return config.vgg_source_free_cfg() if workload == "vgg" else config.r101_c4_source_free_cfg()
+    cfg = config.vgg_source_free_cfg() if workload == "vgg" else config.r101_c4_source_free_cfg()
+    cfg.MODEL.ROI_HEADS.NUM_CLASSES = NUM_CLASSES
+    return cfg
+
+
+def workload_name(workload: str) -> str:
+    name = WORKLOADS[workload]
+    return name if NUM_CLASSES == 8 else name.replace("8 classes", f"{NUM_CLASSES} class(es) (--num-classes; benchmark variant)")
 
 
 def cpu_reference_run(steps: int, warmup: int, budget_s: float, seed: int = 1234, images_per_step: int = 8, with_ema: bool = True,
@@ -188,7 +198,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": info["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": k_run,
             "warmup": w_done, "ms_per_step": round(1e3 * dt / k_run, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "images_per_gpu": args.batch, "images_per_step": args.batch,
+            "config": {"workload": workload_name(args.workload), "images_per_gpu": args.batch, "images_per_step": args.batch,
                        "global_batch": args.batch, "image_hw": list(IMAGE_HW), "num_classes": NUM_CLASSES,
                        "note": "CPU arm runs on rank 0 only, all host cores; same batch per step as the GPU arm, bounded number of steps"},
             "cpu_baseline": info,
@@ -608,7 +618,9 @@ def run_b200(args):
 
     # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture of this same command
     traffic_map = {"bn_finalize_apply": "bn_apply_nchw_kernel", "bn_finalize_apply_pool": "bn_apply_pool_nchw_kernel",
-                   "bn_partial_stats": "bn_stats_nchw_kernel", "roi_align_fwd": "roi_align_fwd_slab_kernel",
+                   "bn_partial_stats": "bn_stats_nchw_kernel",
+                   # VGG 18 x 37: slab-resident kernel; R101-C4 38 x 75 does not fit a slab: transpose + per-ROI L2 kernel
+                   "roi_align_fwd": "roi_align_fwd_slab_kernel" if args.workload == "vgg" else "roi_align_fwd_sep_kernel (+ nchw_to_nhwc transpose, roi_sep_tables)",
                    "ema_multi_tensor": "ema_multi_tensor_kernel"}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
@@ -645,7 +657,7 @@ def run_b200(args):
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "images_per_gpu": B, "images_per_step": B, "global_batch": B * world,
+            "config": {"workload": workload_name(args.workload), "images_per_gpu": B, "images_per_step": B, "global_batch": B * world,
                        "image_hw": list(IMAGE_HW),
                        "num_classes": NUM_CLASSES, "parallelism": f"dp{world} (images sharded per GPU, replicated teacher, no data-path collective "
                                                                   "in the headline step; the AdaBN step of configs[3] with its statistic all-reduce and the "
@@ -856,8 +868,11 @@ def emit(line: dict) -> None:
 
 
 def main():
-    global _REAL_STDOUT
+    global _REAL_STDOUT, NUM_CLASSES
     args = parse_args()
+    if args.num_classes < 1:
+        raise SystemExit("--num-classes must be >= 1")
+    NUM_CLASSES = args.num_classes
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)          # fd 1 -> stderr for the rest of the run
