@@ -373,6 +373,16 @@ def test_rpn_select_reads_the_head_outputs_as_they_lie(ops, cuda_device, cfg_nam
         ops.rpn_select(lg4.to(cuda_device), dl4[:, :-4].contiguous().to(cuda_device), [(600, 1200)], **kw)
 
 
+@pytest.mark.parametrize("H,W,sizes,ratios", [(1, 1, (64,), (1.0,)), (2, 3, (32, 64), (0.5, 1.0, 2.0)), (1, 40, (32,), (0.5, 2.0))])
+@pytest.mark.parametrize("native", [False, True])
+def test_rpn_select_tiny_maps_both_head_layouts(ops, cuda_device, H, W, sizes, ratios, native):
+    """Degenerate feature maps (a single cell with a single anchor, fewer anchors than post_nms_topk, one row): the sort tile is
+    mostly padding and every count is below the caps -- both head layouts equal the oracle bit for bit."""
+    cfg = dict(name="tiny", C=8, H=H, W=W, stride=32, sizes=sizes, ratios=ratios, image=(32 * H, 32 * W))
+    _rpn_case(ops, cuda_device, cfg, 2, 1300 + H * W, 12000, 2000, [(32 * H, 32 * W), (max(16, 32 * H - 7), max(16, 32 * W - 5))],
+              native=native)
+
+
 def test_rpn_select_high_suppression_and_reference_exp(ops, cuda_device):
     """Tiny deltas -> anchors at the same cell overlap heavily -> few survivors (count < post_nms_topk).
     Also compares with the reference-faithful oracle (ATen exp): boxes within 1e-5, keep sets reported."""
