@@ -504,6 +504,16 @@ def rpn_select(logits: Tensor, deltas: Tensor, image_sizes: Sequence[Tuple[int, 
     Either ``anchors`` (HWA, 4) or (``cell_anchors`` (A, 4), ``feat_hw``, ``stride``) must be given.
     Returns (boxes (N, P, 4), logits (N, P), src_index (N, P) int64, count (N) int32, invalid (N) int32)."""
     dev = _require_cuda(logits, deltas, anchors)
+    if (logits.dim() == 4 and deltas.dim() == 4 and not logits.is_contiguous() and not deltas.is_contiguous()
+            and logits.is_contiguous(memory_format=torch.channels_last) and deltas.is_contiguous(memory_format=torch.channels_last)
+            and deltas.shape[1] == 4 * logits.shape[1]):
+        # channels-last head outputs (NHWC backbone): the reference's flatten is a free VIEW of this memory, (N, H, W, A) and
+        # (N, H, W, A, 4) -- take it instead of an NCHW copy
+        if feat_hw is None:
+            feat_hw = (int(logits.shape[2]), int(logits.shape[3]))
+        n_img = logits.shape[0]
+        logits = logits.permute(0, 2, 3, 1).reshape(n_img, -1)
+        deltas = deltas.permute(0, 2, 3, 1).reshape(n_img, -1, 4)
     lg, dl = _f32c(logits), _f32c(deltas)
     native = lg.dim() == 4
     if native:

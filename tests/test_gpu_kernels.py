@@ -371,6 +371,12 @@ def test_rpn_select_reads_the_head_outputs_as_they_lie(ops, cuda_device, cfg_nam
         assert torch.equal(a, b)
     with pytest.raises(ValueError):
         ops.rpn_select(lg4.to(cuda_device), dl4[:, :-4].contiguous().to(cuda_device), [(600, 1200)], **kw)
+    # channels-last head outputs (NHWC backbone): the flatten is a free view of that memory; same results, no copy of the inputs
+    lg_cl = lg4.to(cuda_device).contiguous(memory_format=torch.channels_last)
+    dl_cl = dl4.to(cuda_device).contiguous(memory_format=torch.channels_last)
+    cl = ops.rpn_select(lg_cl, dl_cl, [(600, 1200)], **kw)
+    for a, b in zip(flat, cl):
+        assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("H,W,sizes,ratios", [(1, 1, (64,), (1.0,)), (2, 3, (32, 64), (0.5, 1.0, 2.0)), (1, 40, (32,), (0.5, 2.0))])
