@@ -744,24 +744,30 @@ __device__ __forceinline__ void slab_rows_compact_pk(const float *__restrict__ S
   }
   const int y0 = lim[0], y1 = lim[1];
   const unsigned rstride = (unsigned)W * (kPS * 4);
-  for (int y = y0; y <= y1; ++y) {
-    const float4 a0 = *reinterpret_cast<const float4 *>(Ad + y * 8), a1 = *reinterpret_cast<const float4 *>(Ad + y * 8 + 4);
+  // running addresses (row weights, the seven column windows): nothing in a row waits for an index multiplication
+  const float *ad = Ad + y0 * 8;
+#pragma unroll
+  for (int b = 0; b < kPW; ++b) pb[b] += (unsigned)y0 * rstride;
+  for (int y = y0; y <= y1; ++y, ad += 8) {
+    const float4 a0 = *reinterpret_cast<const float4 *>(ad), a1 = *reinterpret_cast<const float4 *>(ad + 4);
     const float av[kPH] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z};
     const int info = __float_as_int(a1.w);
+    unsigned pr[kPW];
+#pragma unroll
+    for (int b = 0; b < kPW; ++b) { pr[b] = pb[b]; pb[b] += rstride; }
     if (info == 0) continue;   // no bin uses this row
-    const unsigned ro = (unsigned)y * rstride;
     float2 Tp[3];
     float Ts;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const unsigned p0 = pb[2 * i] + ro, p1 = pb[2 * i + 1] + ro;
+      const unsigned p0 = pr[2 * i], p1 = pr[2 * i + 1];
       Tp[i] = __fmul2_rn(bwp[i][0], make_float2(slab_lds<0>(p0), slab_lds<0>(p1)));
       if (NX > 1) Tp[i] = __ffma2_rn(bwp[i][1 % NX], make_float2(slab_lds<kPS * 4>(p0), slab_lds<kPS * 4>(p1)), Tp[i]);
       if (NX > 2) Tp[i] = __ffma2_rn(bwp[i][2 % NX], make_float2(slab_lds<2 * kPS * 4>(p0), slab_lds<2 * kPS * 4>(p1)), Tp[i]);
       if (NX > 3) Tp[i] = __ffma2_rn(bwp[i][3 % NX], make_float2(slab_lds<3 * kPS * 4>(p0), slab_lds<3 * kPS * 4>(p1)), Tp[i]);
     }
     {
-      const unsigned p = pb[6] + ro;
+      const unsigned p = pr[6];
       Ts = bws[0] * slab_lds<0>(p);
       if (NX > 1) Ts = fmaf(bws[1 % NX], slab_lds<kPS * 4>(p), Ts);
       if (NX > 2) Ts = fmaf(bws[2 % NX], slab_lds<2 * kPS * 4>(p), Ts);
