@@ -26,6 +26,7 @@ from . import ops, structures
 from .engine import export as _export
 from .engine import hooks as _hooks
 from .modeling import box_regression, fast_rcnn, matcher, poolers, proposal_generator, roi_heads
+from .modeling import resnet as _resnet
 from .registry import Registry
 from .structures import ShapeSpec
 from .utils import events
@@ -248,7 +249,9 @@ def install(force: bool = False) -> bool:
         "detectron2.structures": _mod("detectron2.structures", Boxes=structures.Boxes, Instances=structures.Instances,
                                       ImageList=structures.ImageList, pairwise_iou=structures.pairwise_iou),
         "detectron2.layers": _mod("detectron2.layers", ShapeSpec=ShapeSpec, batched_nms=ops.batched_nms, cat=cat,
-                                  cross_entropy=matcher.cross_entropy, nonzero_tuple=matcher.nonzero_tuple),
+                                  cross_entropy=matcher.cross_entropy, nonzero_tuple=matcher.nonzero_tuple,
+                                  # reference daod/modeling/roi_heads/box_head.py:9, daod/engine/trainers/base.py:22
+                                  Conv2d=_resnet.Conv2d, get_norm=_resnet.get_norm, FrozenBatchNorm2d=_resnet.FrozenBatchNorm2d),
         "detectron2.utils": _mod("detectron2.utils", __path__=[]),
         "detectron2.utils.events": _mod("detectron2.utils.events", EventStorage=events.EventStorage, get_event_storage=events.get_event_storage),
         "detectron2.utils.comm": _mod("detectron2.utils.comm", get_world_size=get_world_size, get_rank=get_rank, is_main_process=is_main_process,

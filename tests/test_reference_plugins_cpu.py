@@ -55,6 +55,10 @@ def test_reference_plugin_sources_import_and_register(ref):
     assert mods["rpn"].PseudoLabRPN.__module__ == "refdaod_pg.rpn" and issubclass(mods["rpn"].PseudoLabRPN, modeling.RPN)
     assert issubclass(mods["fast"].SourceFreeFastRCNNOutputLayers, modeling.FastRCNNOutputLayers)
     assert mods["heads"].__file__.startswith("/root/reference/")
+    # the rest of the detectron2.layers census of SURVEY.md 8(b) (reference box_head.py:9, trainers/base.py:22)
+    from detectron2.layers import Conv2d, FrozenBatchNorm2d, get_norm
+    assert isinstance(get_norm("BN", 8), torch.nn.BatchNorm2d) and isinstance(get_norm("FrozenBN", 8), FrozenBatchNorm2d)
+    assert get_norm("", 8) is None and issubclass(Conv2d, torch.nn.Conv2d)
 
 
 def test_reference_plugins_build_from_cfg_and_reach_the_kernel_boundary(ref):
