@@ -44,7 +44,7 @@ def test_host_only_entry_points():
     assert L.sfod_abi_version() == 1
     assert L.sfod_status_string(0) == b"ok" and L.sfod_status_string(2) == b"workspace too small"
     assert L.sfod_nms_workspace_bytes(0) == 256 and L.sfod_nms_workspace_bytes(9990) > 9990 * 157 * 8
-    rec = (96 + 8 * 18) * 4                                                                            # per-ROI table record
+    rec = (128 + 8 * 18) * 4                                                                           # per-ROI table record (kRecHead + 8 H floats)
     assert L.sfod_roi_align_fwd_workspace_bytes(8, 512, 18, 37, 16000, 0, 0) >= 8 * 512 * 18 * 37 * 4 + 16000 * rec   # NCHW in -> NHWC copy + records
     cls = 16000 * 16 * 4                                                                               # cost-class lists of the L2 forward
     assert 16000 * rec <= L.sfod_roi_align_fwd_workspace_bytes(8, 512, 18, 37, 16000, 1, 0) <= 16000 * rec + cls + 1024
