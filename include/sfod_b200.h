@@ -47,6 +47,10 @@ enum sfod_layout { SFOD_NCHW = 0, SFOD_NHWC = 1 };
 enum sfod_dtype { SFOD_F32 = 0, SFOD_I64 = 1, SFOD_U8 = 2 };
 
 int sfod_abi_version(void);
+/* sizeof() of the parameter structs as this library was compiled (which: 0 sfod_ema_tensor, 1 sfod_rpn_params,
+ * 2 sfod_frcnn_params, 3 sfod_p2p_comm, 4 sfod_jitter_params, 5 sfod_erase_params; 0 for anything else) -- lets a foreign
+ * binding (ctypes / cffi struct mirrors) check its layout against the C one before the first call. */
+size_t sfod_abi_sizeof(int which);
 const char *sfod_status_string(int status);
 /* Number of kernel launches the library has issued in this process so far (diagnostic, monotonically
  * increasing; bench.py reports the difference across its timed region as "gpu_launches"). */

@@ -57,6 +57,7 @@ class P2PComm(C.Structure):
 # name -> (restype, argtypes); every symbol include/sfod_b200.h declares
 SIGNATURES = {
     "sfod_abi_version": (C.c_int, []),
+    "sfod_abi_sizeof": (C.c_size_t, [C.c_int]),
     "sfod_status_string": (C.c_char_p, [C.c_int]),
     "sfod_debug_launch_count": (C.c_uint64, []),
     "sfod_ema_plan_chunks": (C.c_int64, [C.POINTER(EmaTensor), C.c_int]),

@@ -417,6 +417,18 @@ SFOD_API int sfod_class_histogram(const float *values, const int64_t *classes, c
 
 SFOD_API int sfod_abi_version(void) { return 1; }
 
+SFOD_API size_t sfod_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(sfod_ema_tensor);
+    case 1: return sizeof(sfod_rpn_params);
+    case 2: return sizeof(sfod_frcnn_params);
+    case 3: return sizeof(sfod_p2p_comm);
+    case 4: return sizeof(sfod_jitter_params);
+    case 5: return sizeof(sfod_erase_params);
+    default: return 0;
+  }
+}
+
 SFOD_API const char *sfod_status_string(int status) {
   switch (status) {
     case SFOD_OK: return "ok";

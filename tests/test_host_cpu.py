@@ -42,6 +42,10 @@ def test_library_exports_every_declared_symbol():
 def test_host_only_entry_points():
     L = _lib.lib()
     assert L.sfod_abi_version() == 1
+    # the ctypes mirrors of the parameter structs have the C layout (sizeof as compiled into the library)
+    for which, mirror in enumerate((_lib.EmaTensor, _lib.RpnParams, _lib.FrcnnParams, _lib.P2PComm, _lib.JitterParams, _lib.EraseParams)):
+        assert L.sfod_abi_sizeof(which) == C.sizeof(mirror), (which, mirror.__name__, L.sfod_abi_sizeof(which), C.sizeof(mirror))
+    assert L.sfod_abi_sizeof(99) == 0
     assert L.sfod_status_string(0) == b"ok" and L.sfod_status_string(2) == b"workspace too small"
     assert L.sfod_nms_workspace_bytes(0) == 256 and L.sfod_nms_workspace_bytes(9990) > 9990 * 157 * 8
     rec = (128 + 8 * 18) * 4                                                                           # per-ROI table record (kRecHead + 8 H floats)
