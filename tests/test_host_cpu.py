@@ -364,3 +364,33 @@ def test_box_decode_and_probs_are_differentiable_when_a_gradient_is_requested():
     assert out.requires_grad and torch.equal(out.detach(), o.apply_deltas(deltas.detach(), boxes, (10.0, 10.0, 5.0, 5.0)))
     out.sum().backward()
     assert deltas.grad is not None and torch.isfinite(deltas.grad).all() and deltas.grad.abs().sum() > 0
+
+
+def test_head_layout_helper_inverts_the_reference_flatten():
+    """The GPU tests of ``head_layout = 1`` build (N, A, H, W) / (N, 4A, H, W) inputs from flattened ones with
+    ``test_gpu_kernels._head_layout``; that helper must be the exact inverse of the flatten of reference rpn.py:28-41
+    (``RPN._flatten_head_outputs`` here, checked against the reference's own text in test_reference_plugins_cpu), so that the
+    native-layout tests exercise the index mapping real head outputs have."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("_gpu_kernel_tests", os.path.join(ROOT, "tests", "test_gpu_kernels.py"))
+    tk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tk)
+    from sfod_b200.modeling.proposal_generator import RPN
+    g = torch.Generator().manual_seed(5)
+    N, A, H, W = 2, 3, 4, 5
+    logits4 = torch.randn(N, A, H, W, generator=g)
+    deltas4 = torch.randn(N, 4 * A, H, W, generator=g)
+
+    class _AG:
+        box_dim = 4
+    stub = types.SimpleNamespace(anchor_generator=_AG())
+    flat_l, flat_d = RPN._flatten_head_outputs(stub, [logits4], [deltas4])
+    assert flat_l[0].shape == (N, H * W * A) and flat_d[0].shape == (N, H * W * A, 4)
+    # flattened index i = (h * W + w) * A + a  <->  logits4[n, a, h, w]; deltas4[n, 4a + k, h, w]
+    n, a, h, w, k = 1, 2, 3, 4, 1
+    i = (h * W + w) * A + a
+    assert flat_l[0][n, i] == logits4[n, a, h, w] and flat_d[0][n, i, k] == deltas4[n, 4 * a + k, h, w]
+    back_l, back_d = tk._head_layout(dict(H=H, W=W), flat_l[0], flat_d[0])
+    assert torch.equal(back_l, logits4) and torch.equal(back_d, deltas4)
+
