@@ -3,6 +3,7 @@ FastRCNNOutputLayers.inference, threshold_bbox / process_pseudo_label, _update_t
 They read like the reference's call sites: the plugin objects are built from the VGG source-free config and called
 with the reference's argument lists."""
 import copy
+import os
 
 import pytest
 import torch
@@ -717,3 +718,17 @@ def test_multilevel_rpn_selection_matches_oracle(cuda_device):
                                                [Boxes(a.to(cuda_device)) for a in anchors])
     for n in range(N):
         assert torch.equal(src[n, :int(cnt[n])].cpu(), ref[n]["src_index"]) and int(inv[n]) == 0
+
+
+@pytest.mark.gpu
+def test_integration_md_snippets_run_against_the_library(cuda_device):
+    """The ctypes stubs INTEGRATION.md shows a maintainer (nms; sfod_rpn_select with a parameter struct and the head outputs
+    as they lie) are executed verbatim and must equal ``sfod_b200.ops``."""
+    import runpy
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cwd = os.getcwd()
+    try:
+        runpy.run_path(os.path.join(root, "tools", "integration_snippet_check.py"), run_name="__main__")
+    finally:
+        os.chdir(cwd)
+
